@@ -1,0 +1,103 @@
+"""Generate tests/golden/*.npz from the reference's OWN module code.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+
+* cot_layer_d32.npz / coxt_layer_d48.npz / cothybrid_layer_d32.npz : the reference's unmodified
+  ``CotLayer`` / ``CoXtLayer`` / ``CoTLayer`` (imported through ``oracle/ref_import.py``) run in
+  fp64 on CPU with seeded, perturbed parameters: eval output, train output, d(out)/dx and
+  d(out)/d(param) for a seeded cotangent, and the BN running buffers after the train step.
+* agg_selftest_*.npz : the right-hand sides of the reference self-tests
+  (aggregation_zeropad.py:238-292, aggregation_zeropad_mix.py:344-383) at their exact shapes,
+  evaluated with torch's Unfold -- the reference stores no vectors, this identity is its only pin.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import agg_ref, cot_ref, ref_import  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _layer_fixture(cls, kind, dim, B, H, W, seed, fname):
+    gen = torch.Generator().manual_seed(seed)
+    sd = cot_ref.init_state_dict(kind, dim, gen, dtype=torch.float64, perturb=True)
+    x = torch.relu(torch.randn(B, dim, H, W, generator=gen, dtype=torch.float64))
+    cot = torch.randn(B, dim, H, W, generator=gen, dtype=torch.float64)
+
+    m = cls(dim, 3).double()
+    missing = m.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    rec = {"x": x.numpy(), "cotangent": cot.numpy()}
+    for k_, v_ in sd.items():
+        rec["param/" + k_] = v_.numpy()
+
+    m.eval()
+    with torch.no_grad():
+        rec["out_eval"] = m(x).numpy()
+
+    m.train()
+    xg = x.clone().requires_grad_(True)
+    out = m(xg)
+    rec["out_train"] = out.detach().numpy()
+    (out * cot).sum().backward()
+    rec["grad/x"] = xg.grad.numpy()
+    for n_, p_ in m.named_parameters():
+        rec["grad/" + n_] = p_.grad.numpy()
+    for n_, b_ in m.named_buffers():
+        rec["buf_after/" + n_] = b_.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, fname), **rec)
+    print("wrote", fname, {k: v.shape for k, v in rec.items() if not k.startswith(("param/", "grad/", "buf_after/"))})
+
+
+def _agg_fixture(fname, k, heads, n, cx, cw, H, W, seed):
+    gen = torch.Generator().manual_seed(seed)
+    p = (k - 1 + 1) // 2
+    x = torch.randn(n, cx, H, W, generator=gen, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(n, heads, cw, k * k, H, W, generator=gen, dtype=torch.float64, requires_grad=True)
+    cot = torch.randn(n, heads * cx, H, W, generator=gen, dtype=torch.float64)
+    y = agg_ref.agg_zeropad_unfold(x, w, k, 1, p, 1)
+    gx, gw = torch.autograd.grad((y * cot).sum(), (x, w))
+    np.savez_compressed(os.path.join(OUT, fname), x=x.detach().numpy(), w=w.detach().numpy(), cot=cot.numpy(),
+                        y=y.detach().numpy(), gx=gx.numpy(), gw=gw.numpy(),
+                        meta=np.array([k, 1, p, 1, heads]))
+    print("wrote", fname)
+
+
+def _mix_fixture(fname, seed):
+    gen = torch.Generator().manual_seed(seed)
+    n, cx, cw, H, W = 2, 8, 4, 6, 6
+    x = torch.randn(n, cx, H, W, generator=gen, dtype=torch.float64, requires_grad=True)
+    w1 = torch.randn(n, 1, cw, 9, H, W, generator=gen, dtype=torch.float64, requires_grad=True)
+    w2 = torch.randn(n, 1, cw, 25, H, W, generator=gen, dtype=torch.float64, requires_grad=True)
+    cot = torch.randn(n, 2 * cx, H, W, generator=gen, dtype=torch.float64)
+    y = agg_ref.agg_zeropad_mix_unfold(x, w1, w2, 3, 5, 1, 1, 2, 1)
+    gx, g1, g2 = torch.autograd.grad((y * cot).sum(), (x, w1, w2))
+    np.savez_compressed(os.path.join(OUT, fname), x=x.detach().numpy(), w1=w1.detach().numpy(),
+                        w2=w2.detach().numpy(), cot=cot.numpy(), y=y.detach().numpy(),
+                        gx=gx.numpy(), gw1=g1.numpy(), gw2=g2.numpy())
+    print("wrote", fname)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_import.load()
+    torch.set_num_threads(4)
+    _layer_fixture(ref.CotLayer, "cot", 32, 2, 6, 5, 101, "cot_layer_d32.npz")
+    _layer_fixture(ref.CoXtLayer, "coxt", 48, 2, 5, 6, 202, "coxt_layer_d48.npz")
+    _layer_fixture(ref.CoTLayer, "cot", 32, 3, 4, 4, 303, "cothybrid_layer_d32.npz")
+    # reference self-test shapes: aggregation_zeropad.py:238-246 and :266-274, mix :344-353
+    _agg_fixture("agg_selftest_k5.npz", 5, 2, 2, 8, 4, 9, 9, 11)
+    _agg_fixture("agg_selftest_k1.npz", 1, 2, 2, 8, 4, 9, 9, 12)
+    _agg_fixture("agg_cot_k3.npz", 3, 1, 2, 16, 2, 7, 6, 13)
+    _mix_fixture("agg_mix_selftest.npz", 14)
+
+
+if __name__ == "__main__":
+    main()

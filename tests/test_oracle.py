@@ -1,0 +1,101 @@
+"""Pin the CPU oracle (oracle/) against the golden vectors made from the reference's own module code
+and against the identities the reference's self-tests assert."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import agg_ref, cot_ref, ref_import
+
+TOL = 1e-9  # the reference self-tests' gate (aggregation_zeropad.py:252-260)
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.mark.parametrize("name", ["agg_selftest_k5.npz", "agg_selftest_k1.npz", "agg_cot_k3.npz"])
+def test_loops_match_unfold_golden(golden_dir, name):
+    g = _load(golden_dir, name)
+    k, s, p, d, heads = [int(v) for v in g["meta"]]
+    y = agg_ref.agg_zeropad_fwd_loops(g["x"], g["w"], k, s, p, d)
+    assert np.abs(y - g["y"]).max() < TOL
+    dx, dw = agg_ref.agg_zeropad_bwd_loops(g["cot"], g["x"], g["w"], k, s, p, d)
+    assert np.abs(dx - g["gx"]).max() < TOL
+    assert np.abs(dw - g["gw"]).max() < TOL
+
+
+def test_mix_loops_match_unfold_golden(golden_dir):
+    g = _load(golden_dir, "agg_mix_selftest.npz")
+    y = agg_ref.agg_zeropad_mix_fwd_loops(g["x"], g["w1"], g["w2"], 3, 5, 1, 1, 2, 1)
+    assert np.abs(y - g["y"]).max() < TOL
+    dx, d1, d2 = agg_ref.agg_zeropad_mix_bwd_loops(g["cot"], g["x"], g["w1"], g["w2"], 3, 5, 1, 1, 2, 1)
+    assert np.abs(dx - g["gx"]).max() < TOL
+    assert np.abs(d1 - g["gw1"]).max() < TOL
+    assert np.abs(d2 - g["gw2"]).max() < TOL
+
+
+@pytest.mark.parametrize("k,s,p,d,heads", [(3, 2, 1, 1, 1), (3, 1, 2, 2, 2), (5, 2, 2, 1, 1), (7, 1, 3, 1, 1)])
+def test_loops_vs_unfold_strided_dilated(k, s, p, d, heads):
+    gen = torch.Generator().manual_seed(5)
+    N, C, wc, H, W = 2, 6, 3, 9, 8
+    Ho, Wo = agg_ref.out_size(H, W, k, s, p, d)
+    x = torch.randn(N, C, H, W, generator=gen, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(N, heads, wc, k * k, Ho, Wo, generator=gen, dtype=torch.float64, requires_grad=True)
+    cot = torch.randn(N, heads * C, Ho, Wo, generator=gen, dtype=torch.float64)
+    y = agg_ref.agg_zeropad_unfold(x, w, k, s, p, d)
+    gx, gw = torch.autograd.grad((y * cot).sum(), (x, w))
+    y2 = agg_ref.agg_zeropad_fwd_loops(x.detach().numpy(), w.detach().numpy(), k, s, p, d)
+    dx2, dw2 = agg_ref.agg_zeropad_bwd_loops(cot.numpy(), x.detach().numpy(), w.detach().numpy(), k, s, p, d)
+    assert np.abs(y2 - y.detach().numpy()).max() < TOL
+    assert np.abs(dx2 - gx.numpy()).max() < TOL
+    assert np.abs(dw2 - gw.numpy()).max() < TOL
+
+
+def _run_layer(fn, g, training):
+    sd = {k[len("param/"):]: torch.from_numpy(g[k]).clone() for k in g.files if k.startswith("param/")}
+    x = torch.from_numpy(g["x"]).clone().requires_grad_(training)
+    for k, v in sd.items():
+        if v.dtype.is_floating_point and "running" not in k:
+            v.requires_grad_(training)
+    out = fn(x, sd, training=training)
+    return x, sd, out
+
+
+@pytest.mark.parametrize("name,fn", [("cot_layer_d32.npz", cot_ref.cot_layer),
+                                     ("cothybrid_layer_d32.npz", cot_ref.cot_layer),
+                                     ("coxt_layer_d48.npz", cot_ref.coxt_layer)])
+def test_block_restatement_matches_reference_golden(golden_dir, name, fn):
+    g = _load(golden_dir, name)
+    _, _, out = _run_layer(fn, g, False)
+    assert (out - torch.from_numpy(g["out_eval"])).abs().max() < 1e-11
+    x, sd, out = _run_layer(fn, g, True)
+    assert (out.detach() - torch.from_numpy(g["out_train"])).abs().max() < 1e-11
+    (out * torch.from_numpy(g["cotangent"])).sum().backward()
+    assert (x.grad - torch.from_numpy(g["grad/x"])).abs().max() < 1e-10
+    for k in g.files:
+        if k.startswith("grad/") and k != "grad/x":
+            ref = torch.from_numpy(g[k])
+            got = sd[k[len("grad/"):]].grad
+            assert (got - ref).abs().max() < 1e-10 * max(1.0, ref.abs().max().item()), k
+        if k.startswith("buf_after/"):
+            ref = torch.from_numpy(g[k])
+            got = sd[k[len("buf_after/"):]]
+            assert (got.double() - ref.double()).abs().max() < 1e-12, k
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_restatement_vs_live_reference_module():
+    """Same check against the live reference module (build container only) at another size."""
+    ref = ref_import.load()
+    gen = torch.Generator().manual_seed(77)
+    sd = cot_ref.init_state_dict("cot", 64, gen)
+    x = torch.relu(torch.randn(2, 64, 7, 7, generator=gen, dtype=torch.float64))
+    m = ref.CotLayer(64, 3).double()
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    with torch.no_grad():
+        want = m(x)
+    got = cot_ref.cot_layer(x, {k: v.clone() for k, v in sd.items()}, training=False)
+    assert (got - want).abs().max() < 1e-11
