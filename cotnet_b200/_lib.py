@@ -1,0 +1,122 @@
+"""ctypes binding of libcotb200.so (the C ABI in include/cotb200.h).
+
+PyTorch is only plumbing here: it owns device memory and streams; every kernel is reached through the
+plain-C entry points with raw device pointers.  There is NO CPU or eager fallback: if the library
+cannot be loaded the import of any op raises, loudly.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libcotb200.so")
+
+F32, F64, BF16, F16 = 0, 1, 2, 3
+NCHW, NHWC, NHWC_TAP = 0, 1, 2
+
+_DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16, torch.float16: F16}
+
+
+class AggDesc(ctypes.Structure):
+    """struct cotb200_agg_desc (include/cotb200.h)."""
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "n", "c", "h", "w", "heads", "wc", "kh", "kw", "sh", "sw", "ph", "pw", "dh", "dw", "ho", "wo",
+        "dtype", "layout", "gc", "fold")] + [(n, ctypes.c_longlong) for n in (
+            "x_sn", "x_sp", "w_sn", "w_sp", "y_sn", "y_sp")]
+
+
+_lock = threading.Lock()
+_lib = None
+
+_VP = ctypes.c_void_p
+_DP = ctypes.POINTER(AggDesc)
+
+# name -> (restype, argtypes); every symbol declared in include/cotb200.h must be listed here
+SYMBOLS = {
+    "cotb200_version": (ctypes.c_int, []),
+    "cotb200_last_error": (ctypes.c_char_p, []),
+    "cotb200_launch_count": (ctypes.c_longlong, []),
+    "cotb200_prof_enable": (None, [ctypes.c_int]),
+    "cotb200_prof_report": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
+    "cotb200_agg_zeropad_fwd": (ctypes.c_int, [_DP, _VP, _VP, _VP, _VP]),
+    "cotb200_agg_zeropad_bwd": (ctypes.c_int, [_DP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "cotb200_agg_zeropad_mix_fwd": (ctypes.c_int, [_DP] + [ctypes.c_int] * 4 + [_VP] * 5),
+    "cotb200_agg_zeropad_mix_bwd": (ctypes.c_int, [_DP] + [ctypes.c_int] * 4 + [_VP] * 8),
+}
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load (building first if the sources are newer and nvcc exists) and return the ctypes library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        from . import build as _build
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc and no prebuilt .so
+            raise RuntimeError(
+                "cotnet_b200: libcotb200.so is missing and could not be built (%s). "
+                "There is no CPU fallback: run `python -m cotnet_b200.build` on a box with nvcc." % e) from e
+        lib = ctypes.CDLL(_LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().cotb200_last_error().decode("utf-8", "replace")
+        raise RuntimeError("cotb200 %s failed (rc=%d): %s" % (what, rc, msg))
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError("cotb200: unsupported dtype %s (float32/float64/bfloat16/float16)" % t.dtype)
+
+
+def stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(load().cotb200_launch_count())
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError("cotb200 %s: tensor is on %s; the B200 kernels need CUDA tensors (no CPU fallback)" % (what, t.device))
+
+
+def prof_enable(on: bool):
+    load().cotb200_prof_enable(1 if on else 0)
+
+
+def prof_report():
+    """{kernel name: (launches, total_ms)} of the launches recorded since prof_enable(True)."""
+    lib = load()
+    n = lib.cotb200_prof_report(None, 0)
+    buf = ctypes.create_string_buffer(n + 16)
+    lib.cotb200_prof_report(buf, n + 16)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(" ", 2)
+        out[name] = (int(cnt), float(ms))
+    return out

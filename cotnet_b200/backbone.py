@@ -1,0 +1,121 @@
+"""The caller of the hot path: a timm-style ResNet trunk whose bottleneck ``conv2`` is the CoT block.
+
+Host code stays PyTorch (BASELINE.json north_star); this file exists so the bench / tests can run
+CoTNet-50 / CoTNeXt-50 end to end on the GPU box, where /root/reference is absent.  Module names follow
+the reference (``models/resnet.py:448-611`` ResNet, ``models/cotnet.py:181-264`` Bottleneck) so its
+checkpoints load unchanged:  conv1, bn1, layer{1..4}.{i}.{conv1,bn1,conv2.<CotLayer keys>,conv3,bn3,
+downsample.{0,1}}, fc.
+
+Only what the four ``cotnet*`` entry points (models/cotnet.py:266-288) use is implemented: 7x7 stem,
+max-pool, [3,4,6,3]/[3,4,23,3] stages, 1x1 conv down-sample, 3x3/2 avg-pool in front of the CoT layer
+of stride-2 blocks (``avd``, :199-202,:237-238), global average pool + fc.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .cot_layer import CotLayer, CoXtLayer
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, cardinality=1, base_width=64):
+        super().__init__()
+        width = int(math.floor(planes * (base_width / 64)) * cardinality)
+        outplanes = planes * self.expansion
+        self.conv1 = nn.Conv2d(inplanes, width, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.act1 = nn.ReLU(inplace=True)
+        self.avd = nn.AvgPool2d(3, 2, padding=1) if stride > 1 else None
+        self.conv2 = CotLayer(width, kernel_size=3) if cardinality == 1 else CoXtLayer(width, kernel_size=3)
+        self.conv3 = nn.Conv2d(width, outplanes, kernel_size=1, bias=False)
+        self.bn3 = nn.BatchNorm2d(outplanes)
+        self.act3 = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+    def zero_init_last_bn(self):
+        nn.init.zeros_(self.bn3.weight)
+
+    def forward(self, x):
+        residual = x
+        x = self.act1(self.bn1(self.conv1(x)))
+        if self.avd is not None:
+            x = self.avd(x)
+        x = self.conv2(x)
+        x = self.bn3(self.conv3(x))
+        if self.downsample is not None:
+            residual = self.downsample(residual)
+        x += residual
+        return self.act3(x)
+
+
+class CoTResNet(nn.Module):
+    def __init__(self, layers, num_classes=1000, in_chans=3, cardinality=1, base_width=64, zero_init_last_bn=True):
+        super().__init__()
+        self.num_classes = num_classes
+        inplanes = 64
+        self.conv1 = nn.Conv2d(in_chans, inplanes, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(inplanes)
+        self.act1 = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        for i, (planes, n) in enumerate(zip((64, 128, 256, 512), layers)):
+            stride = 1 if i == 0 else 2
+            blocks = []
+            for b in range(n):
+                s = stride if b == 0 else 1
+                down = None
+                if b == 0 and (s != 1 or inplanes != planes * Bottleneck.expansion):
+                    down = nn.Sequential(
+                        nn.Conv2d(inplanes, planes * Bottleneck.expansion, 1, stride=s, bias=False),
+                        nn.BatchNorm2d(planes * Bottleneck.expansion))
+                blocks.append(Bottleneck(inplanes, planes, s, down, cardinality, base_width))
+                inplanes = planes * Bottleneck.expansion
+            self.add_module("layer%d" % (i + 1), nn.Sequential(*blocks))
+        self.num_features = inplanes
+        self.global_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Linear(self.num_features, num_classes)
+        # models/resnet.py:575-584
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1.0)
+                nn.init.constant_(m.bias, 0.0)
+        if zero_init_last_bn:
+            for m in self.modules():
+                if hasattr(m, "zero_init_last_bn"):
+                    m.zero_init_last_bn()
+
+    def forward_features(self, x):
+        x = self.maxpool(self.act1(self.bn1(self.conv1(x))))
+        return self.layer4(self.layer3(self.layer2(self.layer1(x))))
+
+    def forward(self, x):
+        x = self.global_pool(self.forward_features(x)).flatten(1)
+        return self.fc(x)
+
+    def cot_layers(self):
+        return [m for m in self.modules() if isinstance(m, (CotLayer, CoXtLayer))]
+
+
+def cotnet50(**kw):
+    return CoTResNet([3, 4, 6, 3], **kw)                                   # models/cotnet.py:270-273
+
+
+def cotnext50_2x48d(**kw):
+    return CoTResNet([3, 4, 6, 3], cardinality=2, base_width=48, **kw)     # :275-278
+
+
+def cotnet101(**kw):
+    return CoTResNet([3, 4, 23, 3], **kw)                                  # :280-283
+
+
+def cotnext101_2x48d(**kw):
+    return CoTResNet([3, 4, 23, 3], cardinality=2, base_width=48, **kw)    # :285-288
+
+
+MODELS = {"cotnet50": cotnet50, "cotnext50_2x48d": cotnext50_2x48d, "cotnet101": cotnet101,
+          "cotnext101_2x48d": cotnext101_2x48d}

@@ -1,0 +1,140 @@
+"""CoT block host modules with the reference's module / state-dict contract.
+
+    CotLayer(dim, kernel_size)    /root/reference/models/cotnet.py:36-104
+    CoXtLayer(dim, kernel_size)   /root/reference/models/cotnet.py:106-178
+    CoTLayer = CotLayer           /root/reference/models/cotnet_hybrid.py:48-116 (same arithmetic)
+
+Sub-module names (hence checkpoint keys) are the reference's: key_embed.{0,1}, embed.{0,1,3,4}, conv1x1.{0,1},
+local_conv, bn, se.{0,1,3}, so reference checkpoints load with strict=True and
+``utils/flops_counter.py`` still finds a ``LocalConvolution`` child.
+
+Forward maths is SURVEY.md Appendix A.  Differences from the reference's eager graph that do NOT change results:
+  * no ``torch.cat([x, k])`` / ``cat(dim=2)`` / ``sum(dim=2)`` temporaries for the radix-2 tail: the pooled
+    descriptor is mean(y + k) and the output is a0*y + a1*k directly;
+  * the memory format of the input is preserved (NCHW in -> NCHW-contiguous out as the reference's
+    ``.contiguous()`` gives; channels_last in -> channels_last out, no transposes), and the LocalConv runs on
+    the B200 kernels (NHWC kernels for channels_last tensors).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .aggregation_zeropad import AggregationZeropad, LocalConvolution
+
+
+def _radix2_tail(y, k, se):
+    """models/cotnet.py:92-104 without the [B,C,2,H,W] temporaries."""
+    B, C = y.shape[0], y.shape[1]
+    gap = (y + k).mean((2, 3), keepdim=True)
+    a = se(gap).view(B, C, 2)
+    a = F.softmax(a, dim=2).to(y.dtype)
+    return y * a[:, :, 0].reshape(B, C, 1, 1) + k * a[:, :, 1].reshape(B, C, 1, 1)
+
+
+def _keep_format(out, like):
+    if like.dim() == 4 and not like.is_contiguous() and like.is_contiguous(memory_format=torch.channels_last):
+        return out.contiguous(memory_format=torch.channels_last)
+    return out.contiguous()
+
+
+class CotLayer(nn.Module):
+    def __init__(self, dim, kernel_size):
+        super(CotLayer, self).__init__()
+        self.dim = dim
+        self.kernel_size = kernel_size
+        ks2 = kernel_size * kernel_size
+        share_planes, factor = 8, 2
+        self.key_embed = nn.Sequential(
+            nn.Conv2d(dim, dim, kernel_size, stride=1, padding=kernel_size // 2, groups=4, bias=False),
+            nn.BatchNorm2d(dim),
+            nn.ReLU(inplace=True))
+        self.embed = nn.Sequential(
+            nn.Conv2d(2 * dim, dim // factor, 1, bias=False),
+            nn.BatchNorm2d(dim // factor),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(dim // factor, ks2 * dim // share_planes, kernel_size=1),
+            nn.GroupNorm(num_groups=dim // share_planes, num_channels=ks2 * dim // share_planes))
+        self.conv1x1 = nn.Sequential(
+            nn.Conv2d(dim, dim, kernel_size=1, stride=1, padding=0, dilation=1, bias=False),
+            nn.BatchNorm2d(dim))
+        self.local_conv = LocalConvolution(dim, dim, kernel_size=kernel_size, stride=1,
+                                           padding=(kernel_size - 1) // 2, dilation=1)
+        self.bn = nn.BatchNorm2d(dim)
+        self.act = nn.SiLU(inplace=True)          # get_act_layer('swish'), models/layers/create_act.py:12,80-81
+        self.radix = 2
+        attn_chs = max(dim * self.radix // 4, 32)
+        self.se = nn.Sequential(
+            nn.Conv2d(dim, attn_chs, 1),
+            nn.BatchNorm2d(attn_chs),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(attn_chs, self.radix * dim, 1))
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        k = self.key_embed(x)                                              # static context
+        w = self.embed(torch.cat([x, k], dim=1))                           # logits, GroupNorm'ed, NOT softmaxed
+        w = w.view(B, 1, C // 8, self.kernel_size * self.kernel_size, H, W)
+        v = self.conv1x1(x)
+        y = self.local_conv(v, w.to(v.dtype))                              # B200 LocalConv kernel
+        y = self.act(self.bn(y))
+        return _keep_format(_radix2_tail(y, k, self.se), x)
+
+
+class CoXtLayer(nn.Module):
+    def __init__(self, dim, kernel_size):
+        super(CoXtLayer, self).__init__()
+        self.dim = dim
+        self.kernel_size = kernel_size
+        ks2 = kernel_size * kernel_size
+        self.dw_group = 2
+        share_planes, factor = 8, 2
+        self.key_embed = nn.Sequential(
+            nn.Conv2d(dim, dim, kernel_size, stride=1, padding=kernel_size // 2, groups=8, bias=False),
+            nn.BatchNorm2d(dim),
+            nn.ReLU(inplace=True))
+        self.embed = nn.Sequential(
+            nn.Conv2d(2 * dim, dim // factor, 1, groups=self.dw_group, bias=False),
+            nn.BatchNorm2d(dim // factor),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(dim // factor, ks2 * dim // share_planes, kernel_size=1, groups=self.dw_group),
+            nn.GroupNorm(num_groups=dim // share_planes, num_channels=ks2 * dim // share_planes))
+        self.conv1x1 = nn.Sequential(
+            nn.Conv2d(dim, dim, kernel_size=1, stride=1, padding=0, dilation=1, groups=self.dw_group, bias=False),
+            nn.BatchNorm2d(dim))
+        self.local_conv = LocalConvolution(dim, dim, kernel_size=kernel_size, stride=1,
+                                           padding=(kernel_size - 1) // 2, dilation=1)
+        self.bn = nn.BatchNorm2d(dim)
+        self.act = nn.SiLU(inplace=True)
+        self.radix = 2
+        attn_chs = max(dim * self.radix // 4, 32)
+        self.se = nn.Sequential(
+            nn.Conv2d(dim, attn_chs, 1),
+            nn.BatchNorm2d(attn_chs),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(attn_chs, self.radix * dim, 1))
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        ks = self.kernel_size
+        k = self.key_embed(x)
+        qk = torch.stack([x, k], dim=2).reshape(B, 2 * C, H, W)            # interleaved x0,k0,x1,k1,.. (:153-154)
+        if not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last):
+            qk = qk.contiguous(memory_format=torch.channels_last)
+        w = self.embed(qk)
+        v = self.conv1x1(x)
+        # The reference folds the two channel halves into the batch: view(2B, C/2, H, W) with weights
+        # view(2B, 1, C/16, 9, H, W) (:157-162).  Same arithmetic un-folded: channel c of half f uses weight channel
+        # f*(C/16) + (c % (C/2)) % (C/16) -- the kernels' `fold` argument -- so channels_last tensors need no copy.
+        if v.is_contiguous() and w.is_contiguous():
+            # NCHW: the reference's batch fold is a free view and keeps the register-resident fast kernel
+            G = self.dw_group
+            y = AggregationZeropad.apply(v.view(B * G, C // G, H, W), w.view(B * G, 1, -1, ks * ks, H, W).to(v.dtype),
+                                         ks, 1, (ks - 1) // 2, 1).view(B, C, H, W)
+        else:
+            w = w.view(B, 1, C // 8, ks * ks, H, W).to(v.dtype)
+            y = AggregationZeropad.apply(v, w, ks, 1, (ks - 1) // 2, 1, self.dw_group)
+        y = self.act(self.bn(y))
+        return _keep_format(_radix2_tail(y, k, self.se), x)
+
+
+CoTLayer = CotLayer   # models/cotnet_hybrid.py:48-116 is the same block under another name

@@ -1,0 +1,131 @@
+// Shared helpers for libcotb200 (sm_100a).  Host-side error plumbing + device-side element traits.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include <type_traits>
+
+#include "../../include/cotb200.h"
+
+namespace cotb200 {
+
+// ---------------------------------------------------------------- host: errors + launch accounting
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+// Optional per-launch timing (cotb200_prof_enable): CUDA events recorded on the launch stream around each kernel.
+// Disabled by default (zero overhead beyond one relaxed atomic load); never enable under graph capture.
+struct ProfScope {
+  const char* name; cudaStream_t st; cudaEvent_t e0; bool on;
+  ProfScope(const char* n, cudaStream_t s);
+  ~ProfScope();
+};
+#define COTB200_PROF(name) cotb200::ProfScope _prof_scope(name, st)
+
+inline int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---------------------------------------------------------------- device: element traits
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  using Acc = float;
+  __device__ __forceinline__ static float ld(const float* p) { return __ldg(p); }
+  __device__ __forceinline__ static float from(float a) { return a; }
+};
+template <> struct Elem<double> {
+  using Acc = double;
+  __device__ __forceinline__ static double ld(const double* p) { return __ldg(p); }
+  __device__ __forceinline__ static double from(double a) { return a; }
+};
+template <> struct Elem<__nv_bfloat16> {
+  using Acc = float;
+  __device__ __forceinline__ static float ld(const __nv_bfloat16* p) {
+    return __bfloat162float(__ldg(p));
+  }
+  __device__ __forceinline__ static __nv_bfloat16 from(float a) { return __float2bfloat16_rn(a); }
+};
+template <> struct Elem<__half> {
+  using Acc = float;
+  __device__ __forceinline__ static float ld(const __half* p) { return __half2float(__ldg(p)); }
+  __device__ __forceinline__ static __half from(float a) { return __float2half_rn(a); }
+};
+
+// A VEC-wide packet of T moved with one load/store instruction (VEC*sizeof(T) <= 16 bytes).
+template <typename T, int VEC> struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
+
+template <typename T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> ld_pack(const T* p) {
+  Pack<T, VEC> r;
+  constexpr int B = sizeof(T) * VEC;
+  if constexpr (B == 16) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    r = *reinterpret_cast<Pack<T, VEC>*>(&u);
+  } else if constexpr (B == 8) {
+    uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    r = *reinterpret_cast<Pack<T, VEC>*>(&u);
+  } else if constexpr (B == 4) {
+    unsigned u = __ldg(reinterpret_cast<const unsigned*>(p));
+    r = *reinterpret_cast<Pack<T, VEC>*>(&u);
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r.v[i] = __ldg(p + i);
+  }
+  return r;
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void st_pack(T* p, const Pack<T, VEC>& r) {
+  constexpr int B = sizeof(T) * VEC;
+  if constexpr (B == 16) {
+    *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&r);
+  } else if constexpr (B == 8) {
+    *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(&r);
+  } else if constexpr (B == 4) {
+    *reinterpret_cast<unsigned*>(p) = *reinterpret_cast<const unsigned*>(&r);
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) p[i] = r.v[i];
+  }
+}
+
+template <typename T> __device__ __forceinline__ typename Elem<T>::Acc to_acc(T v);
+template <> __device__ __forceinline__ float to_acc<float>(float v) { return v; }
+template <> __device__ __forceinline__ double to_acc<double>(double v) { return v; }
+template <> __device__ __forceinline__ float to_acc<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_acc<__half>(__half v) { return __half2float(v); }
+
+// dtype dispatch on the host
+#define COTB200_DISPATCH_DTYPE(dtype, ...)                                   \
+  switch (dtype) {                                                           \
+    case COTB200_F32:  { using T = float;          __VA_ARGS__; } break;     \
+    case COTB200_F64:  { using T = double;         __VA_ARGS__; } break;     \
+    case COTB200_BF16: { using T = __nv_bfloat16;  __VA_ARGS__; } break;     \
+    case COTB200_F16:  { using T = __half;         __VA_ARGS__; } break;     \
+    default: cotb200::set_error("unknown dtype %d", (int)(dtype)); return COTB200_EDTYPE; \
+  }
+
+}  // namespace cotb200

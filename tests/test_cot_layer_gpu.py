@@ -1,0 +1,116 @@
+"""GPU parity of the CoT block modules (product) against the oracle restatement and the golden vectors made
+from the reference's own module code.  Tolerances: fp64 1e-8, fp32 atol=rtol=1e-3, bf16 atol=rtol=1e-2 scaled
+by the output magnitude."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cot_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from cotnet_b200 import cot_layer
+    return cot_layer
+
+
+def _load_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name))
+    sd = {k[len("param/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param/")}
+    return g, sd
+
+
+@pytest.mark.parametrize("name,cls,dim", [("cot_layer_d32.npz", "CotLayer", 32), ("cothybrid_layer_d32.npz", "CoTLayer", 32),
+                                          ("coxt_layer_d48.npz", "CoXtLayer", 48)])
+@pytest.mark.parametrize("cl", [False, True])
+def test_golden_fp64(golden_dir, name, cls, dim, cl):
+    g, sd = _load_golden(golden_dir, name)
+    m = getattr(_mods(), cls)(dim, 3).double().cuda()
+    m.load_state_dict(sd, strict=True)
+    x = torch.from_numpy(g["x"]).cuda()
+    cot = torch.from_numpy(g["cotangent"]).cuda()
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+        m = m.to(memory_format=torch.channels_last)
+    m.eval()
+    with torch.no_grad():
+        out = m(x)
+    assert (out.cpu() - torch.from_numpy(g["out_eval"])).abs().max() < 1e-8
+    m.train()
+    xg = x.clone().requires_grad_(True)
+    out = m(xg)
+    assert (out.detach().cpu() - torch.from_numpy(g["out_train"])).abs().max() < 1e-8
+    (out * cot).sum().backward()
+    assert (xg.grad.cpu() - torch.from_numpy(g["grad/x"])).abs().max() < 1e-7
+    for n_, p_ in m.named_parameters():
+        ref = torch.from_numpy(g["grad/" + n_])
+        assert (p_.grad.cpu() - ref).abs().max() < 1e-7 * max(1.0, ref.abs().max().item()), n_
+    for n_, b_ in m.named_buffers():
+        ref = torch.from_numpy(g["buf_after/" + n_])
+        assert (b_.double().cpu() - ref.double()).abs().max() < 1e-9, n_
+
+
+@pytest.mark.parametrize("kind,cls,dim,H", [("cot", "CotLayer", 64, 56), ("cot", "CotLayer", 128, 28), ("cot", "CotLayer", 256, 14),
+                                            ("cot", "CotLayer", 512, 7), ("coxt", "CoXtLayer", 96, 28), ("coxt", "CoXtLayer", 192, 14)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cl", [False, True])
+@pytest.mark.parametrize("training", [False, True])
+def test_stage_shapes_vs_oracle(kind, cls, dim, H, dtype, cl, training):
+    gen = torch.Generator().manual_seed(dim + H)
+    sd64 = cot_ref.init_state_dict(kind, dim, gen, dtype=torch.float64, perturb=True)
+    B = 4
+    x64 = torch.relu(torch.randn(B, dim, H, H, generator=gen, dtype=torch.float64))
+    # bf16 protocol: the oracle sees the same bf16-representable inputs / parameters
+    sd64 = {k: (v.to(dtype).double() if v.dtype.is_floating_point else v) for k, v in sd64.items()}
+    x64 = x64.to(dtype).double()
+    m = getattr(_mods(), cls)(dim, 3)
+    m.load_state_dict(sd64, strict=True)
+    m = m.to(dtype).cuda()
+    x = x64.to(dtype).cuda()
+    if cl:
+        m = m.to(memory_format=torch.channels_last)
+        x = x.contiguous(memory_format=torch.channels_last)
+    m.train(training)
+    fn = cot_ref.cot_layer if kind == "cot" else cot_ref.coxt_layer
+    want = fn(x64, {k: v.clone() for k, v in sd64.items()}, training=training)
+    with torch.set_grad_enabled(training):
+        got = m(x)
+    tol = 1e-3 if dtype == torch.float32 else 1e-2
+    # intermediate tensors are rounded to bf16 between the (unfused) stages of this path, so the bound is
+    # relative to the output scale
+    scale = max(1.0, want.abs().max().item())
+    err = (got.double().cpu() - want).abs()
+    lim = (tol * 4 if dtype == torch.bfloat16 else tol) * scale
+    assert err.max().item() <= lim, "max err %.3e (limit %.3e, |ref|max %.3e)" % (err.max().item(), lim, scale)
+    assert got.shape == x.shape and got.dtype == dtype
+    if cl:
+        assert got.is_contiguous(memory_format=torch.channels_last)
+    else:
+        assert got.is_contiguous()
+
+
+def test_backbone_matches_oracle_model_fp32():
+    from cotnet_b200 import backbone
+    from oracle import cot_model_ref
+    torch.manual_seed(0)
+    m = backbone.cotnet50()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            torch.nn.init.uniform_(mod.weight, 0.3, 0.7)
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.8, 1.2)
+    o = cot_model_ref.build("cotnet50")
+    o.load_reference_state(m.state_dict())
+    x = torch.randn(2, 3, 96, 96)
+    o.eval()
+    with torch.no_grad():
+        want = o(x)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        got = m(x.cuda())
+        got_cl = m.to(memory_format=torch.channels_last)(x.cuda().contiguous(memory_format=torch.channels_last))
+    assert torch.allclose(got.cpu(), want, atol=1e-3, rtol=1e-3)
+    assert torch.allclose(got_cl.cpu(), want, atol=1e-3, rtol=1e-3)
