@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fused
 from .aggregation_zeropad import AggregationZeropad, LocalConvolution
 
 
@@ -69,13 +70,32 @@ class CotLayer(nn.Module):
             nn.ReLU(inplace=True),
             nn.Conv2d(attn_chs, self.radix * dim, 1))
 
+    def _forward_fused(self, x):
+        """channels_last fast path: GroupNorm, bn+SiLU+pool and the radix-2 recombination are fused kernels."""
+        B, C, H, W = x.shape
+        ks2 = self.kernel_size * self.kernel_size
+        k = self.key_embed(x)
+        e = self.embed[2](self.embed[1](self.embed[0](torch.cat([x, k], dim=1))))
+        l = self.embed[3](e)
+        v = self.conv1x1(x)
+        if l.dtype != v.dtype:
+            l = l.to(v.dtype)
+        l = l.contiguous(memory_format=torch.channels_last)
+        w = fused.group_norm9(l, self.embed[4])                            # fp32 statistics, storage dtype out
+        u = self.local_conv(v.contiguous(memory_format=torch.channels_last), w.view(B, 1, C // 8, ks2, H, W))
+        return fused.cot_tail(u, k.contiguous(memory_format=torch.channels_last), self.bn, self.se)
+
     def forward(self, x):
         B, C, H, W = x.shape
+        if self.kernel_size == 3 and fused.supported(x):
+            return self._forward_fused(x)
         k = self.key_embed(x)                                              # static context
         w = self.embed(torch.cat([x, k], dim=1))                           # logits, GroupNorm'ed, NOT softmaxed
-        w = w.view(B, 1, C // 8, self.kernel_size * self.kernel_size, H, W)
         v = self.conv1x1(x)
-        y = self.local_conv(v, w.to(v.dtype))                              # B200 LocalConv kernel
+        # cast BEFORE the 6-D view: .to() on the 4-D tensor keeps channels_last, so the view below is the NHWC weight
+        # layout the kernels take without a copy
+        w = w.to(v.dtype).view(B, 1, C // 8, self.kernel_size * self.kernel_size, H, W)
+        y = self.local_conv(v, w)                                          # B200 LocalConv kernel
         y = self.act(self.bn(y))
         return _keep_format(_radix2_tail(y, k, self.se), x)
 
@@ -113,25 +133,42 @@ class CoXtLayer(nn.Module):
             nn.ReLU(inplace=True),
             nn.Conv2d(attn_chs, self.radix * dim, 1))
 
+    def _forward_fused(self, x):
+        B, C, H, W = x.shape
+        ks = self.kernel_size
+        k = self.key_embed(x)
+        qk = torch.stack([x, k], dim=2).reshape(B, 2 * C, H, W).contiguous(memory_format=torch.channels_last)
+        e = self.embed[2](self.embed[1](self.embed[0](qk)))
+        l = self.embed[3](e)
+        v = self.conv1x1(x)
+        if l.dtype != v.dtype:
+            l = l.to(v.dtype)
+        w = fused.group_norm9(l.contiguous(memory_format=torch.channels_last), self.embed[4])
+        u = AggregationZeropad.apply(v.contiguous(memory_format=torch.channels_last), w.view(B, 1, C // 8, ks * ks, H, W),
+                                     ks, 1, (ks - 1) // 2, 1, self.dw_group)
+        return fused.cot_tail(u, k.contiguous(memory_format=torch.channels_last), self.bn, self.se)
+
     def forward(self, x):
         B, C, H, W = x.shape
         ks = self.kernel_size
+        if ks == 3 and fused.supported(x):
+            return self._forward_fused(x)
         k = self.key_embed(x)
         qk = torch.stack([x, k], dim=2).reshape(B, 2 * C, H, W)            # interleaved x0,k0,x1,k1,.. (:153-154)
         if not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last):
             qk = qk.contiguous(memory_format=torch.channels_last)
-        w = self.embed(qk)
         v = self.conv1x1(x)
+        w = self.embed(qk).to(v.dtype)
         # The reference folds the two channel halves into the batch: view(2B, C/2, H, W) with weights
         # view(2B, 1, C/16, 9, H, W) (:157-162).  Same arithmetic un-folded: channel c of half f uses weight channel
         # f*(C/16) + (c % (C/2)) % (C/16) -- the kernels' `fold` argument -- so channels_last tensors need no copy.
         if v.is_contiguous() and w.is_contiguous():
             # NCHW: the reference's batch fold is a free view and keeps the register-resident fast kernel
             G = self.dw_group
-            y = AggregationZeropad.apply(v.view(B * G, C // G, H, W), w.view(B * G, 1, -1, ks * ks, H, W).to(v.dtype),
+            y = AggregationZeropad.apply(v.view(B * G, C // G, H, W), w.view(B * G, 1, -1, ks * ks, H, W),
                                          ks, 1, (ks - 1) // 2, 1).view(B, C, H, W)
         else:
-            w = w.view(B, 1, C // 8, ks * ks, H, W).to(v.dtype)
+            w = w.view(B, 1, C // 8, ks * ks, H, W)
             y = AggregationZeropad.apply(v, w, ks, 1, (ks - 1) // 2, 1, self.dw_group)
         y = self.act(self.bn(y))
         return _keep_format(_radix2_tail(y, k, self.se), x)

@@ -107,6 +107,49 @@ __global__ void agg_dx_generic(const T* __restrict__ dy, const T* __restrict__ w
   }
 }
 
+// Mix op: dX = dX(kernel 1) + dX(kernel 2) accumulated in fp32 in ONE pass (a second accumulate-in-place launch would
+// round the first half to the storage type first -- visible in bf16).
+template <typename T>
+__global__ void agg_dx_generic2(const T* __restrict__ dy1, const T* __restrict__ w1, Geo g1, const T* __restrict__ dy2,
+                                const T* __restrict__ w2, Geo g2, T* __restrict__ dx, long long total) {
+  using Acc = typename Elem<T>::Acc;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int wq = r % g1.W; r /= g1.W;
+    const int h = r % g1.H; r /= g1.H;
+    const int c = r % g1.C;
+    const int n = r / g1.C;
+    Acc acc = 0;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const Geo& g = pass ? g2 : g1;
+      const T* dy = pass ? dy2 : dy1;
+      const T* w = pass ? w2 : w1;
+      const int gch = wch_of(g, c);
+      for (int head = 0; head < g.heads; ++head) {
+        const T* wp = w + n * g.w_sn + head * g.w_shead;
+        const T* dp = dy + n * g.y_sn + (long long)(head * g.C + c) * g.y_sc;
+        for (int kh = 0; kh < g.KH; ++kh) {
+          const int hs = h + g.PH - kh * g.DH;
+          if (hs < 0 || hs % g.SH) continue;
+          const int ho = hs / g.SH;
+          if (ho >= g.HO) continue;
+          for (int kw = 0; kw < g.KW; ++kw) {
+            const int ws = wq + g.PW - kw * g.DW;
+            if (ws < 0 || ws % g.SW) continue;
+            const int wo = ws / g.SW;
+            if (wo >= g.WO) continue;
+            acc += to_acc(wp[ho * g.w_sh + wo * g.w_sw + w_gt(g, gch, kh * g.KW + kw)]) *
+                   to_acc(dp[ho * g.y_sh + wo * g.y_sw]);
+          }
+        }
+      }
+    }
+    dx[n * g1.x_sn + c * g1.x_sc + h * g1.x_sh + wq * g1.x_sw] = Elem<T>::from(acc);
+  }
+}
+
 // dW[n,head,gch,tap,ho,wo] = sum_{cc = gch (mod wc)} x[n,cc,hi,wi] * dY[n,head*C+cc,ho,wo]   (0 for padded taps)
 template <typename T>
 __global__ void agg_dw_generic(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dw, Geo g,
@@ -700,9 +743,17 @@ extern "C" int cotb200_agg_zeropad_mix_bwd(const cotb200_agg_desc* d, int k2h, i
   cudaStream_t st = (cudaStream_t)stream;
   const long long half = (long long)g1.heads * g1.C * g1.HO * g1.WO;
   COTB200_DISPATCH_DTYPE(d->dtype, {
-    rc = bwd_impl<T>(g1, (const T*)dy, (const T*)x, (const T*)w1, (T*)dx, (T*)dw1, false, st);
+    if (dx) {   // both halves of dX in one fp32-accumulating pass
+      const long long total = (long long)g1.N * g1.C * g1.H * g1.W;
+      COTB200_PROF("agg_mix_dx");
+      agg_dx_generic2<T><<<grid_for(total, 256, 16), 256, 0, st>>>((const T*)dy, (const T*)w1, g1, (const T*)dy + half,
+                                                                  (const T*)w2, g2, (T*)dx, total);
+      rc = check_launch("agg_mix_dx");
+      if (rc) return rc;
+    }
+    rc = bwd_impl<T>(g1, (const T*)dy, (const T*)x, (const T*)w1, (T*)nullptr, (T*)dw1, false, st);
     if (rc) return rc;
-    return bwd_impl<T>(g2, (const T*)dy + half, (const T*)x, (const T*)w2, (T*)dx, (T*)dw2, dx != nullptr, st);
+    return bwd_impl<T>(g2, (const T*)dy + half, (const T*)x, (const T*)w2, (T*)nullptr, (T*)dw2, false, st);
   });
   return 0;
 }

@@ -1,0 +1,653 @@
+// Fused normalisation / split-attention kernels of the CoT block on NHWC tensors (sm_100a, HBM-bound).
+//
+// They replace long chains of eager element-wise / reduction launches of the reference block
+// (/root/reference/models/cotnet.py:89-104 and the GroupNorm at :56), each a full HBM round trip:
+//   * GroupNorm over the 9 taps of one weight channel (nn.GroupNorm(C/8, 9C/8), :56): stats, apply, backward
+//   * the "tail":  y = SiLU(BN(u)) (:89-90);  p = mean_hw(y + k) (:92-98);  out = a0*y + a1*k (:101-104)
+//     and its backward, including the BatchNorm batch-statistics reductions of training mode.
+// All tensors are [B, HW, C] with the channel dimension contiguous (torch channels_last); math is fp32.
+//
+// One skeleton: a CTA owns (sample b, a chunk of rows); threads are (tx = 16-byte channel packet, ty = row lane), so a
+// warp always touches whole 128-byte lines; per-column partial sums live in registers, are reduced across ty through
+// shared memory and leave the CTA as ONE atomicAdd per column.
+#include "common.cuh"
+
+namespace cotb200 {
+
+static constexpr int NT_THREADS = 256;
+
+struct RowsGeo {
+  int B, HW, C;          // rows per sample, channels
+  int rows_per_cta;      // row chunk
+  int cq;                // packets per row = C / VEC
+  int ry;                // row lanes = NT_THREADS / cq_pad
+  int cq_pad;            // power-of-two >= cq (thread x extent)
+};
+
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + __expf(-z)); }
+
+// Reduce acc[NS][VEC] over the ty lanes of the CTA; result for column c lands in smem_out[s*C + c].
+template <int NS, int VEC>
+__device__ __forceinline__ void cta_col_reduce(float (&acc)[NS][VEC], float* sm, const RowsGeo& g, int tx, int ty, bool active) {
+  // sm layout: [NS][ry][C]
+  if (active) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) sm[(s * g.ry + ty) * g.C + tx * VEC + i] = acc[s][i];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NS * g.C; idx += NT_THREADS) {
+    const int s = idx / g.C, c = idx - s * g.C;
+    float t = 0.f;
+    for (int y = 0; y < g.ry; ++y) t += sm[(s * g.ry + y) * g.C + c];
+    sm[(s * g.ry) * g.C + c] = t;             // row 0 of each sum plane holds the CTA total
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------ column statistics
+// sum[c] += sum_rows x, sq[c] += sum_rows x^2       (BatchNorm batch statistics of u, models/cotnet.py:89)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(NT_THREADS)
+col_stats_kernel(const T* __restrict__ x, float* __restrict__ sum, float* __restrict__ sq, RowsGeo g) {
+  extern __shared__ float sm[];
+  const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
+  const bool active = tx < g.cq && ty < g.ry;
+  const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
+  float acc[2][VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+  if (active) {
+    const T* xp = x + ((long long)b * g.HW) * g.C + tx * VEC;
+    for (int r = r0 + ty; r < r1; r += g.ry) {
+      const Pack<T, VEC> v = ld_pack<T, VEC>(xp + (long long)r * g.C);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { const float f = to_acc(v.v[i]); acc[0][i] += f; acc[1][i] = fmaf(f, f, acc[1][i]); }
+    }
+  }
+  cta_col_reduce<2, VEC>(acc, sm, g, tx, ty, active);
+  for (int c = threadIdx.x; c < g.C; c += NT_THREADS) {
+    atomicAdd(sum + c, sm[c]);
+    atomicAdd(sq + c, sm[g.ry * g.C + c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ tail forward
+// psum[b,c] += sum_rows ( silu(u*scale+shift) + k )                      (models/cotnet.py:89-98)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(NT_THREADS)
+tail_pool_kernel(const T* __restrict__ u, const T* __restrict__ k, const float* __restrict__ scale,
+                 const float* __restrict__ shift, float* __restrict__ psum, RowsGeo g) {
+  extern __shared__ float sm[];
+  const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
+  const bool active = tx < g.cq && ty < g.ry;
+  const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
+  float acc[1][VEC], sc[VEC], sh[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { acc[0][i] = 0.f; sc[i] = active ? scale[tx * VEC + i] : 0.f; sh[i] = active ? shift[tx * VEC + i] : 0.f; }
+  if (active) {
+    const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+    for (int r = r0 + ty; r < r1; r += g.ry) {
+      const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
+      const Pack<T, VEC> kv = ld_pack<T, VEC>(k + base + (long long)r * g.C);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float z = fmaf(to_acc(uv.v[i]), sc[i], sh[i]);
+        acc[0][i] += z * sigmoidf_(z) + to_acc(kv.v[i]);
+      }
+    }
+  }
+  cta_col_reduce<1, VEC>(acc, sm, g, tx, ty, active);
+  for (int c = threadIdx.x; c < g.C; c += NT_THREADS) atomicAdd(psum + (long long)b * g.C + c, sm[c]);
+}
+
+// out = a0 * silu(u*scale+shift) + a1 * k        a: [B, C, 2] fp32          (models/cotnet.py:101-104)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(NT_THREADS)
+tail_combine_kernel(const T* __restrict__ u, const T* __restrict__ k, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ a, T* __restrict__ out, RowsGeo g) {
+  const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
+  if (!(tx < g.cq && ty < g.ry)) return;
+  const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
+  float sc[VEC], sh[VEC], a0[VEC], a1[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c = tx * VEC + i;
+    sc[i] = scale[c]; sh[i] = shift[c];
+    a0[i] = a[((long long)b * g.C + c) * 2]; a1[i] = a[((long long)b * g.C + c) * 2 + 1];
+  }
+  const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+  for (int r = r0 + ty; r < r1; r += g.ry) {
+    const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
+    const Pack<T, VEC> kv = ld_pack<T, VEC>(k + base + (long long)r * g.C);
+    Pack<T, VEC> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float z = fmaf(to_acc(uv.v[i]), sc[i], sh[i]);
+      o.v[i] = Elem<T>::from(fmaf(a0[i], z * sigmoidf_(z), a1[i] * to_acc(kv.v[i])));
+    }
+    st_pack<T, VEC>(out + base + (long long)r * g.C, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ tail backward
+// S[b,c,0] += sum_rows dout*y ; S[b,c,1] += sum_rows dout*k     (gradients of the radix-2 attention weights)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(NT_THREADS)
+tail_bwd_sums_kernel(const T* __restrict__ dout, const T* __restrict__ u, const T* __restrict__ k,
+                     const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ S, RowsGeo g) {
+  extern __shared__ float sm[];
+  const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
+  const bool active = tx < g.cq && ty < g.ry;
+  const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
+  float acc[2][VEC], sc[VEC], sh[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { acc[0][i] = acc[1][i] = 0.f; sc[i] = active ? scale[tx * VEC + i] : 0.f; sh[i] = active ? shift[tx * VEC + i] : 0.f; }
+  if (active) {
+    const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+    for (int r = r0 + ty; r < r1; r += g.ry) {
+      const Pack<T, VEC> dv = ld_pack<T, VEC>(dout + base + (long long)r * g.C);
+      const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
+      const Pack<T, VEC> kv = ld_pack<T, VEC>(k + base + (long long)r * g.C);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float z = fmaf(to_acc(uv.v[i]), sc[i], sh[i]);
+        const float d = to_acc(dv.v[i]);
+        acc[0][i] = fmaf(d, z * sigmoidf_(z), acc[0][i]);
+        acc[1][i] = fmaf(d, to_acc(kv.v[i]), acc[1][i]);
+      }
+    }
+  }
+  cta_col_reduce<2, VEC>(acc, sm, g, tx, ty, active);
+  for (int c = threadIdx.x; c < g.C; c += NT_THREADS) {
+    atomicAdd(S + ((long long)b * g.C + c) * 2, sm[c]);
+    atomicAdd(S + ((long long)b * g.C + c) * 2 + 1, sm[g.ry * g.C + c]);
+  }
+}
+
+// dz = (a0*dout + dpn) * silu'(z),  z = u*scale+shift  -- the gradient entering the BatchNorm.
+// Accumulates sum_dz[c], sum_dzx[c] (x = normalised u) for the training-mode BatchNorm backward.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(NT_THREADS)
+tail_bwd_dz_sums_kernel(const T* __restrict__ dout, const T* __restrict__ u, const float* __restrict__ scale,
+                        const float* __restrict__ shift, const float* __restrict__ mu, const float* __restrict__ rstd,
+                        const float* __restrict__ a, const float* __restrict__ dpn, float* __restrict__ sum_dz,
+                        float* __restrict__ sum_dzx, RowsGeo g) {
+  extern __shared__ float sm[];
+  const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
+  const bool active = tx < g.cq && ty < g.ry;
+  const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
+  float acc[2][VEC], sc[VEC], sh[VEC], m[VEC], rs[VEC], a0[VEC], dp[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c = tx * VEC + i;
+    acc[0][i] = acc[1][i] = 0.f;
+    sc[i] = active ? scale[c] : 0.f; sh[i] = active ? shift[c] : 0.f; m[i] = active ? mu[c] : 0.f; rs[i] = active ? rstd[c] : 0.f;
+    a0[i] = active ? a[((long long)b * g.C + c) * 2] : 0.f; dp[i] = active ? dpn[(long long)b * g.C + c] : 0.f;
+  }
+  if (active) {
+    const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+    for (int r = r0 + ty; r < r1; r += g.ry) {
+      const Pack<T, VEC> dv = ld_pack<T, VEC>(dout + base + (long long)r * g.C);
+      const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float uf = to_acc(uv.v[i]);
+        const float z = fmaf(uf, sc[i], sh[i]);
+        const float s = sigmoidf_(z);
+        const float dz = fmaf(a0[i], to_acc(dv.v[i]), dp[i]) * (s * (1.f + z * (1.f - s)));
+        acc[0][i] += dz;
+        acc[1][i] = fmaf(dz, (uf - m[i]) * rs[i], acc[1][i]);
+      }
+    }
+  }
+  cta_col_reduce<2, VEC>(acc, sm, g, tx, ty, active);
+  for (int c = threadIdx.x; c < g.C; c += NT_THREADS) {
+    atomicAdd(sum_dz + c, sm[c]);
+    atomicAdd(sum_dzx + c, sm[g.ry * g.C + c]);
+  }
+}
+
+// du = scale * (dz - c1 - xhat*c2)   [c1 = sum_dz/n, c2 = sum_dzx/n in training; 0 in eval]
+// dk = a1*dout + dpn
+template <typename T, int VEC>
+__global__ void __launch_bounds__(NT_THREADS)
+tail_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ u, const float* __restrict__ scale,
+                      const float* __restrict__ shift, const float* __restrict__ mu, const float* __restrict__ rstd,
+                      const float* __restrict__ a, const float* __restrict__ dpn, const float* __restrict__ c1,
+                      const float* __restrict__ c2, T* __restrict__ du, T* __restrict__ dk, RowsGeo g) {
+  const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
+  if (!(tx < g.cq && ty < g.ry)) return;
+  const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
+  float sc[VEC], sh[VEC], m[VEC], rs[VEC], a0[VEC], a1[VEC], dp[VEC], k1[VEC], k2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c = tx * VEC + i;
+    sc[i] = scale[c]; sh[i] = shift[c]; m[i] = mu[c]; rs[i] = rstd[c];
+    a0[i] = a[((long long)b * g.C + c) * 2]; a1[i] = a[((long long)b * g.C + c) * 2 + 1]; dp[i] = dpn[(long long)b * g.C + c];
+    k1[i] = c1 ? c1[c] : 0.f; k2[i] = c2 ? c2[c] : 0.f;
+  }
+  const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+  for (int r = r0 + ty; r < r1; r += g.ry) {
+    const Pack<T, VEC> dv = ld_pack<T, VEC>(dout + base + (long long)r * g.C);
+    const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
+    Pack<T, VEC> o1, o2;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float uf = to_acc(uv.v[i]), d = to_acc(dv.v[i]);
+      const float z = fmaf(uf, sc[i], sh[i]);
+      const float s = sigmoidf_(z);
+      const float dz = fmaf(a0[i], d, dp[i]) * (s * (1.f + z * (1.f - s)));
+      o1.v[i] = Elem<T>::from(sc[i] * (dz - k1[i] - (uf - m[i]) * rs[i] * k2[i]));
+      o2.v[i] = Elem<T>::from(fmaf(a1[i], d, dp[i]));
+    }
+    st_pack<T, VEC>(du + base + (long long)r * g.C, o1);
+    st_pack<T, VEC>(dk + base + (long long)r * g.C, o2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm(9 taps)
+// Channel j of the logits belongs to group grp(j): plain order j = g*9 + t; tap-major chunks (gc) otherwise.
+__device__ __forceinline__ int gn_group(int j, int gc) {
+  if (gc <= 0) return j / 9;
+  const int chunk = j / (9 * gc), rr = j - chunk * 9 * gc;
+  return chunk * gc + rr % gc;
+}
+
+// gsum[b,g] += sum over (9 taps x rows) of l ; gsq likewise
+template <typename T, int VEC>
+__global__ void __launch_bounds__(NT_THREADS)
+gn_stats_kernel(const T* __restrict__ l, float* __restrict__ gsum, float* __restrict__ gsq, RowsGeo g, int wc, int gc) {
+  extern __shared__ float sm[];
+  const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
+  const bool active = tx < g.cq && ty < g.ry;
+  const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
+  float acc[2][VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { acc[0][i] = acc[1][i] = 0.f; }
+  if (active) {
+    const T* lp = l + ((long long)b * g.HW) * g.C + tx * VEC;
+    for (int r = r0 + ty; r < r1; r += g.ry) {
+      const Pack<T, VEC> v = ld_pack<T, VEC>(lp + (long long)r * g.C);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { const float f = to_acc(v.v[i]); acc[0][i] += f; acc[1][i] = fmaf(f, f, acc[1][i]); }
+    }
+  }
+  cta_col_reduce<2, VEC>(acc, sm, g, tx, ty, active);
+  // fold the 9 tap columns of each group, one atomic per (b, group)
+  for (int gi = threadIdx.x; gi < wc; gi += NT_THREADS) {
+    float s = 0.f, q = 0.f;
+    if (gc <= 0) {
+      for (int t = 0; t < 9; ++t) { s += sm[gi * 9 + t]; q += sm[g.ry * g.C + gi * 9 + t]; }
+    } else {
+      const int chunk = gi / gc, i = gi % gc;
+      for (int t = 0; t < 9; ++t) { const int j = (chunk * 9 + t) * gc + i; s += sm[j]; q += sm[g.ry * g.C + j]; }
+    }
+    atomicAdd(gsum + (long long)b * wc + gi, s);
+    atomicAdd(gsq + (long long)b * wc + gi, q);
+  }
+}
+
+// ghat = (l - mean[b,g]) * rstd[b,g] * gamma[j] + beta[j]
+template <typename T, int VEC>
+__global__ void __launch_bounds__(NT_THREADS)
+gn_apply_kernel(const T* __restrict__ l, const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ out, RowsGeo g, int wc, int gc) {
+  const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
+  if (!(tx < g.cq && ty < g.ry)) return;
+  const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
+  float A[VEC], Bc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int j = tx * VEC + i, gi = gn_group(j, gc);
+    const float rs = rstd[(long long)b * wc + gi], mn = mean[(long long)b * wc + gi];
+    A[i] = rs * gamma[j];
+    Bc[i] = beta[j] - mn * A[i];
+  }
+  const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+  for (int r = r0 + ty; r < r1; r += g.ry) {
+    const Pack<T, VEC> v = ld_pack<T, VEC>(l + base + (long long)r * g.C);
+    Pack<T, VEC> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o.v[i] = Elem<T>::from(fmaf(to_acc(v.v[i]), A[i], Bc[i]));
+    st_pack<T, VEC>(out + base + (long long)r * g.C, o);
+  }
+}
+
+// backward sums: s1[b,g] += sum dg*gamma ; s2[b,g] += sum dg*gamma*lhat ; dgamma[j] += sum dg*lhat ; dbeta[j] += sum dg
+template <typename T, int VEC>
+__global__ void __launch_bounds__(NT_THREADS)
+gn_bwd_sums_kernel(const T* __restrict__ dg, const T* __restrict__ l, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ s1,
+                   float* __restrict__ s2, float* __restrict__ dgamma, float* __restrict__ dbeta, RowsGeo g, int wc, int gc) {
+  extern __shared__ float sm[];
+  const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
+  const bool active = tx < g.cq && ty < g.ry;
+  const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
+  float acc[2][VEC], mn[VEC], rs[VEC];    // acc[0] = sum dg ; acc[1] = sum dg*lhat   (per column j)
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    acc[0][i] = acc[1][i] = 0.f;
+    const int gi = active ? gn_group(tx * VEC + i, gc) : 0;
+    mn[i] = active ? mean[(long long)b * wc + gi] : 0.f; rs[i] = active ? rstd[(long long)b * wc + gi] : 0.f;
+  }
+  if (active) {
+    const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+    for (int r = r0 + ty; r < r1; r += g.ry) {
+      const Pack<T, VEC> dv = ld_pack<T, VEC>(dg + base + (long long)r * g.C);
+      const Pack<T, VEC> lv = ld_pack<T, VEC>(l + base + (long long)r * g.C);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float d = to_acc(dv.v[i]);
+        acc[0][i] += d;
+        acc[1][i] = fmaf(d, (to_acc(lv.v[i]) - mn[i]) * rs[i], acc[1][i]);
+      }
+    }
+  }
+  cta_col_reduce<2, VEC>(acc, sm, g, tx, ty, active);
+  for (int j = threadIdx.x; j < g.C; j += NT_THREADS) {
+    atomicAdd(dbeta + j, sm[j]);
+    atomicAdd(dgamma + j, sm[g.ry * g.C + j]);
+  }
+  for (int gi = threadIdx.x; gi < wc; gi += NT_THREADS) {
+    float a = 0.f, q = 0.f;
+    for (int t = 0; t < 9; ++t) {
+      const int j = gc <= 0 ? gi * 9 + t : ((gi / gc) * 9 + t) * gc + gi % gc;
+      a = fmaf(sm[j], gamma[j], a);
+      q = fmaf(sm[g.ry * g.C + j], gamma[j], q);
+    }
+    atomicAdd(s1 + (long long)b * wc + gi, a);
+    atomicAdd(s2 + (long long)b * wc + gi, q);
+  }
+}
+
+// dl = rstd * ( dg*gamma - s1/n - lhat * s2/n ),  n = 9*HW
+template <typename T, int VEC>
+__global__ void __launch_bounds__(NT_THREADS)
+gn_bwd_apply_kernel(const T* __restrict__ dg, const T* __restrict__ l, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ s1,
+                    const float* __restrict__ s2, T* __restrict__ dl, RowsGeo g, int wc, int gc) {
+  const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
+  if (!(tx < g.cq && ty < g.ry)) return;
+  const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
+  const float inv_n = 1.f / (9.f * (float)g.HW);
+  float mn[VEC], rs[VEC], ga[VEC], k1[VEC], k2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int j = tx * VEC + i, gi = gn_group(j, gc);
+    mn[i] = mean[(long long)b * wc + gi]; rs[i] = rstd[(long long)b * wc + gi]; ga[i] = gamma[j];
+    k1[i] = s1[(long long)b * wc + gi] * inv_n; k2[i] = s2[(long long)b * wc + gi] * inv_n;
+  }
+  const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+  for (int r = r0 + ty; r < r1; r += g.ry) {
+    const Pack<T, VEC> dv = ld_pack<T, VEC>(dg + base + (long long)r * g.C);
+    const Pack<T, VEC> lv = ld_pack<T, VEC>(l + base + (long long)r * g.C);
+    Pack<T, VEC> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float lh = (to_acc(lv.v[i]) - mn[i]) * rs[i];
+      o.v[i] = Elem<T>::from(rs[i] * (to_acc(dv.v[i]) * ga[i] - k1[i] - lh * k2[i]));
+    }
+    st_pack<T, VEC>(dl + base + (long long)r * g.C, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+template <typename T>
+static int pick_vec(int C, const void* p0, const void* p1 = nullptr, const void* p2 = nullptr, const void* p3 = nullptr) {
+  for (int vec = 16 / (int)sizeof(T); vec >= 1; vec >>= 1) {
+    if (C % vec) continue;
+    const uintptr_t m = (uintptr_t)(vec * sizeof(T)) - 1;
+    auto ok = [&](const void* p) { return !p || ((uintptr_t)p & m) == 0; };
+    if (ok(p0) && ok(p1) && ok(p2) && ok(p3)) return vec;
+  }
+  return 1;
+}
+
+static int make_geo(RowsGeo& g, int B, int HW, int C, int vec, int nsums, size_t* smem) {
+  if (B <= 0 || HW <= 0 || C <= 0) { set_error("norm/tail kernel: non-positive dims"); return COTB200_EINVAL; }
+  g.B = B; g.HW = HW; g.C = C; g.cq = C / vec;
+  g.cq_pad = 1;
+  while (g.cq_pad < g.cq) g.cq_pad <<= 1;
+  if (g.cq_pad > NT_THREADS) { set_error("norm/tail kernel: %d channels exceed the %d-packet row limit", C, NT_THREADS); return COTB200_EINVAL; }
+  g.ry = NT_THREADS / g.cq_pad;
+  // rows per CTA: enough CTAs to fill the machine (>= ~6 waves of 148), at least 2 rows per lane when possible
+  long long want = (long long)num_sms() * 6;
+  int chunks = (int)((want + B - 1) / B);
+  if (chunks < 1) chunks = 1;
+  int rows = (HW + chunks - 1) / chunks;
+  const int min_rows = g.ry * 4;
+  if (rows < min_rows) rows = min_rows;
+  if (rows > HW) rows = HW;
+  g.rows_per_cta = rows;
+  *smem = (size_t)nsums * g.ry * C * sizeof(float);
+  if (*smem > 96 * 1024) { set_error("norm/tail kernel: shared memory %zu too large", *smem); return COTB200_EINVAL; }
+  return 0;
+}
+
+#define NT_DISPATCH_VEC(vec, ...)                                  \
+  switch (vec) {                                                   \
+    case 8: if constexpr (sizeof(T) == 2) { constexpr int V = 8; __VA_ARGS__; } break; \
+    case 4: { constexpr int V = 4; __VA_ARGS__; } break;           \
+    case 2: { constexpr int V = 2; __VA_ARGS__; } break;           \
+    default: { constexpr int V = 1; __VA_ARGS__; } break;          \
+  }
+
+template <typename KFn>
+static int ensure_smem(KFn fn, size_t smem) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  return 0;
+}
+
+}  // namespace cotb200
+
+using namespace cotb200;
+
+#define NT_GRID dim3((g.HW + g.rows_per_cta - 1) / g.rows_per_cta, g.B)
+
+extern "C" int cotb200_col_stats(int dtype, int B, int HW, int C, const void* x, float* sum, float* sq, void* stream) {
+  if (!x || !sum || !sq) { set_error("col_stats: NULL pointer"); return COTB200_ENULL; }
+  if (dtype == COTB200_F64) { set_error("col_stats: fp64 not supported"); return COTB200_EDTYPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  COTB200_DISPATCH_DTYPE(dtype, {
+    if constexpr (!std::is_same<T, double>::value) {
+      const int vec = pick_vec<T>(C, x);
+      RowsGeo g; size_t smem;
+      int rc = make_geo(g, B, HW, C, vec, 2, &smem);
+      if (rc) return rc;
+      COTB200_PROF("col_stats");
+      NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(col_stats_kernel<T, V>, smem))) return rc;
+                             col_stats_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)x, sum, sq, g); });
+      return check_launch("col_stats");
+    }
+  });
+  return 0;
+}
+
+extern "C" int cotb200_tail_pool(int dtype, int B, int HW, int C, const void* u, const void* k, const float* scale,
+                                 const float* shift, float* psum, void* stream) {
+  if (!u || !k || !scale || !shift || !psum) { set_error("tail_pool: NULL pointer"); return COTB200_ENULL; }
+  if (dtype == COTB200_F64) { set_error("tail_pool: fp64 not supported"); return COTB200_EDTYPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  COTB200_DISPATCH_DTYPE(dtype, {
+    if constexpr (!std::is_same<T, double>::value) {
+      const int vec = pick_vec<T>(C, u, k);
+      RowsGeo g; size_t smem;
+      int rc = make_geo(g, B, HW, C, vec, 1, &smem);
+      if (rc) return rc;
+      COTB200_PROF("tail_pool");
+      NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(tail_pool_kernel<T, V>, smem))) return rc;
+                             tail_pool_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)u, (const T*)k, scale, shift, psum, g); });
+      return check_launch("tail_pool");
+    }
+  });
+  return 0;
+}
+
+extern "C" int cotb200_tail_combine(int dtype, int B, int HW, int C, const void* u, const void* k, const float* scale,
+                                    const float* shift, const float* a, void* out, void* stream) {
+  if (!u || !k || !scale || !shift || !a || !out) { set_error("tail_combine: NULL pointer"); return COTB200_ENULL; }
+  if (dtype == COTB200_F64) { set_error("tail_combine: fp64 not supported"); return COTB200_EDTYPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  COTB200_DISPATCH_DTYPE(dtype, {
+    if constexpr (!std::is_same<T, double>::value) {
+      const int vec = pick_vec<T>(C, u, k, out);
+      RowsGeo g; size_t smem;
+      int rc = make_geo(g, B, HW, C, vec, 1, &smem);
+      if (rc) return rc;
+      COTB200_PROF("tail_combine");
+      NT_DISPATCH_VEC(vec, { tail_combine_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)u, (const T*)k, scale, shift, a, (T*)out, g); });
+      return check_launch("tail_combine");
+    }
+  });
+  return 0;
+}
+
+extern "C" int cotb200_tail_bwd_sums(int dtype, int B, int HW, int C, const void* dout, const void* u, const void* k,
+                                     const float* scale, const float* shift, float* S, void* stream) {
+  if (!dout || !u || !k || !scale || !shift || !S) { set_error("tail_bwd_sums: NULL pointer"); return COTB200_ENULL; }
+  if (dtype == COTB200_F64) { set_error("tail_bwd_sums: fp64 not supported"); return COTB200_EDTYPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  COTB200_DISPATCH_DTYPE(dtype, {
+    if constexpr (!std::is_same<T, double>::value) {
+      const int vec = pick_vec<T>(C, dout, u, k);
+      RowsGeo g; size_t smem;
+      int rc = make_geo(g, B, HW, C, vec, 2, &smem);
+      if (rc) return rc;
+      COTB200_PROF("tail_bwd_sums");
+      NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(tail_bwd_sums_kernel<T, V>, smem))) return rc;
+                             tail_bwd_sums_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dout, (const T*)u, (const T*)k, scale, shift, S, g); });
+      return check_launch("tail_bwd_sums");
+    }
+  });
+  return 0;
+}
+
+extern "C" int cotb200_tail_bwd_dz_sums(int dtype, int B, int HW, int C, const void* dout, const void* u, const float* scale,
+                                        const float* shift, const float* mu, const float* rstd, const float* a,
+                                        const float* dpn, float* sum_dz, float* sum_dzx, void* stream) {
+  if (!dout || !u || !scale || !shift || !mu || !rstd || !a || !dpn || !sum_dz || !sum_dzx) { set_error("tail_bwd_dz_sums: NULL pointer"); return COTB200_ENULL; }
+  if (dtype == COTB200_F64) { set_error("tail_bwd_dz_sums: fp64 not supported"); return COTB200_EDTYPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  COTB200_DISPATCH_DTYPE(dtype, {
+    if constexpr (!std::is_same<T, double>::value) {
+      const int vec = pick_vec<T>(C, dout, u);
+      RowsGeo g; size_t smem;
+      int rc = make_geo(g, B, HW, C, vec, 2, &smem);
+      if (rc) return rc;
+      COTB200_PROF("tail_bwd_dz_sums");
+      NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(tail_bwd_dz_sums_kernel<T, V>, smem))) return rc;
+                             tail_bwd_dz_sums_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dout, (const T*)u, scale, shift, mu, rstd, a, dpn, sum_dz, sum_dzx, g); });
+      return check_launch("tail_bwd_dz_sums");
+    }
+  });
+  return 0;
+}
+
+extern "C" int cotb200_tail_bwd_apply(int dtype, int B, int HW, int C, const void* dout, const void* u, const float* scale,
+                                      const float* shift, const float* mu, const float* rstd, const float* a,
+                                      const float* dpn, const float* c1, const float* c2, void* du, void* dk, void* stream) {
+  if (!dout || !u || !scale || !shift || !mu || !rstd || !a || !dpn || !du || !dk) { set_error("tail_bwd_apply: NULL pointer"); return COTB200_ENULL; }
+  if (dtype == COTB200_F64) { set_error("tail_bwd_apply: fp64 not supported"); return COTB200_EDTYPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  COTB200_DISPATCH_DTYPE(dtype, {
+    if constexpr (!std::is_same<T, double>::value) {
+      const int vec = pick_vec<T>(C, dout, u, du, dk);
+      RowsGeo g; size_t smem;
+      int rc = make_geo(g, B, HW, C, vec, 1, &smem);
+      if (rc) return rc;
+      COTB200_PROF("tail_bwd_apply");
+      NT_DISPATCH_VEC(vec, { tail_bwd_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dout, (const T*)u, scale, shift, mu, rstd, a, dpn, c1, c2, (T*)du, (T*)dk, g); });
+      return check_launch("tail_bwd_apply");
+    }
+  });
+  return 0;
+}
+
+extern "C" int cotb200_gn9_stats(int dtype, int B, int HW, int wc, int gc, const void* l, float* gsum, float* gsq, void* stream) {
+  if (!l || !gsum || !gsq) { set_error("gn9_stats: NULL pointer"); return COTB200_ENULL; }
+  if (dtype == COTB200_F64) { set_error("gn9_stats: fp64 not supported"); return COTB200_EDTYPE; }
+  if (gc > 0 && wc % gc) { set_error("gn9: gc %d does not divide wc %d", gc, wc); return COTB200_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int J = 9 * wc;
+  COTB200_DISPATCH_DTYPE(dtype, {
+    if constexpr (!std::is_same<T, double>::value) {
+      const int vec = pick_vec<T>(J, l);
+      RowsGeo g; size_t smem;
+      int rc = make_geo(g, B, HW, J, vec, 2, &smem);
+      if (rc) return rc;
+      COTB200_PROF("gn9_stats");
+      NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(gn_stats_kernel<T, V>, smem))) return rc;
+                             gn_stats_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)l, gsum, gsq, g, wc, gc); });
+      return check_launch("gn9_stats");
+    }
+  });
+  return 0;
+}
+
+extern "C" int cotb200_gn9_apply(int dtype, int B, int HW, int wc, int gc, const void* l, const float* mean, const float* rstd,
+                                 const float* gamma, const float* beta, void* out, void* stream) {
+  if (!l || !mean || !rstd || !gamma || !beta || !out) { set_error("gn9_apply: NULL pointer"); return COTB200_ENULL; }
+  if (dtype == COTB200_F64) { set_error("gn9_apply: fp64 not supported"); return COTB200_EDTYPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int J = 9 * wc;
+  COTB200_DISPATCH_DTYPE(dtype, {
+    if constexpr (!std::is_same<T, double>::value) {
+      const int vec = pick_vec<T>(J, l, out);
+      RowsGeo g; size_t smem;
+      int rc = make_geo(g, B, HW, J, vec, 1, &smem);
+      if (rc) return rc;
+      COTB200_PROF("gn9_apply");
+      NT_DISPATCH_VEC(vec, { gn_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)l, mean, rstd, gamma, beta, (T*)out, g, wc, gc); });
+      return check_launch("gn9_apply");
+    }
+  });
+  return 0;
+}
+
+extern "C" int cotb200_gn9_bwd_sums(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* mean,
+                                    const float* rstd, const float* gamma, float* s1, float* s2, float* dgamma, float* dbeta,
+                                    void* stream) {
+  if (!dg || !l || !mean || !rstd || !gamma || !s1 || !s2 || !dgamma || !dbeta) { set_error("gn9_bwd_sums: NULL pointer"); return COTB200_ENULL; }
+  if (dtype == COTB200_F64) { set_error("gn9_bwd_sums: fp64 not supported"); return COTB200_EDTYPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int J = 9 * wc;
+  COTB200_DISPATCH_DTYPE(dtype, {
+    if constexpr (!std::is_same<T, double>::value) {
+      const int vec = pick_vec<T>(J, dg, l);
+      RowsGeo g; size_t smem;
+      int rc = make_geo(g, B, HW, J, vec, 2, &smem);
+      if (rc) return rc;
+      COTB200_PROF("gn9_bwd_sums");
+      NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(gn_bwd_sums_kernel<T, V>, smem))) return rc;
+                             gn_bwd_sums_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dg, (const T*)l, mean, rstd, gamma, s1, s2, dgamma, dbeta, g, wc, gc); });
+      return check_launch("gn9_bwd_sums");
+    }
+  });
+  return 0;
+}
+
+extern "C" int cotb200_gn9_bwd_apply(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* mean,
+                                     const float* rstd, const float* gamma, const float* s1, const float* s2, void* dl,
+                                     void* stream) {
+  if (!dg || !l || !mean || !rstd || !gamma || !s1 || !s2 || !dl) { set_error("gn9_bwd_apply: NULL pointer"); return COTB200_ENULL; }
+  if (dtype == COTB200_F64) { set_error("gn9_bwd_apply: fp64 not supported"); return COTB200_EDTYPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int J = 9 * wc;
+  COTB200_DISPATCH_DTYPE(dtype, {
+    if constexpr (!std::is_same<T, double>::value) {
+      const int vec = pick_vec<T>(J, dg, l, dl);
+      RowsGeo g; size_t smem;
+      int rc = make_geo(g, B, HW, J, vec, 1, &smem);
+      if (rc) return rc;
+      COTB200_PROF("gn9_bwd_apply");
+      NT_DISPATCH_VEC(vec, { gn_bwd_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dg, (const T*)l, mean, rstd, gamma, s1, s2, (T*)dl, g, wc, gc); });
+      return check_launch("gn9_bwd_apply");
+    }
+  });
+  return 0;
+}

@@ -1,0 +1,435 @@
+// tcgen05 / TMEM / TMA GEMM family for the dense contractions of the CoT block (sm_100a only).
+//
+//   plain mode : D[M,N] = epi( A1[M,K1] * B1[N,K1]^T  (+ A2[M,K2] * B2[N,K2]^T) )
+//                1x1 convolutions on NHWC activations (rows = pixels).  The optional second operand pair is the
+//                concat-free form of  embed.0( cat[x, k] )  (/root/reference/models/cotnet.py:81,52).
+//   conv mode  : 3x3 / pad 1 / stride 1 grouped convolution as an im2col-FREE implicit GEMM: for each tap the A
+//                tile is a 4-D TMA box {64 ch, W, hbox, bbox} of the NHWC input fetched at the tap's (dh,dw) offset;
+//                TMA's out-of-bounds zero fill IS the zero padding (key_embed.0, models/cotnet.py:44).
+//   epilogue   : per-column scale/shift (folded BatchNorm or bias), optional ReLU, bf16 store; optional per-column
+//                sum / sum-of-squares of the raw accumulator (training-mode BatchNorm statistics) reduced with a
+//                butterfly transpose-reduce in registers, one global atomic per column per CTA.
+//
+// Structure (one CTA per 128-row x BN-col tile, 192 threads):
+//   warp 0  : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem stages, mbarrier complete_tx)
+//   warp 1  : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, bf16 -> fp32 in TMEM)
+//   warps 2-5: epilogue (tcgen05.ld 32x32b, one TMEM lane quadrant per warp)
+// All mbarrier waits are bounded (trap instead of hanging the GPU).
+#include <cuda.h>
+#include "common.cuh"
+
+namespace cotb200 {
+
+static constexpr int TC_BM = 128;      // UMMA M (cta_group::1)
+static constexpr int TC_BK = 64;       // 64 bf16 = 128 B = one swizzle atom
+static constexpr int TC_STAGES = 4;
+static constexpr int TC_THREADS = 192;
+
+struct TcParams {
+  int M, N;                 // valid rows (pixels) / output channels
+  int rows_per_tile;        // D rows per CTA (128 plain; rows of the pixel box in conv mode)
+  int bn;                   // N tile (multiple of 16, <= 256)
+  int mode;                 // 0 plain, 1 conv3x3
+  int kb1, kb2;             // plain: 64-wide k-blocks of operand pair 1 / 2
+  int H, W, B, hbox, bbox;  // conv geometry
+  int kc;                   // conv: 64-channel chunks per tap (= bn / 64)
+  int relu;
+  long long ldd;            // D row pitch (elements)
+  __nv_bfloat16* D;
+  const float* scale;       // [N] or null (=1)
+  const float* shift;       // [N] or null (=0)
+  float* col_sum;           // [N] or null
+  float* col_sqsum;         // [N] or null
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (int spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spin > (1 << 22)) __trap();   // never hang the GPU: a broken pipeline aborts the launch
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO unused (=1), version 1.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
+__device__ __forceinline__ uint32_t umma_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Butterfly transpose-reduce: each lane holds 32 column values of ITS row; afterwards lane j holds the sum over
+// the warp's 32 rows of column j.  31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_bytes = TC_BM * TC_BK * 2;             // 16 KB
+  const int b_bytes = p.bn * TC_BK * 2;
+  const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
+  __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_accum;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_sum[256], s_sq[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, n0 = blockIdx.y * p.bn;
+  const int nkb = p.mode == 0 ? p.kb1 + p.kb2 : 9 * p.kc;
+
+  // tile -> first pixel row
+  int b0 = 0, h0 = 0;
+  long long m0;
+  int rows_valid;
+  if (p.mode == 0) {
+    m0 = (long long)tile_m * TC_BM;
+    rows_valid = (int)min((long long)TC_BM, (long long)p.M - m0);
+  } else if (p.bbox == 1) {
+    const int tps = (p.H + p.hbox - 1) / p.hbox;
+    b0 = tile_m / tps; h0 = (tile_m % tps) * p.hbox;
+    m0 = ((long long)b0 * p.H + h0) * p.W;
+    rows_valid = min(p.hbox, p.H - h0) * p.W;
+  } else {
+    b0 = tile_m * p.bbox;
+    m0 = (long long)b0 * p.H * p.W;
+    rows_valid = min(p.bbox, p.B - b0) * p.H * p.W;
+  }
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB1) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
+    mbar_init(smem_u32(&s_accum), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t ncols = 32;
+  while ((int)ncols < p.bn) ncols <<= 1;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 256; i += TC_THREADS) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(smem_u32(&s_empty[s]), ph ^ 1);
+        const uint32_t full = smem_u32(&s_full[s]);
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
+        // TMA counts the whole box (zero-filled elements included): conv boxes hold rows_per_tile <= 128 rows
+        mbar_expect_tx(full, (uint32_t)(p.rows_per_tile * TC_BK * 2 + b_bytes));
+        if (p.mode == 0) {
+          if (kb < p.kb1) {
+            tma_load_2d(sa, &mapA1, full, kb * TC_BK, (int)m0);
+            tma_load_2d(sb, &mapB1, full, kb * TC_BK, n0);
+          } else {
+            tma_load_2d(sa, &mapA2, full, (kb - p.kb1) * TC_BK, (int)m0);
+            tma_load_2d(sb, &mapB2, full, (kb - p.kb1) * TC_BK, n0);
+          }
+        } else {
+          const int tap = kb / p.kc, cc = kb % p.kc;
+          const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+          // A: 4-D box {64 ch, W, hbox, bbox}; negative / overflowing coordinates are zero-filled == zero padding
+          tma_load_4d(sa, &mapA1, full, n0 + cc * TC_BK, dw, h0 + dh, b0);
+          tma_load_2d(sb, &mapB1, full, kb * TC_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(p.bn);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(smem_u32(&s_full[s]), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
+        const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // advance 16 bf16 = 32 B inside the 128 B swizzle atom: start-address field += 2
+          umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(smem_u32(&s_empty[s]));           // frees the smem stage when the MMAs above retire
+      }
+      umma_commit(smem_u32(&s_accum));                // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (4 warps, TMEM lane quadrant = warp % 4) =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const bool row_ok = r < rows_valid && (m0 + r) < p.M;
+    mbar_wait(smem_u32(&s_accum), 0);
+    __syncwarp();
+    tc_fence_after();
+    const bool stats = p.col_sum != nullptr;
+    __nv_bfloat16* drow = p.D + (m0 + r) * p.ldd + n0;
+    for (int c = 0; c * 32 < p.bn; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), raw);
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      if (stats) {
+        float a[32], b[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { a[j] = row_ok ? v[j] : 0.f; b[j] = a[j] * a[j]; }
+        const float cs = warp_colsum32(a);
+        const float cq = warp_colsum32(b);
+        atomicAdd(&s_sum[c * 32 + lane], cs);
+        atomicAdd(&s_sq[c * 32 + lane], cq);
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          const int nb = n0 + c * 32 + j8 * 8;
+          if (nb < p.N && c * 32 + j8 * 8 < p.bn) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float lo = v[j8 * 8 + 2 * e], hi = v[j8 * 8 + 2 * e + 1];
+              const int n = nb + 2 * e;
+              if (p.scale) { lo *= __ldg(p.scale + n); hi *= __ldg(p.scale + n + 1); }
+              if (p.shift) { lo += __ldg(p.shift + n); hi += __ldg(p.shift + n + 1); }
+              if (p.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(drow + c * 32 + j8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+    }
+    if (stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");    // the 4 epilogue warps only
+      const int t = threadIdx.x - 64;
+      for (int j = t; j < p.bn; j += 128) {
+        if (n0 + j < p.N) {
+          atomicAdd(p.col_sum + n0 + j, s_sum[j]);
+          atomicAdd(p.col_sqsum + n0 + j, s_sq[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with pitch ld (elements); box {64, box_rows}, 128B swizzle, zero OOB fill
+static int make_map_2d(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return COTB200_EINVAL; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15)) { set_error("TMA operand not 16-byte aligned (ld=%lld)", ld); return COTB200_EALIGN; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d) failed: %d", (int)r); return COTB200_EINVAL; }
+  return 0;
+}
+
+// 4-D NHWC bf16 activation [B,H,W,C] (pixel pitch ldc); box {64, W, hbox, bbox}
+static int make_map_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, long long ldc, int hbox, int bbox) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return COTB200_EINVAL; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ldc * 2) & 15)) { set_error("TMA operand not 16-byte aligned"); return COTB200_EALIGN; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ldc * 2, (cuuint64_t)ldc * 2 * W, (cuuint64_t)ldc * 2 * W * H};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)W, (cuuint32_t)hbox, (cuuint32_t)bbox};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(4d) failed: %d", (int)r); return COTB200_EINVAL; }
+  return 0;
+}
+
+static int tc_launch(const CUtensorMap& a1, const CUtensorMap& b1, const CUtensorMap& a2, const CUtensorMap& b2,
+                     const TcParams& p, int m_tiles, cudaStream_t st, const char* what) {
+  const int a_bytes = TC_BM * TC_BK * 2, b_bytes = p.bn * TC_BK * 2;
+  const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
+  const int smem = TC_STAGES * stage_bytes + 1024;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured = 200 * 1024;
+  }
+  dim3 grid(m_tiles, (p.N + p.bn - 1) / p.bn);
+  COTB200_PROF(what);
+  tc_gemm_kernel<<<grid, TC_THREADS, smem, st>>>(a1, b1, a2, b2, p);
+  return check_launch(what);
+}
+
+static int pick_bn(int N) {
+  // whole N when it fits one UMMA (<= 256), else the smallest equal split; always a multiple of 16
+  int parts = (N + 255) / 256;
+  int bn = (N + parts - 1) / parts;
+  return (bn + 15) & ~15;
+}
+
+}  // namespace cotb200
+
+using namespace cotb200;
+
+// D[M,N] = epi(A1 B1^T + A2 B2^T), all bf16 row-major; see include/cotb200.h
+extern "C" int cotb200_gemm_bf16(int M, int N, int K1, const void* A1, long long lda1, const void* B1, long long ldb1,
+                                 int K2, const void* A2, long long lda2, const void* B2, long long ldb2, void* D,
+                                 long long ldd, const float* scale, const float* shift, int relu, float* col_sum,
+                                 float* col_sqsum, void* stream) {
+  if (M <= 0 || N <= 0 || K1 <= 0 || K2 < 0) { set_error("gemm_bf16: bad dims M=%d N=%d K1=%d K2=%d", M, N, K1, K2); return COTB200_EINVAL; }
+  if (!A1 || !B1 || !D || (K2 > 0 && (!A2 || !B2))) { set_error("gemm_bf16: NULL operand"); return COTB200_ENULL; }
+  if ((N & 7) || (K1 & 7) || (K2 & 7) || (ldd & 7)) { set_error("gemm_bf16: N, K, ldd must be multiples of 8"); return COTB200_EALIGN; }
+  if ((col_sum == nullptr) != (col_sqsum == nullptr)) { set_error("gemm_bf16: col_sum and col_sqsum go together"); return COTB200_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  TcParams p{};
+  p.M = M; p.N = N; p.rows_per_tile = TC_BM; p.bn = pick_bn(N); p.mode = 0;
+  p.kb1 = (K1 + TC_BK - 1) / TC_BK; p.kb2 = (K2 + TC_BK - 1) / TC_BK;
+  p.relu = relu; p.ldd = ldd; p.D = (__nv_bfloat16*)D; p.scale = scale; p.shift = shift; p.col_sum = col_sum; p.col_sqsum = col_sqsum;
+  CUtensorMap a1, b1, a2, b2;
+  int rc;
+  if ((rc = make_map_2d(&a1, A1, M, K1, lda1, TC_BM))) return rc;
+  if ((rc = make_map_2d(&b1, B1, N, K1, ldb1, p.bn))) return rc;
+  if (K2 > 0) {
+    if ((rc = make_map_2d(&a2, A2, M, K2, lda2, TC_BM))) return rc;
+    if ((rc = make_map_2d(&b2, B2, N, K2, ldb2, p.bn))) return rc;
+  } else { a2 = a1; b2 = b1; }
+  return tc_launch(a1, b1, a2, b2, p, (M + TC_BM - 1) / TC_BM, st, "tc_gemm_1x1");
+}
+
+// 3x3 / pad 1 / stride 1 convolution, NHWC bf16, with dense-per-N-tile prepared weights
+//   Wp [C_out, 9 * bn] bf16 row-major: Wp[n, (tap*kc + cc)*64 + ci] = weight of output channel n for input channel
+//   (n0(n) + cc*64 + ci) at tap (0 where that input channel is outside n's group); bn = N tile in {64,128,192,256}.
+extern "C" int cotb200_conv3x3_bf16(int B, int H, int W, int C, const void* X, long long ldx, const void* Wp, int bn, void* D,
+                                    long long ldd, const float* scale, const float* shift, int relu, float* col_sum,
+                                    float* col_sqsum, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0) { set_error("conv3x3_bf16: bad dims"); return COTB200_EINVAL; }
+  if (!X || !Wp || !D) { set_error("conv3x3_bf16: NULL operand"); return COTB200_ENULL; }
+  if (bn % 64 || bn > 256 || C % bn) { set_error("conv3x3_bf16: N tile %d must be a multiple of 64 dividing C=%d", bn, C); return COTB200_EINVAL; }
+  if (W > 128) { set_error("conv3x3_bf16: W=%d > 128 not supported by the pixel-box tiling", W); return COTB200_EINVAL; }
+  if ((col_sum == nullptr) != (col_sqsum == nullptr)) { set_error("conv3x3_bf16: col_sum and col_sqsum go together"); return COTB200_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  TcParams p{};
+  p.M = B * H * W; p.N = C; p.bn = bn; p.mode = 1; p.kc = bn / 64;
+  p.H = H; p.W = W; p.B = B;
+  int m_tiles;
+  if (H * W <= TC_BM / 2) {                      // several whole samples per tile (7x7: 2 samples = 98 rows)
+    p.bbox = TC_BM / (H * W); p.hbox = H;
+    m_tiles = (B + p.bbox - 1) / p.bbox;
+  } else {                                       // a band of whole rows of one sample
+    p.bbox = 1;
+    int hb = TC_BM / W; if (hb > H) hb = H; if (hb < 1) hb = 1;
+    while (H % hb) --hb;                         // bands tile the sample exactly
+    p.hbox = hb;
+    m_tiles = B * (H / hb);
+  }
+  p.rows_per_tile = p.bbox * p.hbox * W;
+  p.relu = relu; p.ldd = ldd; p.D = (__nv_bfloat16*)D; p.scale = scale; p.shift = shift; p.col_sum = col_sum; p.col_sqsum = col_sqsum;
+  CUtensorMap a1, b1;
+  int rc;
+  if ((rc = make_map_nhwc(&a1, X, B, H, W, C, ldx, p.hbox, p.bbox))) return rc;
+  if ((rc = make_map_2d(&b1, Wp, C, 9LL * bn, 9LL * bn, bn))) return rc;
+  return tc_launch(a1, b1, a1, b1, p, m_tiles, st, "tc_conv3x3");
+}

@@ -1,0 +1,79 @@
+"""Thin torch-side wrappers of the tcgen05 GEMM / implicit-GEMM conv entry points (include/cotb200.h).
+
+These are plumbing for the fused CoT block and for the unit tests: they allocate outputs with torch, pass raw
+pointers + the current stream to the C ABI, and never fall back to cuBLAS/cuDNN."""
+import torch
+
+from . import _lib
+
+
+def _rows(t: torch.Tensor):
+    """[M, K] view of a 2-D tensor or of a channels_last 4-D activation ([B,C,H,W] with NHWC memory)."""
+    if t.dim() == 2:
+        assert t.stride(1) == 1
+        return t.shape[0], t.shape[1], t.stride(0)
+    assert t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
+    B, C, H, W = t.shape
+    return B * H * W, C, C
+
+
+def gemm_bf16(a1, b1, a2=None, b2=None, scale=None, shift=None, relu=False, stats=None, out=None):
+    """D[M,N] = epi(a1 @ b1.T (+ a2 @ b2.T)); bf16 in/out, fp32 accumulate.  stats=(col_sum, col_sqsum) fp32 [N],
+    accumulated in place.  a* may be 2-D row-major or channels_last activations (rows = pixels)."""
+    M, K1, lda1 = _rows(a1)
+    N, K1b = b1.shape
+    assert K1 == K1b and a1.dtype == torch.bfloat16 and b1.dtype == torch.bfloat16 and b1.stride(1) == 1
+    K2, lda2, ldb2 = 0, 0, 0
+    if a2 is not None:
+        M2, K2, lda2 = _rows(a2)
+        assert M2 == M and b2.shape == (N, K2) and b2.stride(1) == 1
+        ldb2 = b2.stride(0)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a1.device)
+    assert out.stride(-1) == 1
+    cs, cq = (stats if stats is not None else (None, None))
+    rc = _lib.load().cotb200_gemm_bf16(M, N, K1, a1.data_ptr(), lda1, b1.data_ptr(), b1.stride(0), K2, _lib.ptr(a2), lda2,
+                                       _lib.ptr(b2), ldb2, out.data_ptr(), out.stride(0), _lib.ptr(scale), _lib.ptr(shift),
+                                       1 if relu else 0, _lib.ptr(cs), _lib.ptr(cq), _lib.stream_ptr(a1))
+    _lib.check(rc, "gemm_bf16")
+    return out
+
+
+def conv_tile(C, groups):
+    """N tile (output channels per CTA) used by conv3x3_bf16 for a grouped conv, or None if unsupported."""
+    cg = C // groups
+    for bn in (64, 128, 192, 256):
+        if C % bn == 0 and (bn % cg == 0):
+            return bn
+    return None
+
+
+def prepare_conv3x3_weight(weight, groups, transpose_for_dgrad=False):
+    """[C, C/groups, 3, 3] -> Wp [C, 9*bn] bf16 (dense inside each N tile, zero outside the group); see cotb200.h.
+    transpose_for_dgrad: build the weight of the data-gradient convolution (taps flipped, in/out swapped per group)."""
+    C, cg = weight.shape[0], weight.shape[1]
+    bn = conv_tile(C, groups)
+    assert bn is not None, "unsupported grouped-conv geometry for the tcgen05 path"
+    w = weight.detach().float().view(groups, cg, cg, 3, 3)            # [g, out, in, kh, kw]
+    if transpose_for_dgrad:
+        w = w.permute(0, 2, 1, 3, 4).flip(3, 4)                       # dX = conv(dY, W^T flipped)
+    w = w.reshape(C, cg, 9)
+    Wp = torch.zeros(C, 9, bn, dtype=torch.float32, device=weight.device)
+    n = torch.arange(C, device=weight.device)
+    off = (n // cg) * cg - (n // bn) * bn                              # first input channel of n's group inside the tile
+    idx = off[:, None] + torch.arange(cg, device=weight.device)[None, :]          # [C, cg]
+    Wp.scatter_(2, idx[:, None, :].expand(C, 9, cg), w.permute(0, 2, 1))
+    return Wp.reshape(C, 9 * bn).to(torch.bfloat16).contiguous(), bn
+
+
+def conv3x3_bf16(x, wp, bn, scale=None, shift=None, relu=False, stats=None, out=None):
+    """x: channels_last bf16 [B,C,H,W]; returns channels_last bf16 [B,C,H,W]."""
+    assert x.dim() == 4 and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+    B, C, H, W = x.shape
+    if out is None:
+        out = torch.empty_like(x, memory_format=torch.channels_last)
+    cs, cq = (stats if stats is not None else (None, None))
+    rc = _lib.load().cotb200_conv3x3_bf16(B, H, W, C, x.data_ptr(), C, wp.data_ptr(), bn, out.data_ptr(), C, _lib.ptr(scale),
+                                          _lib.ptr(shift), 1 if relu else 0, _lib.ptr(cs), _lib.ptr(cq), _lib.stream_ptr(x))
+    _lib.check(rc, "conv3x3_bf16")
+    return out

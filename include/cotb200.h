@@ -99,6 +99,66 @@ int cotb200_agg_zeropad_mix_bwd(const cotb200_agg_desc* d, int k2h, int k2w, int
                                 const void* dy, const void* x, const void* w1, const void* w2,
                                 void* dx, void* dw1, void* dw2, void* stream);
 
+/* ---- fused normalisation / split-attention kernels on NHWC tensors [B, HW, C] (channel contiguous), fp32 math ----
+ * They replace chains of eager launches of the reference block (models/cotnet.py:56 and :89-104).
+ * dtype: COTB200_F32 / BF16 / F16.  All float* arguments are fp32 device arrays; sums are ACCUMULATED (+=) with
+ * atomics, so the caller zeroes them. */
+
+/* sum[c] += sum_rows x, sq[c] += sum_rows x^2 : BatchNorm batch statistics (nn.BatchNorm2d training mode, :65,:89) */
+int cotb200_col_stats(int dtype, int B, int HW, int C, const void* x, float* sum, float* sq, void* stream);
+/* psum[b,c] += sum_rows( silu(u*scale+shift) + k ) : bn + SiLU (:89-90) and the pooled descriptor of :92-98 */
+int cotb200_tail_pool(int dtype, int B, int HW, int C, const void* u, const void* k, const float* scale,
+                      const float* shift, float* psum, void* stream);
+/* out = a[b,c,0]*silu(u*scale+shift) + a[b,c,1]*k : the radix-2 recombination (:101-104); a is [B,C,2] fp32 */
+int cotb200_tail_combine(int dtype, int B, int HW, int C, const void* u, const void* k, const float* scale,
+                         const float* shift, const float* a, void* out, void* stream);
+/* S[b,c,0] += sum_rows dout*y, S[b,c,1] += sum_rows dout*k : gradient of the attention weights */
+int cotb200_tail_bwd_sums(int dtype, int B, int HW, int C, const void* dout, const void* u, const void* k,
+                          const float* scale, const float* shift, float* S, void* stream);
+/* dz = (a0*dout + dpn)*silu'(z); sum_dz[c] += sum dz, sum_dzx[c] += sum dz*xhat (BatchNorm backward reductions) */
+int cotb200_tail_bwd_dz_sums(int dtype, int B, int HW, int C, const void* dout, const void* u, const float* scale,
+                             const float* shift, const float* mu, const float* rstd, const float* a, const float* dpn,
+                             float* sum_dz, float* sum_dzx, void* stream);
+/* du = scale*(dz - c1 - xhat*c2) (c1,c2 NULL in eval mode), dk = a1*dout + dpn */
+int cotb200_tail_bwd_apply(int dtype, int B, int HW, int C, const void* dout, const void* u, const float* scale,
+                           const float* shift, const float* mu, const float* rstd, const float* a, const float* dpn,
+                           const float* c1, const float* c2, void* du, void* dk, void* stream);
+/* GroupNorm(num_groups = wc, channels = 9*wc) of the attention logits (models/cotnet.py:56): group g = the 9 taps of
+ * weight channel g.  gc = 0: channel j = g*9 + t (reference order); gc > 0: tap-major chunks (COTB200_NHWC_TAP). */
+int cotb200_gn9_stats(int dtype, int B, int HW, int wc, int gc, const void* l, float* gsum, float* gsq, void* stream);
+int cotb200_gn9_apply(int dtype, int B, int HW, int wc, int gc, const void* l, const float* mean, const float* rstd,
+                      const float* gamma, const float* beta, void* out, void* stream);
+int cotb200_gn9_bwd_sums(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* mean,
+                         const float* rstd, const float* gamma, float* s1, float* s2, float* dgamma, float* dbeta,
+                         void* stream);
+int cotb200_gn9_bwd_apply(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* mean,
+                          const float* rstd, const float* gamma, const float* s1, const float* s2, void* dl, void* stream);
+
+/* ---- dense contractions of the block on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operands) ----
+ * bf16 operands, fp32 accumulation, bf16 output.  Row-major everywhere; "ld*" are row pitches in elements.
+ *
+ * cotb200_gemm_bf16:  D[M,N] = epi( A1[M,K1] B1[N,K1]^T + A2[M,K2] B2[N,K2]^T )      (K2 == 0: single product)
+ *   Replaces the 1x1 nn.Conv2d launches of the block (cuDNN in the reference): embed.0 on cat[x,k] without the
+ *   concat (models/cotnet.py:52,81), embed.3 (:55), conv1x1.0 (:60) -- rows are NHWC pixels.
+ *   epi(acc)[m,n] = relu?( acc*scale[n] + shift[n] )  (scale/shift NULL = 1/0: folded eval-mode BatchNorm or bias);
+ *   col_sum/col_sqsum (both or neither): += sum_m acc[m,n], sum_m acc[m,n]^2 of the RAW accumulator
+ *   (training-mode BatchNorm batch statistics, models/cotnet.py:45,53,61).
+ *   Requirements: N, K1, K2, ldd multiples of 8; operands 16-byte aligned. */
+int cotb200_gemm_bf16(int M, int N, int K1, const void* A1, long long lda1, const void* B1, long long ldb1,
+                      int K2, const void* A2, long long lda2, const void* B2, long long ldb2,
+                      void* D, long long ldd, const float* scale, const float* shift, int relu,
+                      float* col_sum, float* col_sqsum, void* stream);
+
+/* cotb200_conv3x3_bf16: 3x3 / stride 1 / zero-pad 1 grouped convolution on an NHWC bf16 tensor X[B,H,W,C] (pixel pitch
+ *   ldx) as an im2col-free implicit GEMM; replaces key_embed.0 = nn.Conv2d(dim, dim, 3, padding=1, groups=4)
+ *   (models/cotnet.py:44) and, with transposed/flipped weights, its data gradient.
+ *   Wp [C, 9*bn] is the weight prepared per N tile of bn output channels (bn in {64,128,192,256}, bn | C, every
+ *   group inside one tile): Wp[n, (tap*(bn/64) + cc)*64 + ci] multiplies input channel (n/bn)*bn + cc*64 + ci at tap
+ *   (tap = 3*kh + kw), zero for channels outside n's group.  Same epilogue as cotb200_gemm_bf16. */
+int cotb200_conv3x3_bf16(int B, int H, int W, int C, const void* X, long long ldx, const void* Wp, int bn,
+                         void* D, long long ldd, const float* scale, const float* shift, int relu,
+                         float* col_sum, float* col_sqsum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

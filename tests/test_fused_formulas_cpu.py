@@ -1,0 +1,89 @@
+"""CPU check of the closed-form backward formulas implemented by csrc/norm_tail.cu (GroupNorm-of-9-taps and the
+radix-2 tail), restated here in torch fp64 and compared with autograd.  Guards the kernel maths before GPU time is
+spent; the kernels themselves are checked against the oracle in the -m gpu tests."""
+import torch
+
+
+def test_groupnorm9_backward_formula():
+    torch.manual_seed(0)
+    B, wc, HW = 3, 4, 10
+    J = 9 * wc
+    l = torch.randn(B, HW, J, dtype=torch.float64, requires_grad=True)
+    gamma = torch.rand(J, dtype=torch.float64) + 0.5
+    beta = torch.randn(J, dtype=torch.float64)
+    gamma.requires_grad_(True); beta.requires_grad_(True)
+    eps = 1e-5
+    # reference: nn.GroupNorm semantics on [B, J, HW]
+    ref = torch.nn.functional.group_norm(l.permute(0, 2, 1), wc, gamma, beta, eps).permute(0, 2, 1)
+    dg = torch.randn_like(ref)
+    gl, gg, gb = torch.autograd.grad(ref, (l, gamma, beta), dg)
+    # kernel maths (gn_stats / gn_bwd_sums / gn_bwd_apply)
+    with torch.no_grad():
+        n = 9.0 * HW
+        lg = l.view(B, HW, wc, 9)
+        mean = lg.sum((1, 3)) / n
+        var = (lg * lg).sum((1, 3)) / n - mean * mean
+        rstd = torch.rsqrt(var + eps)
+        lhat = (lg - mean[:, None, :, None]) * rstd[:, None, :, None]
+        dgg = dg.view(B, HW, wc, 9)
+        gam = gamma.view(wc, 9)
+        s1 = (dgg * gam).sum((1, 3))
+        s2 = (dgg * gam * lhat).sum((1, 3))
+        dl = rstd[:, None, :, None] * (dgg * gam - (s1 / n)[:, None, :, None] - lhat * (s2 / n)[:, None, :, None])
+        dgamma = (dgg * lhat).sum((0, 1)).view(J)
+        dbeta = dgg.sum((0, 1)).view(J)
+    assert (dl.reshape(B, HW, J) - gl).abs().max() < 1e-10
+    assert (dgamma - gg).abs().max() < 1e-10 and (dbeta - gb).abs().max() < 1e-10
+
+
+def test_tail_backward_formula():
+    torch.manual_seed(1)
+    B, C, HW = 4, 6, 7
+    A = 5
+    u = torch.randn(B, HW, C, dtype=torch.float64, requires_grad=True)
+    k = torch.relu(torch.randn(B, HW, C, dtype=torch.float64)).requires_grad_(True)
+    gw = (torch.rand(C, dtype=torch.float64) + 0.5).requires_grad_(True)
+    gb = torch.randn(C, dtype=torch.float64).requires_grad_(True)
+    W1 = torch.randn(A, C, dtype=torch.float64, requires_grad=True)
+    W2 = torch.randn(2 * C, A, dtype=torch.float64, requires_grad=True)
+    eps = 1e-5
+
+    def se(p):
+        return torch.relu(p @ W1.t()) @ W2.t()
+
+    # reference graph (training-mode BN over B*HW rows)
+    mean = u.mean((0, 1)); var = u.var((0, 1), unbiased=False)
+    z = (u - mean) / torch.sqrt(var + eps) * gw + gb
+    y = z * torch.sigmoid(z)
+    p = (y + k).mean(1)
+    a = torch.softmax(se(p).view(B, C, 2), 2)
+    out = y * a[:, None, :, 0] + k * a[:, None, :, 1]
+    dout = torch.randn_like(out)
+    gu, gk, ggw, ggb = torch.autograd.grad(out, (u, k, gw, gb), dout, retain_graph=True)
+
+    # kernel maths
+    with torch.no_grad():
+        n = float(B * HW)
+        mu = u.sum((0, 1)) / n
+        va = (u * u).sum((0, 1)) / n - mu * mu
+        rstd = torch.rsqrt(va + eps)
+        scale = gw * rstd; shift = gb - mu * scale
+        zz = u * scale + shift
+        sg = torch.sigmoid(zz)
+        yy = zz * sg
+        S0 = (dout * yy).sum(1); S1 = (dout * k).sum(1)          # tail_bwd_sums
+    S = torch.stack([S0, S1], 2)
+    p_leaf = ((yy + k.detach()).sum(1) / HW).requires_grad_(True)
+    a2 = torch.softmax(se(p_leaf).view(B, C, 2), 2)
+    (dp,) = torch.autograd.grad(a2, (p_leaf,), S)
+    with torch.no_grad():
+        dpn = dp / HW
+        a0, a1 = a2[:, :, 0].detach(), a2[:, :, 1].detach()
+        dz = (a0[:, None] * dout + dpn[:, None]) * (sg * (1 + zz * (1 - sg)))
+        xhat = (u - mu) * rstd
+        sum_dz = dz.sum((0, 1)); sum_dzx = (dz * xhat).sum((0, 1))
+        du = scale * (dz - sum_dz / n - xhat * sum_dzx / n)
+        dk = a1[:, None] * dout + dpn[:, None]
+    assert (du - gu).abs().max() < 1e-10
+    assert (dk - gk).abs().max() < 1e-10
+    assert (sum_dzx - ggw).abs().max() < 1e-10 and (sum_dz - ggb).abs().max() < 1e-10

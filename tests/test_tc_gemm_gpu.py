@@ -1,0 +1,78 @@
+"""GPU tests of the tcgen05/TMA GEMM and implicit-GEMM 3x3 conv against fp32 torch math on the same
+bf16-representable operands (tolerance: bf16 output rounding, atol=rtol=1e-2)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _tc():
+    from cotnet_b200 import tc
+    return tc
+
+
+def _close(got, want, tol=1e-2):
+    got, want = got.float(), want.float()
+    err = (got - want).abs()
+    lim = tol + tol * want.abs()
+    assert bool((err <= lim).all()), "max err %.4e at |ref| %.3e" % (err.max().item(), want.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 32, 128), (3136, 72, 32), (777, 144, 64), (4096, 256, 512),
+                                   (513, 288, 128), (2048, 576, 256), (300, 512, 1024), (128, 16, 8)])
+def test_gemm_plain(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g, device="cuda").bfloat16()
+    b = (torch.randn(N, K, generator=g, device="cuda") / K ** 0.5).bfloat16()
+    d = _tc().gemm_bf16(a, b)
+    _close(d, a.float() @ b.float().t())
+
+
+def test_gemm_two_pairs_epilogue_and_stats():
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K1, K2 = 3000, 64, 128, 128
+    a1 = torch.randn(M, K1, generator=g, device="cuda").bfloat16()
+    a2 = torch.randn(M, K2, generator=g, device="cuda").bfloat16()
+    b = (torch.randn(N, K1 + K2, generator=g, device="cuda") / 16).bfloat16()
+    b1, b2 = b[:, :K1], b[:, K1:]                       # column slices of one weight: concat-free embed.0
+    scale = torch.rand(N, generator=g, device="cuda") + 0.5
+    shift = torch.randn(N, generator=g, device="cuda")
+    cs = torch.zeros(N, device="cuda")
+    cq = torch.zeros(N, device="cuda")
+    d = _tc().gemm_bf16(a1, b1, a2, b2, scale=scale, shift=shift, relu=True, stats=(cs, cq))
+    acc = torch.cat([a1, a2], 1).float() @ b.float().t()
+    _close(d, torch.relu(acc * scale + shift))
+    assert torch.allclose(cs, acc.sum(0), atol=1e-1, rtol=1e-3)
+    assert torch.allclose(cq, (acc * acc).sum(0), atol=1e-1, rtol=1e-3)
+
+
+def test_gemm_channels_last_rows():
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn(3, 64, 14, 14, generator=g, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 64, generator=g, device="cuda") / 8).bfloat16()
+    d = _tc().gemm_bf16(x, w)
+    want = F.conv2d(x.float(), w.float()[:, :, None, None])
+    _close(d.view(3, 14, 14, 64).permute(0, 3, 1, 2), want)
+
+
+@pytest.mark.parametrize("C,groups,H,B", [(64, 4, 56, 2), (128, 4, 28, 3), (256, 4, 14, 3), (512, 4, 7, 5), (64, 4, 8, 2),
+                                          (64, 1, 10, 2)])
+def test_conv3x3(C, groups, H, B):
+    tc = _tc()
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    x = torch.randn(B, C, H, H, generator=g, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(C, C // groups, 3, 3, generator=g, device="cuda") / (3 * (C // groups) ** 0.5)).bfloat16()
+    wp, bn = tc.prepare_conv3x3_weight(w, groups)
+    cs = torch.zeros(C, device="cuda")
+    cq = torch.zeros(C, device="cuda")
+    d = tc.conv3x3_bf16(x, wp, bn, stats=(cs, cq))
+    want = F.conv2d(x.float(), w.float(), None, 1, 1, 1, groups)
+    _close(d, want)
+    assert torch.allclose(cs, want.sum((0, 2, 3)), atol=2e-1, rtol=2e-3)
+    # data gradient as the same kernel with transposed / flipped weights
+    wpt, bnt = tc.prepare_conv3x3_weight(w, groups, transpose_for_dgrad=True)
+    gy = torch.randn(B, C, H, H, generator=g, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    dx = tc.conv3x3_bf16(gy, wpt, bnt)
+    want_dx = torch.nn.grad.conv2d_input(x.shape, w.float(), gy.float(), 1, 1, 1, groups)
+    _close(dx, want_dx)
