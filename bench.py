@@ -115,19 +115,30 @@ def cot_layer_shapes(model, batch, res):
     return shapes
 
 
+# ALGORITHMIC elements moved per pixel by each libcotb200 kernel, in units of (C, J=9C/8); DESIGN.md section 4
+_KERNEL_ELEMS = {
+    # LocalConv: read x (C) + w (J), write y (C)   [dX: dy, w -> dx ; dW: x, dy -> dw]
+    "agg3_fwd_nhwc2": (2, 1), "agg3_dx_nhwc2": (2, 1), "agg3_dw_nhwc2": (2, 1),
+    "agg3_fwd_nhwc": (2, 1), "agg3_dx_nhwc": (2, 1), "agg3_dw_nhwc": (2, 1),
+    "agg3_fwd_nchw2": (2, 1), "agg3_bwd_nchw2_dx": (2, 1), "agg3_bwd_nchw2_dw": (2, 1), "agg3_bwd_nchw2_dxdw": (3, 2),
+    "agg_fwd_nchw_k3": (2, 1), "agg_bwd_nchw_dx": (2, 1), "agg_bwd_nchw_dw": (2, 1), "agg_bwd_nchw_dxdw": (3, 2),
+    "agg_fwd_generic": (2, 1), "agg_dx_generic": (2, 1), "agg_dw_generic": (2, 1),
+    # BatchNorm statistics of u; bn+SiLU+pool; recombination; their backward passes
+    "col_stats": (1, 0), "tail_pool": (2, 0), "tail_combine": (3, 0),
+    "tail_bwd_sums": (3, 0), "tail_bwd_dz_sums": (2, 0), "tail_bwd_apply": (4, 0),
+    # GroupNorm over the 9 taps
+    "gn9_stats": (0, 1), "gn9_apply": (0, 2), "gn9_bwd_sums": (0, 2), "gn9_bwd_apply": (0, 3),
+}
+
+
 def algorithmic_bytes(kernel, shapes, batch, esize):
-    """SURVEY.md section 8(d) / BASELINE.md section 3, summed over the step's launches of `kernel`."""
+    """SURVEY.md section 8(d) / BASELINE.md section 3, summed over the step's launches of `kernel` (one per CoT layer)."""
+    if kernel not in _KERNEL_ELEMS:
+        return None
+    nc, nj = _KERNEL_ELEMS[kernel]
     tot = 0
     for (C, H, W, fold) in shapes:
-        px = H * W * batch
-        if kernel.startswith("agg3_fwd") or kernel.startswith("agg_fwd") or kernel in ("agg3_dx_nhwc", "agg3_dw_nhwc",
-                                                                                      "agg_bwd_nchw_dx", "agg_bwd_nchw_dw",
-                                                                                      "agg_dx_generic", "agg_dw_generic"):
-            tot += (2 * C + 9 * C // 8) * px * esize
-        elif kernel == "agg_bwd_nchw_dxdw":
-            tot += (3 * C + 2 * (9 * C // 8)) * px * esize
-        else:
-            return None
+        tot += (nc * C + nj * (9 * C // 8)) * H * W * batch * esize
     return tot
 
 
@@ -342,8 +353,8 @@ def main_ours(a):
                                    "channels_last%s" % (a.model, R, R, B, " [FORWARD ONLY diagnostic]" if a.fwd_only else ""),
                        "global_batch": B * world, "parallelism": "dp%d" % world,
                        "l2": "per-step working set (activations, several GB) >> 126 MB L2; no explicit flush needed",
-                       "cot_path": "libcotb200 LocalConv kernels behind aggregation_zeropad/LocalConvolution; "
-                                   "other ops of the block and the trunk: PyTorch/cuDNN"},
+                       "cot_path": "libcotb200: LocalConv fwd/dX/dW, GroupNorm(9 taps) fwd/bwd, bn+SiLU+pool+radix-2 "
+                                   "recombination fwd/bwd; the block's convolutions and the trunk: PyTorch/cuDNN"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

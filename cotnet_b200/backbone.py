@@ -15,6 +15,7 @@ import math
 import torch
 import torch.nn as nn
 
+from . import fused
 from .cot_layer import CotLayer, CoXtLayer
 
 
@@ -40,6 +41,8 @@ class Bottleneck(nn.Module):
         nn.init.zeros_(self.bn3.weight)
 
     def forward(self, x):
+        if fused.supported(x):
+            return self._forward_fused(x)
         residual = x
         x = self.act1(self.bn1(self.conv1(x)))
         if self.avd is not None:
@@ -50,6 +53,20 @@ class Bottleneck(nn.Module):
             residual = self.downsample(residual)
         x += residual
         return self.act3(x)
+
+    def _forward_fused(self, x):
+        """channels_last path: bn1+ReLU and bn3+residual+ReLU run on the fused BatchNorm
+        kernels (2 passes each way) instead of ATen's channels_last batch-norm kernels."""
+        cl = torch.channels_last
+        residual = x
+        y = fused.bn_act(self.conv1(x).contiguous(memory_format=cl), self.bn1, relu=True)
+        if self.avd is not None:
+            y = self.avd(y)
+        y = self.conv2(y.contiguous(memory_format=cl))
+        if self.downsample is not None:
+            residual = fused.bn_act(self.downsample[0](x).contiguous(memory_format=cl), self.downsample[1], relu=False)
+        return fused.bn_act(self.conv3(y).contiguous(memory_format=cl), self.bn3, relu=True,
+                            res=residual.contiguous(memory_format=cl))
 
 
 class CoTResNet(nn.Module):
@@ -90,7 +107,10 @@ class CoTResNet(nn.Module):
                     m.zero_init_last_bn()
 
     def forward_features(self, x):
-        x = self.maxpool(self.act1(self.bn1(self.conv1(x))))
+        if fused.supported(x):
+            x = self.maxpool(fused.bn_act(self.conv1(x).contiguous(memory_format=torch.channels_last), self.bn1, relu=True))
+        else:
+            x = self.maxpool(self.act1(self.bn1(self.conv1(x))))
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))
 
     def forward(self, x):

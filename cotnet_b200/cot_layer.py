@@ -74,15 +74,17 @@ class CotLayer(nn.Module):
         """channels_last fast path: GroupNorm, bn+SiLU+pool and the radix-2 recombination are fused kernels."""
         B, C, H, W = x.shape
         ks2 = self.kernel_size * self.kernel_size
-        k = self.key_embed(x)
-        e = self.embed[2](self.embed[1](self.embed[0](torch.cat([x, k], dim=1))))
+        cl = torch.channels_last
+        k = fused.bn_act(self.key_embed[0](x).contiguous(memory_format=cl), self.key_embed[1], relu=True)
+        e = fused.bn_act(self.embed[0](torch.cat([x, k], dim=1)).contiguous(memory_format=cl), self.embed[1], relu=True)
         l = self.embed[3](e)
-        v = self.conv1x1(x)
+        v = fused.bn_act(self.conv1x1[0](x).contiguous(memory_format=cl), self.conv1x1[1], relu=False)
         if l.dtype != v.dtype:
             l = l.to(v.dtype)
         l = l.contiguous(memory_format=torch.channels_last)
-        w = fused.group_norm9(l, self.embed[4])                            # fp32 statistics, storage dtype out
-        u = self.local_conv(v.contiguous(memory_format=torch.channels_last), w.view(B, 1, C // 8, ks2, H, W))
+        gc = fused.tap_chunk(C // 8)                                       # tap-major weight order for the fast kernels
+        w = fused.group_norm9(l, self.embed[4], gc)                        # fp32 statistics, storage dtype out
+        u = fused.AggTapFn.apply(v.contiguous(memory_format=torch.channels_last), w, 1, gc)
         return fused.cot_tail(u, k.contiguous(memory_format=torch.channels_last), self.bn, self.se)
 
     def forward(self, x):
@@ -136,16 +138,17 @@ class CoXtLayer(nn.Module):
     def _forward_fused(self, x):
         B, C, H, W = x.shape
         ks = self.kernel_size
-        k = self.key_embed(x)
-        qk = torch.stack([x, k], dim=2).reshape(B, 2 * C, H, W).contiguous(memory_format=torch.channels_last)
-        e = self.embed[2](self.embed[1](self.embed[0](qk)))
+        cl = torch.channels_last
+        k = fused.bn_act(self.key_embed[0](x).contiguous(memory_format=cl), self.key_embed[1], relu=True)
+        qk = torch.stack([x, k], dim=2).reshape(B, 2 * C, H, W).contiguous(memory_format=cl)
+        e = fused.bn_act(self.embed[0](qk).contiguous(memory_format=cl), self.embed[1], relu=True)
         l = self.embed[3](e)
-        v = self.conv1x1(x)
+        v = fused.bn_act(self.conv1x1[0](x).contiguous(memory_format=cl), self.conv1x1[1], relu=False)
         if l.dtype != v.dtype:
             l = l.to(v.dtype)
-        w = fused.group_norm9(l.contiguous(memory_format=torch.channels_last), self.embed[4])
-        u = AggregationZeropad.apply(v.contiguous(memory_format=torch.channels_last), w.view(B, 1, C // 8, ks * ks, H, W),
-                                     ks, 1, (ks - 1) // 2, 1, self.dw_group)
+        gc = fused.tap_chunk(C // 8, self.dw_group)
+        w = fused.group_norm9(l.contiguous(memory_format=torch.channels_last), self.embed[4], gc)
+        u = fused.AggTapFn.apply(v.contiguous(memory_format=torch.channels_last), w, self.dw_group, gc)
         return fused.cot_tail(u, k.contiguous(memory_format=torch.channels_last), self.bn, self.se)
 
     def forward(self, x):

@@ -472,6 +472,18 @@ agg3_dw_nhwc_fast(const T* __restrict__ dy, const T* __restrict__ x, T* __restri
   }
 }
 
+// second-generation NHWC kernels (agg_nhwc2.cu)
+struct Nhwc2Args {
+  int N, C, H, W, wc, fold, layout, gc, dtype;
+  long long x_sn, x_sp, w_sn, w_sp, y_sn, y_sp;
+};
+template <typename T> int nhwc2_fwd(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);
+template <typename T> int nhwc2_dx(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);
+template <typename T> int nhwc2_dw(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);
+// second-generation NCHW kernels (agg_nchw2.cu)
+template <typename T> int nchw2_fwd(int, int, int, int, int, long long, const T*, const T*, T*, cudaStream_t, int*);
+template <typename T> int nchw2_bwd(int, int, int, int, int, long long, const T*, const T*, const T*, T*, T*, cudaStream_t, int*);
+
 // ------------------------------------------------------------------------------------------------ host
 static int grid_for(long long total, int block, int per_sm = 8) {
   long long need = (total + block - 1) / block;
@@ -547,8 +559,23 @@ static int nhwc_vec(const Geo& g, const void* a, const void* b, const void* c) {
   return 0;
 }
 
+static Nhwc2Args nhwc2_args(const Geo& g) {
+  Nhwc2Args a;
+  a.N = g.N; a.C = g.C; a.H = g.H; a.W = g.W; a.wc = g.wc; a.fold = g.fold; a.layout = g.layout; a.gc = g.gc; a.dtype = 0;
+  a.x_sn = g.x_sn; a.x_sp = g.x_sw; a.w_sn = g.w_sn; a.w_sp = g.w_sw; a.y_sn = g.y_sn; a.y_sp = g.y_sw;
+  return a;
+}
+
 template <typename T>
 static int fwd_impl(const Geo& g, const T* x, const T* w, T* y, cudaStream_t st) {
+  if (g.layout != COTB200_NCHW && is_same3(g, 3)) {
+    int rc2 = 0;
+    if (nhwc2_fwd<T>(nhwc2_args(g), x, w, y, st, &rc2)) return rc2;
+  }
+  if (g.layout == COTB200_NCHW && nofold(g) && fits32(g) && is_same3(g, 3)) {
+    int rc2 = 0;
+    if (nchw2_fwd<T>(g.N, g.C, g.H, g.W, g.wc, g.y_sn, x, w, y, st, &rc2)) return rc2;
+  }
   if (g.layout == COTB200_NCHW && nofold(g) && fits32(g) && (is_same3(g, 3) || is_same3(g, 5))) {
     if constexpr (!std::is_same<T, double>::value) {
       const int total = g.N * g.wc * g.H * g.W;
@@ -590,6 +617,10 @@ static int fwd_impl(const Geo& g, const T* x, const T* w, T* y, cudaStream_t st)
 template <typename T>
 static int bwd_impl(const Geo& g, const T* dy, const T* x, const T* w, T* dx, T* dw, bool acc_dx, cudaStream_t st) {
   if (!dx && !dw) return 0;
+  if (g.layout == COTB200_NCHW && nofold(g) && fits32(g) && is_same3(g, 3) && !acc_dx) {
+    int rc2 = 0;
+    if (nchw2_bwd<T>(g.N, g.C, g.H, g.W, g.wc, g.y_sn, dy, x, w, dx, dw, st, &rc2)) return rc2;
+  }
   if (g.layout == COTB200_NCHW && nofold(g) && fits32(g) && (is_same3(g, 3) || is_same3(g, 5))) {
     if constexpr (!std::is_same<T, double>::value) {
       const int total = g.N * g.wc * g.H * g.W;
@@ -610,6 +641,13 @@ static int bwd_impl(const Geo& g, const T* dy, const T* x, const T* w, T* dx, T*
 #undef COTB200_LAUNCH_BWD
       return check_launch("agg_bwd_nchw_fast");
     }
+  }
+  if (g.layout == COTB200_NHWC_TAP && !acc_dx && is_same3(g, 3)) {
+    // second-generation kernels; whatever they do not take falls through to the first-generation ones below
+    int rc2 = 0;
+    if (dx && nhwc2_dx<T>(nhwc2_args(g), dy, w, dx, st, &rc2)) { if (rc2) return rc2; dx = nullptr; }
+    if (dw && nhwc2_dw<T>(nhwc2_args(g), dy, x, dw, st, &rc2)) { if (rc2) return rc2; dw = nullptr; }
+    if (!dx && !dw) return 0;
   }
   if (g.layout != COTB200_NCHW && !acc_dx) {
     if constexpr (!std::is_same<T, double>::value) {

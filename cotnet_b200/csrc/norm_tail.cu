@@ -247,18 +247,127 @@ tail_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ u, const
   }
 }
 
+// ------------------------------------------------------------------------------------------------ BatchNorm (+ReLU, +residual)
+// Training / eval BatchNorm2d on NHWC tensors as 2 + 2 HBM passes (col_stats + apply; bwd sums + bwd apply), replacing
+// ATen's channels_last batch-norm kernels (ncu: 4 kernels, ~0.65 TB/s on the stage-1 tensors).
+//   ACT: 0 none, 1 ReLU.   y = act(x*scale + shift (+ res))                  (models/cotnet.py:45-46,53-54,61-62,:248-262)
+template <typename T, int VEC, int ACT, bool RES>
+__global__ void __launch_bounds__(NT_THREADS)
+bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ scale,
+                const float* __restrict__ shift, T* __restrict__ y, RowsGeo g) {
+  const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
+  if (!(tx < g.cq && ty < g.ry)) return;
+  const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
+  float sc[VEC], sh[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { sc[i] = scale[tx * VEC + i]; sh[i] = shift[tx * VEC + i]; }
+  const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+  for (int r = r0 + ty; r < r1; r += g.ry) {
+    const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.C);
+    Pack<T, VEC> rv;
+    if (RES) rv = ld_pack<T, VEC>(res + base + (long long)r * g.C);
+    Pack<T, VEC> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float z = fmaf(to_acc(xv.v[i]), sc[i], sh[i]);
+      if (RES) z += to_acc(rv.v[i]);
+      if (ACT == 1) z = fmaxf(z, 0.f);
+      o.v[i] = Elem<T>::from(z);
+    }
+    st_pack<T, VEC>(y + base + (long long)r * g.C, o);
+  }
+}
+
+// dz = dy * [y > 0] (ACT==1) ; sum_dz[c] += dz ; sum_dzx[c] += dz * xhat
+template <typename T, int VEC, int ACT>
+__global__ void __launch_bounds__(NT_THREADS)
+bn_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ mu,
+                   const float* __restrict__ rstd, float* __restrict__ sum_dz, float* __restrict__ sum_dzx, RowsGeo g) {
+  extern __shared__ float sm[];
+  const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
+  const bool active = tx < g.cq && ty < g.ry;
+  const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
+  float acc[2][VEC], m[VEC], rs[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { acc[0][i] = acc[1][i] = 0.f; m[i] = active ? mu[tx * VEC + i] : 0.f; rs[i] = active ? rstd[tx * VEC + i] : 0.f; }
+  if (active) {
+    const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+    for (int r = r0 + ty; r < r1; r += g.ry) {
+      const Pack<T, VEC> dv = ld_pack<T, VEC>(dy + base + (long long)r * g.C);
+      const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.C);
+      Pack<T, VEC> yv;
+      if (ACT == 1) yv = ld_pack<T, VEC>(y + base + (long long)r * g.C);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float dz = to_acc(dv.v[i]);
+        if (ACT == 1 && !(to_acc(yv.v[i]) > 0.f)) dz = 0.f;
+        acc[0][i] += dz;
+        acc[1][i] = fmaf(dz, (to_acc(xv.v[i]) - m[i]) * rs[i], acc[1][i]);
+      }
+    }
+  }
+  cta_col_reduce<2, VEC>(acc, sm, g, tx, ty, active);
+  for (int c = threadIdx.x; c < g.C; c += NT_THREADS) {
+    atomicAdd(sum_dz + c, sm[c]);
+    atomicAdd(sum_dzx + c, sm[g.ry * g.C + c]);
+  }
+}
+
+// dx = scale * (dz - c1 - xhat*c2)   (c1 = c2 = 0 in eval mode);   dres = dz when RES
+template <typename T, int VEC, int ACT, bool RES>
+__global__ void __launch_bounds__(NT_THREADS)
+bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ scale,
+                    const float* __restrict__ mu, const float* __restrict__ rstd, const float* __restrict__ c1,
+                    const float* __restrict__ c2, T* __restrict__ dx, T* __restrict__ dres, RowsGeo g) {
+  const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
+  if (!(tx < g.cq && ty < g.ry)) return;
+  const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
+  float sc[VEC], m[VEC], rs[VEC], k1[VEC], k2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c = tx * VEC + i;
+    sc[i] = scale[c]; m[i] = mu[c]; rs[i] = rstd[c]; k1[i] = c1 ? c1[c] : 0.f; k2[i] = c2 ? c2[c] : 0.f;
+  }
+  const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+  for (int r = r0 + ty; r < r1; r += g.ry) {
+    const Pack<T, VEC> dv = ld_pack<T, VEC>(dy + base + (long long)r * g.C);
+    const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.C);
+    Pack<T, VEC> yv;
+    if (ACT == 1) yv = ld_pack<T, VEC>(y + base + (long long)r * g.C);
+    Pack<T, VEC> o, o2;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float dz = to_acc(dv.v[i]);
+      if (ACT == 1 && !(to_acc(yv.v[i]) > 0.f)) dz = 0.f;
+      o.v[i] = Elem<T>::from(sc[i] * (dz - k1[i] - (to_acc(xv.v[i]) - m[i]) * rs[i] * k2[i]));
+      if (RES) o2.v[i] = Elem<T>::from(dz);
+    }
+    st_pack<T, VEC>(dx + base + (long long)r * g.C, o);
+    if (RES) st_pack<T, VEC>(dres + base + (long long)r * g.C, o2);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ GroupNorm(9 taps)
-// Channel j of the logits belongs to group grp(j): plain order j = g*9 + t; tap-major chunks (gc) otherwise.
-__device__ __forceinline__ int gn_group(int j, int gc) {
-  if (gc <= 0) return j / 9;
-  const int chunk = j / (9 * gc), rr = j - chunk * 9 * gc;
-  return chunk * gc + rr % gc;
+// The logits l (and dl) are always in the reference channel order j = g*9 + t (they come out of / go into the
+// embed.3 convolution).  The normalised weights ghat (and their gradient dg) are stored in the order the LocalConv
+// kernels want: gc == 0 the same order; gc > 0 tap-major chunks of gc weight channels (COTB200_NHWC_TAP):
+// position of (g, t) = ((g/gc)*9 + t)*gc + g%gc.
+__device__ __forceinline__ int gn_pos(int j, int gc) {
+  if (gc <= 0) return j;
+  const int gi = j / 9, t = j - gi * 9;
+  return ((gi / gc) * 9 + t) * gc + gi % gc;
+}
+__device__ __forceinline__ int gn_j_of_pos(int pos, int gc) {
+  if (gc <= 0) return pos;
+  const int chunk = pos / (9 * gc), rr = pos - chunk * 9 * gc;
+  const int t = rr / gc, i = rr - t * gc;
+  return (chunk * gc + i) * 9 + t;
 }
 
 // gsum[b,g] += sum over (9 taps x rows) of l ; gsq likewise
 template <typename T, int VEC>
 __global__ void __launch_bounds__(NT_THREADS)
-gn_stats_kernel(const T* __restrict__ l, float* __restrict__ gsum, float* __restrict__ gsq, RowsGeo g, int wc, int gc) {
+gn_stats_kernel(const T* __restrict__ l, float* __restrict__ gsum, float* __restrict__ gsq, RowsGeo g, int wc) {
   extern __shared__ float sm[];
   const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
   const bool active = tx < g.cq && ty < g.ry;
@@ -275,21 +384,16 @@ gn_stats_kernel(const T* __restrict__ l, float* __restrict__ gsum, float* __rest
     }
   }
   cta_col_reduce<2, VEC>(acc, sm, g, tx, ty, active);
-  // fold the 9 tap columns of each group, one atomic per (b, group)
-  for (int gi = threadIdx.x; gi < wc; gi += NT_THREADS) {
+  for (int gi = threadIdx.x; gi < wc; gi += NT_THREADS) {      // fold the 9 tap columns of each group
     float s = 0.f, q = 0.f;
-    if (gc <= 0) {
-      for (int t = 0; t < 9; ++t) { s += sm[gi * 9 + t]; q += sm[g.ry * g.C + gi * 9 + t]; }
-    } else {
-      const int chunk = gi / gc, i = gi % gc;
-      for (int t = 0; t < 9; ++t) { const int j = (chunk * 9 + t) * gc + i; s += sm[j]; q += sm[g.ry * g.C + j]; }
-    }
+    for (int t = 0; t < 9; ++t) { s += sm[gi * 9 + t]; q += sm[g.ry * g.C + gi * 9 + t]; }
     atomicAdd(gsum + (long long)b * wc + gi, s);
     atomicAdd(gsq + (long long)b * wc + gi, q);
   }
 }
 
-// ghat = (l - mean[b,g]) * rstd[b,g] * gamma[j] + beta[j]
+// ghat[pos(j)] = (l[j] - mean[b,g]) * rstd[b,g] * gamma[j] + beta[j].  Thread = one OUTPUT packet (coalesced 16-byte
+// store); the VEC inputs are gathered (stride 9 inside the pixel's 18*wc-byte row, L1 hits).
 template <typename T, int VEC>
 __global__ void __launch_bounds__(NT_THREADS)
 gn_apply_kernel(const T* __restrict__ l, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -298,24 +402,33 @@ gn_apply_kernel(const T* __restrict__ l, const float* __restrict__ mean, const f
   if (!(tx < g.cq && ty < g.ry)) return;
   const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
   float A[VEC], Bc[VEC];
+  int jin[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    const int j = tx * VEC + i, gi = gn_group(j, gc);
+    const int j = gn_j_of_pos(tx * VEC + i, gc), gi = j / 9;
+    jin[i] = j;
     const float rs = rstd[(long long)b * wc + gi], mn = mean[(long long)b * wc + gi];
     A[i] = rs * gamma[j];
     Bc[i] = beta[j] - mn * A[i];
   }
-  const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+  const long long base = ((long long)b * g.HW) * g.C;
   for (int r = r0 + ty; r < r1; r += g.ry) {
-    const Pack<T, VEC> v = ld_pack<T, VEC>(l + base + (long long)r * g.C);
+    const T* lr = l + base + (long long)r * g.C;
     Pack<T, VEC> o;
+    if (gc <= 0) {
+      const Pack<T, VEC> v = ld_pack<T, VEC>(lr + tx * VEC);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) o.v[i] = Elem<T>::from(fmaf(to_acc(v.v[i]), A[i], Bc[i]));
-    st_pack<T, VEC>(out + base + (long long)r * g.C, o);
+      for (int i = 0; i < VEC; ++i) o.v[i] = Elem<T>::from(fmaf(to_acc(v.v[i]), A[i], Bc[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o.v[i] = Elem<T>::from(fmaf(Elem<T>::ld(lr + jin[i]), A[i], Bc[i]));
+    }
+    st_pack<T, VEC>(out + base + (long long)r * g.C + tx * VEC, o);
   }
 }
 
 // backward sums: s1[b,g] += sum dg*gamma ; s2[b,g] += sum dg*gamma*lhat ; dgamma[j] += sum dg*lhat ; dbeta[j] += sum dg
+// Thread = one packet of l in the reference order; dg gathered from its storage order.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(NT_THREADS)
 gn_bwd_sums_kernel(const T* __restrict__ dg, const T* __restrict__ l, const float* __restrict__ mean,
@@ -326,20 +439,24 @@ gn_bwd_sums_kernel(const T* __restrict__ dg, const T* __restrict__ l, const floa
   const bool active = tx < g.cq && ty < g.ry;
   const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
   float acc[2][VEC], mn[VEC], rs[VEC];    // acc[0] = sum dg ; acc[1] = sum dg*lhat   (per column j)
+  int pos[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     acc[0][i] = acc[1][i] = 0.f;
-    const int gi = active ? gn_group(tx * VEC + i, gc) : 0;
+    const int j = tx * VEC + i, gi = active ? j / 9 : 0;
+    pos[i] = active ? gn_pos(j, gc) : 0;
     mn[i] = active ? mean[(long long)b * wc + gi] : 0.f; rs[i] = active ? rstd[(long long)b * wc + gi] : 0.f;
   }
   if (active) {
-    const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+    const long long base = ((long long)b * g.HW) * g.C;
     for (int r = r0 + ty; r < r1; r += g.ry) {
-      const Pack<T, VEC> dv = ld_pack<T, VEC>(dg + base + (long long)r * g.C);
-      const Pack<T, VEC> lv = ld_pack<T, VEC>(l + base + (long long)r * g.C);
+      const T* dr = dg + base + (long long)r * g.C;
+      const Pack<T, VEC> lv = ld_pack<T, VEC>(l + base + (long long)r * g.C + tx * VEC);
+      Pack<T, VEC> dv;
+      if (gc <= 0) dv = ld_pack<T, VEC>(dr + tx * VEC);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
-        const float d = to_acc(dv.v[i]);
+        const float d = gc <= 0 ? to_acc(dv.v[i]) : (float)Elem<T>::ld(dr + pos[i]);
         acc[0][i] += d;
         acc[1][i] = fmaf(d, (to_acc(lv.v[i]) - mn[i]) * rs[i], acc[1][i]);
       }
@@ -353,7 +470,7 @@ gn_bwd_sums_kernel(const T* __restrict__ dg, const T* __restrict__ l, const floa
   for (int gi = threadIdx.x; gi < wc; gi += NT_THREADS) {
     float a = 0.f, q = 0.f;
     for (int t = 0; t < 9; ++t) {
-      const int j = gc <= 0 ? gi * 9 + t : ((gi / gc) * 9 + t) * gc + gi % gc;
+      const int j = gi * 9 + t;
       a = fmaf(sm[j], gamma[j], a);
       q = fmaf(sm[g.ry * g.C + j], gamma[j], q);
     }
@@ -373,23 +490,28 @@ gn_bwd_apply_kernel(const T* __restrict__ dg, const T* __restrict__ l, const flo
   const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
   const float inv_n = 1.f / (9.f * (float)g.HW);
   float mn[VEC], rs[VEC], ga[VEC], k1[VEC], k2[VEC];
+  int pos[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    const int j = tx * VEC + i, gi = gn_group(j, gc);
+    const int j = tx * VEC + i, gi = j / 9;
+    pos[i] = gn_pos(j, gc);
     mn[i] = mean[(long long)b * wc + gi]; rs[i] = rstd[(long long)b * wc + gi]; ga[i] = gamma[j];
     k1[i] = s1[(long long)b * wc + gi] * inv_n; k2[i] = s2[(long long)b * wc + gi] * inv_n;
   }
-  const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+  const long long base = ((long long)b * g.HW) * g.C;
   for (int r = r0 + ty; r < r1; r += g.ry) {
-    const Pack<T, VEC> dv = ld_pack<T, VEC>(dg + base + (long long)r * g.C);
-    const Pack<T, VEC> lv = ld_pack<T, VEC>(l + base + (long long)r * g.C);
+    const T* dr = dg + base + (long long)r * g.C;
+    const Pack<T, VEC> lv = ld_pack<T, VEC>(l + base + (long long)r * g.C + tx * VEC);
+    Pack<T, VEC> dv;
+    if (gc <= 0) dv = ld_pack<T, VEC>(dr + tx * VEC);
     Pack<T, VEC> o;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
+      const float d = gc <= 0 ? to_acc(dv.v[i]) : (float)Elem<T>::ld(dr + pos[i]);
       const float lh = (to_acc(lv.v[i]) - mn[i]) * rs[i];
-      o.v[i] = Elem<T>::from(rs[i] * (to_acc(dv.v[i]) * ga[i] - k1[i] - lh * k2[i]));
+      o.v[i] = Elem<T>::from(rs[i] * (d * ga[i] - k1[i] - lh * k2[i]));
     }
-    st_pack<T, VEC>(dl + base + (long long)r * g.C, o);
+    st_pack<T, VEC>(dl + base + (long long)r * g.C + tx * VEC, o);
   }
 }
 
@@ -582,7 +704,7 @@ extern "C" int cotb200_gn9_stats(int dtype, int B, int HW, int wc, int gc, const
       if (rc) return rc;
       COTB200_PROF("gn9_stats");
       NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(gn_stats_kernel<T, V>, smem))) return rc;
-                             gn_stats_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)l, gsum, gsq, g, wc, gc); });
+                             gn_stats_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)l, gsum, gsq, g, wc); });
       return check_launch("gn9_stats");
     }
   });
@@ -647,6 +769,80 @@ extern "C" int cotb200_gn9_bwd_apply(int dtype, int B, int HW, int wc, int gc, c
       COTB200_PROF("gn9_bwd_apply");
       NT_DISPATCH_VEC(vec, { gn_bwd_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dg, (const T*)l, mean, rstd, gamma, s1, s2, (T*)dl, g, wc, gc); });
       return check_launch("gn9_bwd_apply");
+    }
+  });
+  return 0;
+}
+
+extern "C" int cotb200_bn_apply(int dtype, int B, int HW, int C, const void* x, const void* res, const float* scale,
+                                const float* shift, int relu, void* y, void* stream) {
+  if (!x || !scale || !shift || !y) { set_error("bn_apply: NULL pointer"); return COTB200_ENULL; }
+  if (dtype == COTB200_F64) { set_error("bn_apply: fp64 not supported"); return COTB200_EDTYPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  COTB200_DISPATCH_DTYPE(dtype, {
+    if constexpr (!std::is_same<T, double>::value) {
+      const int vec = pick_vec<T>(C, x, res, y);
+      RowsGeo g; size_t smem;
+      int rc = make_geo(g, B, HW, C, vec, 1, &smem);
+      if (rc) return rc;
+      COTB200_PROF("bn_apply");
+      NT_DISPATCH_VEC(vec, {
+        if (relu) { if (res) bn_apply_kernel<T, V, 1, true><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)x, (const T*)res, scale, shift, (T*)y, g);
+                    else bn_apply_kernel<T, V, 1, false><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)x, nullptr, scale, shift, (T*)y, g); }
+        else { if (res) bn_apply_kernel<T, V, 0, true><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)x, (const T*)res, scale, shift, (T*)y, g);
+               else bn_apply_kernel<T, V, 0, false><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)x, nullptr, scale, shift, (T*)y, g); }
+      });
+      return check_launch("bn_apply");
+    }
+  });
+  return 0;
+}
+
+extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y, const float* mu,
+                                   const float* rstd, int relu, float* sum_dz, float* sum_dzx, void* stream) {
+  if (!dy || !x || !mu || !rstd || !sum_dz || !sum_dzx || (relu && !y)) { set_error("bn_bwd_sums: NULL pointer"); return COTB200_ENULL; }
+  if (dtype == COTB200_F64) { set_error("bn_bwd_sums: fp64 not supported"); return COTB200_EDTYPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  COTB200_DISPATCH_DTYPE(dtype, {
+    if constexpr (!std::is_same<T, double>::value) {
+      const int vec = pick_vec<T>(C, dy, x, y);
+      RowsGeo g; size_t smem;
+      int rc = make_geo(g, B, HW, C, vec, 2, &smem);
+      if (rc) return rc;
+      COTB200_PROF("bn_bwd_sums");
+      NT_DISPATCH_VEC(vec, {
+        if (relu) { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 1>, smem))) return rc;
+                    bn_bwd_sums_kernel<T, V, 1><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dy, (const T*)x, (const T*)y, mu, rstd, sum_dz, sum_dzx, g); }
+        else { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 0>, smem))) return rc;
+               bn_bwd_sums_kernel<T, V, 0><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dy, (const T*)x, nullptr, mu, rstd, sum_dz, sum_dzx, g); }
+      });
+      return check_launch("bn_bwd_sums");
+    }
+  });
+  return 0;
+}
+
+extern "C" int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y,
+                                    const float* scale, const float* mu, const float* rstd, const float* c1, const float* c2,
+                                    int relu, void* dx, void* dres, void* stream) {
+  if (!dy || !x || !scale || !mu || !rstd || !dx || (relu && !y)) { set_error("bn_bwd_apply: NULL pointer"); return COTB200_ENULL; }
+  if (dtype == COTB200_F64) { set_error("bn_bwd_apply: fp64 not supported"); return COTB200_EDTYPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  COTB200_DISPATCH_DTYPE(dtype, {
+    if constexpr (!std::is_same<T, double>::value) {
+      const int vec = pick_vec<T>(C, dy, x, y, dx);
+      RowsGeo g; size_t smem;
+      int rc = make_geo(g, B, HW, C, (dres && ((uintptr_t)dres & (vec * sizeof(T) - 1))) ? 1 : vec, 1, &smem);
+      if (rc) return rc;
+      const int v2 = g.C / g.cq;
+      COTB200_PROF("bn_bwd_apply");
+      NT_DISPATCH_VEC(v2, {
+        if (relu) { if (dres) bn_bwd_apply_kernel<T, V, 1, true><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, scale, mu, rstd, c1, c2, (T*)dx, (T*)dres, g);
+                    else bn_bwd_apply_kernel<T, V, 1, false><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, scale, mu, rstd, c1, c2, (T*)dx, nullptr, g); }
+        else { if (dres) bn_bwd_apply_kernel<T, V, 0, true><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dy, (const T*)x, nullptr, scale, mu, rstd, c1, c2, (T*)dx, (T*)dres, g);
+               else bn_bwd_apply_kernel<T, V, 0, false><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dy, (const T*)x, nullptr, scale, mu, rstd, c1, c2, (T*)dx, nullptr, g); }
+      });
+      return check_launch("bn_bwd_apply");
     }
   });
   return 0;

@@ -28,6 +28,83 @@ def _f32(t):
     return t.detach().float().contiguous()
 
 
+def _bn_batch_stats(x, bn, lib, st, dt):
+    """(mean, biased var) of a channels_last tensor; training mode updates the module's running buffers exactly like
+    nn.BatchNorm2d (momentum, unbiased running variance, num_batches_tracked)."""
+    B, C, H, W = x.shape
+    n = float(B * H * W)
+    if bn.training or bn.running_mean is None:
+        stats = torch.zeros(2, C, dtype=torch.float32, device=x.device)
+        _lib.check(lib.cotb200_col_stats(dt, B, H * W, C, x.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), st), "col_stats")
+        mean = stats[0] / n
+        var = (stats[1] / n - mean * mean).clamp_min_(0.0)
+        if bn.running_mean is not None and bn.track_running_stats:
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+                mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                bn.running_mean.mul_(1 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)
+                bn.running_var.mul_(1 - mom).add_((var * (n / max(n - 1.0, 1.0))).to(bn.running_var.dtype), alpha=mom)
+        return mean, var, True
+    return bn.running_mean.float(), bn.running_var.float(), False
+
+
+class BNActFn(Function):
+    """y = act(BatchNorm2d(x) (+ res)) on channels_last tensors: col_stats + bn_apply forward, bn_bwd_sums + bn_bwd_apply
+    backward.  Replaces the nn.BatchNorm2d / nn.ReLU (/ residual add) modules of models/cotnet.py:45-46,53-54,61-62 and
+    :231-235,:249-262 -- ATen's channels_last batch-norm kernels are the largest single cost of the eager step."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, res, bn, relu):
+        assert _is_cl(x) and (res is None or (_is_cl(res) and res.dtype == x.dtype and res.shape == x.shape))
+        B, C, H, W = x.shape
+        lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.dtype_code(x)
+        x = x.detach()
+        mean, var, batch = _bn_batch_stats(x, bn, lib, st, dt)
+        rstd = torch.rsqrt(var + bn.eps).contiguous()
+        scale = (weight.detach().float() * rstd).contiguous()
+        shift = (bias.detach().float() - mean * scale).contiguous()
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        _lib.check(lib.cotb200_bn_apply(dt, B, H * W, C, x.data_ptr(), _lib.ptr(res), scale.data_ptr(), shift.data_ptr(),
+                                        1 if relu else 0, y.data_ptr(), st), "bn_apply")
+        ctx.save_for_backward(x, y if relu else None, scale, mean.contiguous(), rstd)
+        ctx.cfg = (relu, batch, res is not None, weight.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, scale, mean, rstd = ctx.saved_tensors
+        relu, batch, has_res, wdt, bdt = ctx.cfg
+        B, C, H, W = x.shape
+        n = float(B * H * W)
+        lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.dtype_code(x)
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        sums = None
+        if batch or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)
+            _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), x.data_ptr(), _lib.ptr(y), mean.data_ptr(),
+                                               rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
+                       "bn_bwd_sums")
+        c1 = c2 = None
+        if batch:
+            c1, c2 = (sums[0] / n).contiguous(), (sums[1] / n).contiguous()
+        dx = torch.empty_like(x, memory_format=torch.channels_last) if ctx.needs_input_grad[0] else None
+        dres = torch.empty_like(x, memory_format=torch.channels_last) if (has_res and ctx.needs_input_grad[3]) else None
+        if dx is not None or dres is not None:
+            if dx is None:
+                dx = torch.empty_like(x, memory_format=torch.channels_last)
+            _lib.check(lib.cotb200_bn_bwd_apply(dt, B, H * W, C, dy.data_ptr(), x.data_ptr(), _lib.ptr(y), scale.data_ptr(),
+                                                mean.data_ptr(), rstd.data_ptr(), _lib.ptr(c1), _lib.ptr(c2), 1 if relu else 0,
+                                                dx.data_ptr(), _lib.ptr(dres), st), "bn_bwd_apply")
+        dgamma = sums[1].to(wdt) if ctx.needs_input_grad[1] else None
+        dbeta = sums[0].to(bdt) if ctx.needs_input_grad[2] else None
+        return dx, dgamma, dbeta, dres, None, None
+
+
+def bn_act(x, bn: torch.nn.BatchNorm2d, relu=False, res=None):
+    """Fused BatchNorm2d (+ residual add) (+ ReLU) with the module's parameters / buffers / train-eval semantics."""
+    return BNActFn.apply(x, bn.weight, bn.bias, res, bn, relu)
+
+
 class GroupNorm9Fn(Function):
     """l [B, 9*wc, H, W] channels_last -> GroupNorm with wc groups of 9 consecutive channels (gc=0) or tap-major
     chunks (gc>0); gamma/beta [9*wc]."""
@@ -86,20 +163,7 @@ class CotTailFn(Function):
         HW, n = H * W, float(B * H * W)
         lib, st, dt = _lib.load(), _lib.stream_ptr(u), _lib.dtype_code(u)
         u, k = u.detach(), k.detach()
-        training = bn.training
-        if training or bn.running_mean is None:
-            stats = torch.zeros(2, C, dtype=torch.float32, device=u.device)
-            _lib.check(lib.cotb200_col_stats(dt, B, HW, C, u.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), st), "col_stats")
-            mean = stats[0] / n
-            var = (stats[1] / n - mean * mean).clamp_min_(0.0)
-            if bn.running_mean is not None and bn.track_running_stats:
-                with torch.no_grad():
-                    bn.num_batches_tracked += 1
-                    mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-                    bn.running_mean.mul_(1 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)
-                    bn.running_var.mul_(1 - mom).add_((var * (n / max(n - 1.0, 1.0))).to(bn.running_var.dtype), alpha=mom)
-        else:
-            mean, var = bn.running_mean.float(), bn.running_var.float()
+        mean, var, training = _bn_batch_stats(u, bn, lib, st, dt)
         rstd = torch.rsqrt(var + bn.eps)
         scale = (bn_weight.detach().float() * rstd).contiguous()
         shift = (bn_bias.detach().float() - mean * scale).contiguous()
@@ -108,10 +172,11 @@ class CotTailFn(Function):
         _lib.check(lib.cotb200_tail_pool(dt, B, HW, C, u.data_ptr(), k.data_ptr(), scale.data_ptr(), shift.data_ptr(),
                                          psum.data_ptr(), st), "tail_pool")
         # the SE MLP on [B, C] (3 tiny GEMV-sized ops) stays PyTorch; its graph is kept for backward
-        with torch.enable_grad():
+        # ... in fp32 whatever the storage dtype: se.1 normalises over the batch, which amplifies bf16 rounding of the
+        # pooled descriptor by an order of magnitude (the fp32 math costs nothing at [B, C])
+        with torch.enable_grad(), torch.autocast("cuda", enabled=False):
             p_leaf = (psum / HW).requires_grad_(True)
-            z = se(p_leaf.view(B, C, 1, 1).to(u.dtype if not torch.is_autocast_enabled() else torch.float32))
-            a = torch.softmax(z.float().view(B, C, 2), dim=2)
+            a = torch.softmax(_se_fp32(se, p_leaf).view(B, C, 2), dim=2)
         a_c = a.detach().contiguous()
         out = torch.empty_like(u, memory_format=torch.channels_last)
         _lib.check(lib.cotb200_tail_combine(dt, B, HW, C, u.data_ptr(), k.data_ptr(), scale.data_ptr(), shift.data_ptr(),
@@ -154,6 +219,78 @@ class CotTailFn(Function):
         dbeta = sums[0].to(ctx.bn_dtypes[1]) if ctx.needs_input_grad[3] else None
         ctx.graph = None
         return (du, dk, dgamma, dbeta, None, None) + tuple(se_grads)
+
+
+class AggTapFn(Function):
+    """LocalConv 3x3 (stride 1, zero pad 1) on channels_last tensors with the weights in the block-internal tap-major
+    order (COTB200_NHWC_TAP, chunk width gc) -- or the reference order when gc == 0.  v [B,C,H,W], w [B,9*wc,H,W]."""
+
+    @staticmethod
+    def forward(ctx, v, w, fold, gc):
+        assert _is_cl(v) and _is_cl(w) and v.dtype == w.dtype
+        v, w = v.detach(), w.detach()
+        out = torch.empty_like(v, memory_format=torch.channels_last)
+        dsc = AggTapFn._desc(v, w, fold, gc)
+        _lib.check(_lib.load().cotb200_agg_zeropad_fwd(dsc, v.data_ptr(), w.data_ptr(), out.data_ptr(), _lib.stream_ptr(v)),
+                   "agg_zeropad_fwd")
+        ctx.save_for_backward(v, w)
+        ctx.cfg = (fold, gc)
+        return out
+
+    @staticmethod
+    def _desc(v, w, fold, gc):
+        B, C, H, W = v.shape
+        d = _lib.AggDesc()
+        d.n, d.c, d.h, d.w = B, C, H, W
+        d.heads, d.wc = 1, w.shape[1] // 9
+        d.kh = d.kw = 3
+        d.sh = d.sw = d.ph = d.pw = d.dh = d.dw = 1
+        d.ho, d.wo = H, W
+        d.dtype = _lib.dtype_code(v)
+        d.layout = _lib.NHWC_TAP if gc > 0 else _lib.NHWC
+        d.gc, d.fold = gc, fold
+        return d
+
+    @staticmethod
+    def backward(ctx, dy):
+        v, w = ctx.saved_tensors
+        fold, gc = ctx.cfg
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dv = torch.empty_like(v, memory_format=torch.channels_last) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w, memory_format=torch.channels_last) if ctx.needs_input_grad[1] else None
+        if dv is not None or dw is not None:
+            dsc = AggTapFn._desc(v, w, fold, gc)
+            _lib.check(_lib.load().cotb200_agg_zeropad_bwd(dsc, dy.data_ptr(), v.data_ptr(), w.data_ptr(), _lib.ptr(dv),
+                                                           _lib.ptr(dw), _lib.stream_ptr(v)), "agg_zeropad_bwd")
+        return dv, dw, None, None
+
+
+def tap_chunk(wc, fold=1):
+    """Chunk width of the tap-major weight order the fast kernels use, 0 when wc does not allow it."""
+    return 8 if (wc // fold) % 8 == 0 else 0
+
+
+def _se_fp32(se, p):
+    """models/cotnet.py:69-77 on p [B, C] in fp32: conv1x1 -> BatchNorm2d -> ReLU -> conv1x1, using (and updating) the
+    module's parameters / buffers; differentiable w.r.t. p and the parameters."""
+    c0, b1, c3 = se[0], se[1], se[3]
+    z = torch.nn.functional.linear(p, c0.weight.float().flatten(1), None if c0.bias is None else c0.bias.float())
+    if b1.training or b1.running_mean is None:
+        rm = None if b1.running_mean is None else b1.running_mean.float()
+        rv = None if b1.running_var is None else b1.running_var.float()
+        if b1.num_batches_tracked is not None:
+            b1.num_batches_tracked += 1
+        mom = b1.momentum if b1.momentum is not None else 1.0 / float(b1.num_batches_tracked)
+        z = torch.nn.functional.batch_norm(z, rm, rv, b1.weight.float(), b1.bias.float(), True, mom, b1.eps)
+        if rm is not None:
+            with torch.no_grad():
+                b1.running_mean.copy_(rm)
+                b1.running_var.copy_(rv)
+    else:
+        z = torch.nn.functional.batch_norm(z, b1.running_mean.float(), b1.running_var.float(), b1.weight.float(),
+                                           b1.bias.float(), False, 0.0, b1.eps)
+    z = torch.relu(z)
+    return torch.nn.functional.linear(z, c3.weight.float().flatten(1), None if c3.bias is None else c3.bias.float())
 
 
 def group_norm9(l, gn: torch.nn.GroupNorm, gc=0):

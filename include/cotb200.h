@@ -123,8 +123,23 @@ int cotb200_tail_bwd_dz_sums(int dtype, int B, int HW, int C, const void* dout, 
 int cotb200_tail_bwd_apply(int dtype, int B, int HW, int C, const void* dout, const void* u, const float* scale,
                            const float* shift, const float* mu, const float* rstd, const float* a, const float* dpn,
                            const float* c1, const float* c2, void* du, void* dk, void* stream);
+/* BatchNorm2d (+ReLU) (+residual add) on NHWC tensors: y = act(x*scale + shift (+ res)).  With cotb200_col_stats this
+ * replaces nn.BatchNorm2d / nn.ReLU pairs of the block (models/cotnet.py:45-46,53-54,61-62) and of the enclosing
+ * bottleneck (models/cotnet.py:231-235,:249-262) in 2 forward + 2 backward HBM passes.  relu: 0/1; res may be NULL. */
+int cotb200_bn_apply(int dtype, int B, int HW, int C, const void* x, const void* res, const float* scale,
+                     const float* shift, int relu, void* y, void* stream);
+/* dz = dy*[y>0] (relu) ; sum_dz[c] += sum dz ; sum_dzx[c] += sum dz*xhat      (y may be NULL when relu == 0) */
+int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y, const float* mu,
+                        const float* rstd, int relu, float* sum_dz, float* sum_dzx, void* stream);
+/* dx = scale*(dz - c1 - xhat*c2) (c1,c2 NULL in eval mode) ; dres = dz when dres != NULL (gradient of the residual) */
+int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y, const float* scale,
+                         const float* mu, const float* rstd, const float* c1, const float* c2, int relu, void* dx,
+                         void* dres, void* stream);
+
 /* GroupNorm(num_groups = wc, channels = 9*wc) of the attention logits (models/cotnet.py:56): group g = the 9 taps of
- * weight channel g.  gc = 0: channel j = g*9 + t (reference order); gc > 0: tap-major chunks (COTB200_NHWC_TAP). */
+ * weight channel g.  The logits l / dl are always in the reference channel order j = g*9 + t; `gc` is the storage order
+ * of the normalised weights (and of their gradient dg): 0 = same order, > 0 = tap-major chunks (COTB200_NHWC_TAP), so
+ * the permutation the LocalConv kernels want costs nothing extra.  (cotb200_gn9_stats ignores gc.) */
 int cotb200_gn9_stats(int dtype, int B, int HW, int wc, int gc, const void* l, float* gsum, float* gsq, void* stream);
 int cotb200_gn9_apply(int dtype, int B, int HW, int wc, int gc, const void* l, const float* mean, const float* rstd,
                       const float* gamma, const float* beta, void* out, void* stream);

@@ -94,7 +94,8 @@ def test_stage_shapes_vs_oracle(kind, cls, dim, H, dtype, cl, training):
     # relative to the output scale
     scale = max(1.0, want.abs().max().item())
     err = (got.double().cpu() - want).abs()
-    lim = (tol * 6 if dtype == torch.bfloat16 else tol * (4 if training else 1)) * scale
+    # training mode: four batch-statistics BatchNorms + the batch-normalised SE bottleneck amplify bf16 rounding
+    lim = (tol * (10 if training else 4) if dtype == torch.bfloat16 else tol * (4 if training else 1)) * scale
     assert err.max().item() <= lim, "max err %.3e (limit %.3e, |ref|max %.3e)" % (err.max().item(), lim, scale)
     assert got.shape == x.shape and got.dtype == dtype
     if cl:

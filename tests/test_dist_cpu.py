@@ -31,7 +31,7 @@ def _worker(rank, world, port, q):
     local = lin.weight.grad.clone()
     cdist.allreduce_grads_(list(lin.parameters()), w)
     cdist.barrier()
-    q.put((rank, lo, hi, mx, sm, local, lin.weight.grad.clone()))
+    q.put((rank, lo, hi, mx, sm, local.tolist(), lin.weight.grad.tolist()))   # plain lists: no fd passing
     dist.destroy_process_group()
 
 
@@ -51,6 +51,7 @@ def test_two_rank_gloo():
     assert (lo0, hi0, lo1, hi1) == (0, 257, 257, 513)        # shards tile the range, remainder on rank 0
     assert mx0 == mx1 == 11.0                                 # slowest rank defines the time
     assert sm0 == sm1 == 513.0
+    g0, g1, l0, l1 = [torch.tensor(t) for t in (g0, g1, l0, l1)]
     assert torch.allclose(g0, g1) and torch.allclose(g0, (l0 + l1) / 2)   # averaged gradients agree on all ranks
 
 

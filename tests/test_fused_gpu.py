@@ -7,13 +7,69 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def _cl(t):
     return t.contiguous(memory_format=torch.channels_last)
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+def _to_tap(t, gc):
+    """reference channel order (g*9+t) -> tap-major chunks of gc, on a [B, J, H, W] tensor"""
+    if gc == 0:
+        return t
+    B, J, H, W = t.shape
+    wc = J // 9
+    return t.view(B, wc // gc, gc, 9, H, W).permute(0, 1, 3, 2, 4, 5).reshape(B, J, H, W)
+
+
+def _from_tap(t, gc):
+    if gc == 0:
+        return t
+    B, J, H, W = t.shape
+    wc = J // 9
+    return t.view(B, wc // gc, 9, gc, H, W).permute(0, 1, 3, 2, 4, 5).reshape(B, J, H, W)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("C,wc,H,fold,gc", [(64, 8, 56, 1, 8), (128, 16, 28, 1, 8), (256, 32, 14, 1, 8), (512, 64, 7, 1, 8),
+                                           (384, 48, 7, 2, 8), (64, 8, 9, 1, 0), (96, 12, 10, 2, 0), (192, 24, 14, 2, 0)])
+def test_agg_tap(dtype, C, wc, H, fold, gc):
+    """AggTapFn (block-internal weight order, second-generation kernels) vs the oracle, fwd + dX + dW."""
+    from cotnet_b200 import fused
+    from oracle import agg_ref
+    g = torch.Generator().manual_seed(C + H + gc)
+    B = 3
+    x64 = torch.randn(B, C, H, H, generator=g, dtype=torch.float64).to(dtype).double()
+    w64 = torch.randn(B, 9 * wc, H, H, generator=g, dtype=torch.float64).to(dtype).double()
+    c64 = torch.randn(B, C, H, H, generator=g, dtype=torch.float64).to(dtype).double()
+    x = _cl(x64.to(dtype).cuda()).requires_grad_(True)
+    w = _cl(_to_tap(w64, gc).to(dtype).cuda()).requires_grad_(True)
+    y = fused.AggTapFn.apply(x, w, fold, gc)
+    gx, gw = torch.autograd.grad(y, (x, w), _cl(c64.to(dtype).cuda()))
+    xr, wr = x64.clone().requires_grad_(True), w64.clone().requires_grad_(True)
+    # un-folded semantics == the reference's view(B*fold, C/fold, ...) trick (models/cotnet.py:157-162)
+    yr = agg_ref.agg_zeropad_unfold(xr.view(B * fold, C // fold, H, H), wr.view(B * fold, 1, wc // fold, 9, H, H), 3, 1, 1, 1)
+    yr = yr.view(B, C, H, H)
+    gxr, gwr = torch.autograd.grad(yr, (xr, wr), c64)
+    tol = 1e-3 if dtype == torch.float32 else 1e-2
+    for a, b, name in ((y, yr, "y"), (gx, gxr, "dX"), (_from_tap(gw, gc), gwr, "dW")):
+        err = (a.double().cpu() - b).abs()
+        assert bool((err <= tol + tol * b.abs()).all()), "%s max err %.3e" % (name, err.max().item())
+
+
+@pytest.mark.parametrize("gc", [0, 8])
 @pytest.mark.parametrize("wc,H", [(8, 14), (16, 9), (12, 7), (64, 7)])
-def test_groupnorm9(dtype, tol, wc, H):
+def test_groupnorm9(dtype, tol, wc, H, gc):
+    if gc and wc % gc:
+        pytest.skip("chunk does not divide wc")
     from cotnet_b200 import fused
     g = torch.Generator(device="cuda").manual_seed(wc + H)
     B, J = 5, 9 * wc
@@ -23,8 +79,9 @@ def test_groupnorm9(dtype, tol, wc, H):
         gn.bias.normal_(0, 0.3, generator=g)
     l = _cl((torch.randn(B, J, H, H, generator=g, device="cuda") * 2 + 0.5).to(dtype)).requires_grad_(True)
     cot = _cl(torch.randn(B, J, H, H, generator=g, device="cuda").to(dtype))
-    out = fused.group_norm9(l, gn)
-    gl, gw, gb = torch.autograd.grad(out, (l, gn.weight, gn.bias), cot)
+    out_t = fused.group_norm9(l, gn, gc)
+    gl, gw, gb = torch.autograd.grad(out_t, (l, gn.weight, gn.bias), _cl(_to_tap(cot, gc)))
+    out = _from_tap(out_t, gc)
     lr = l.detach().double().requires_grad_(True)
     gnr = nn.GroupNorm(wc, J).cuda().double()
     gnr.load_state_dict(gn.state_dict())
@@ -34,7 +91,7 @@ def test_groupnorm9(dtype, tol, wc, H):
         err = (a.double() - b).abs().max().item()
         scale = max(1.0, b.abs().max().item())
         assert err <= tol * scale, "%s err %.3e scale %.3e" % (name, err, scale)
-    assert out.is_contiguous(memory_format=torch.channels_last) and out.dtype == dtype
+    assert out_t.is_contiguous(memory_format=torch.channels_last) and out_t.dtype == dtype
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-4), (torch.bfloat16, 4e-2)])
@@ -78,3 +135,41 @@ def test_cot_tail(dtype, tol, C, H, training):
         assert torch.allclose(bn.running_mean.double(), bn_r.running_mean, atol=1e-2 if dtype != torch.float32 else 1e-5)
         assert torch.allclose(bn.running_var.double(), bn_r.running_var, atol=1e-2 if dtype != torch.float32 else 1e-4)
         assert int(bn.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("C,H", [(64, 14), (256, 7), (96, 9), (2048, 7)])
+@pytest.mark.parametrize("relu,res", [(False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("training", [False, True])
+def test_bn_act(dtype, tol, C, H, relu, res, training):
+    """Fused BatchNorm2d (+residual) (+ReLU) vs eager fp64 modules: output, dX, dres, dgamma, dbeta, running buffers."""
+    import copy
+    from cotnet_b200 import fused
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    B = 8
+    bn = nn.BatchNorm2d(C).cuda()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5, generator=g); bn.bias.normal_(0, 0.3, generator=g)
+        bn.running_mean.normal_(0, 0.3, generator=g); bn.running_var.uniform_(0.5, 2, generator=g)
+    bn_r = copy.deepcopy(bn).double()
+    bn.train(training); bn_r.train(training)
+    x = _cl((torch.randn(B, C, H, H, generator=g, device="cuda") * 1.5 + 0.3).to(dtype)).requires_grad_(True)
+    r = _cl(torch.randn(B, C, H, H, generator=g, device="cuda").to(dtype)).requires_grad_(True) if res else None
+    cot = _cl(torch.randn(B, C, H, H, generator=g, device="cuda").to(dtype))
+    y = fused.bn_act(x, bn, relu=relu, res=r)
+    ins = [x, bn.weight, bn.bias] + ([r] if res else [])
+    grads = torch.autograd.grad(y, ins, cot)
+    xr = x.detach().double().requires_grad_(True)
+    rr = r.detach().double().requires_grad_(True) if res else None
+    z = bn_r(xr)
+    if res:
+        z = z + rr
+    yr = torch.relu(z) if relu else z
+    grads_r = torch.autograd.grad(yr, [xr, bn_r.weight, bn_r.bias] + ([rr] if res else []), cot.double())
+    assert (y.double() - yr).abs().max().item() <= tol * max(1.0, yr.abs().max().item())
+    for i, (a, b) in enumerate(zip(grads, grads_r)):
+        e = (a.double() - b).abs().max().item()
+        assert e <= 4 * tol * max(1.0, b.abs().max().item()), "grad %d err %.3e" % (i, e)
+    if training:
+        assert torch.allclose(bn.running_mean.double(), bn_r.running_mean, atol=2e-2 if dtype != torch.float32 else 1e-5)
+        assert torch.allclose(bn.running_var.double(), bn_r.running_var, atol=2e-2 if dtype != torch.float32 else 1e-4)
