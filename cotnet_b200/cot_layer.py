@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import fused
+from . import fused, tc
 from .aggregation_zeropad import AggregationZeropad, LocalConvolution
 
 
@@ -87,9 +87,79 @@ class CotLayer(nn.Module):
         u = fused.AggTapFn.apply(v.contiguous(memory_format=torch.channels_last), w, 1, gc)
         return fused.cot_tail(u, k.contiguous(memory_format=torch.channels_last), self.bn, self.se)
 
+    # ---- inference path: every convolution of the block on the tcgen05 kernels, BatchNorms folded into epilogues ----
+    def _tc_eval_ok(self, x):
+        return (not self.training and not torch.is_grad_enabled() and x.dtype == torch.bfloat16 and self.kernel_size == 3
+                and self.dim % 64 == 0 and tc.conv_tile(self.dim, 4) is not None and x.shape[3] <= 128)
+
+    def _tc_params(self, device):
+        """bf16 GEMM operands + folded BatchNorm scale/shift, cached until a parameter / buffer changes."""
+        key = (str(device),) + tuple(t._version for t in list(self.parameters()) + list(self.buffers()))
+        cache = getattr(self, "_tc_cache", None)
+        if cache is not None and cache["key"] == key:
+            return cache
+        C = self.dim
+
+        def fold(bn):
+            rstd = torch.rsqrt(bn.running_var.float() + bn.eps)
+            scale = bn.weight.float() * rstd
+            return scale.contiguous(), (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
+
+        with torch.no_grad():
+            wk, bnk = tc.prepare_conv3x3_weight(self.key_embed[0].weight, 4)
+            we1 = self.embed[0].weight.detach().view(C // 2, 2 * C).to(torch.bfloat16)
+            cache = {
+                "key": key, "wk": wk, "bnk": bnk, "k_ss": fold(self.key_embed[1]),
+                "we1x": we1[:, :C].contiguous(), "we1k": we1[:, C:].contiguous(), "e_ss": fold(self.embed[1]),
+                "we2": self.embed[3].weight.detach().view(-1, C // 2).to(torch.bfloat16).contiguous(),
+                "be2": self.embed[3].bias.detach().float().contiguous(),
+                "wv": self.conv1x1[0].weight.detach().view(C, C).to(torch.bfloat16).contiguous(),
+                "v_ss": fold(self.conv1x1[1]),
+            }
+        self._tc_cache = cache
+        return cache
+
+    def _forward_tc_eval(self, x):
+        """models/cotnet.py:79-104 in eval mode with NO cuDNN/cuBLAS call: 3x3 grouped key conv = implicit GEMM over TMA
+        pixel boxes, the three 1x1 convs = tcgen05 GEMMs on the NHWC pixel matrix (embed.0 consumes x and k as two
+        operand pairs, no concat), every BatchNorm / bias / ReLU is a GEMM epilogue."""
+        B, C, H, W = x.shape
+        p = self._tc_params(x.device)
+        k = tc.conv3x3_bf16(x, p["wk"], p["bnk"], scale=p["k_ss"][0], shift=p["k_ss"][1], relu=True)
+        e = tc.gemm_bf16(x, p["we1x"], k, p["we1k"], scale=p["e_ss"][0], shift=p["e_ss"][1], relu=True)
+        l = tc.gemm_bf16(e, p["we2"], shift=p["be2"])
+        v = tc.gemm_bf16(x, p["wv"], scale=p["v_ss"][0], shift=p["v_ss"][1])
+        J = l.shape[1]
+        gc = fused.tap_chunk(C // 8)
+        w = fused.group_norm9(l.view(B, H, W, J).permute(0, 3, 1, 2), self.embed[4], gc)
+        u = fused.AggTapFn.apply(v.view(B, H, W, C).permute(0, 3, 1, 2), w, 1, gc)
+        return fused.cot_tail(u, k, self.bn, self.se)
+
+    def _forward_tc_train(self, x):
+        """Autograd-capable path with every convolution of the block on the tcgen05 kernels (forward + data gradients;
+        BatchNorm batch statistics from the GEMM epilogues; no torch.cat, no separate statistics pass)."""
+        B, C, H, W = x.shape
+        ke, em, cv = self.key_embed, self.embed, self.conv1x1
+        k = fused.TcConv3x3Fn.apply(x, ke[0].weight, ke[1].weight, ke[1].bias, ke[1], 4, True)
+        e = fused.TcConv1x1Fn.apply(x, k, em[0].weight, None, em[1].weight, em[1].bias, em[1], True)
+        l = fused.TcConv1x1Fn.apply(e, None, em[3].weight, em[3].bias, None, None, None, False)
+        v = fused.TcConv1x1Fn.apply(x, None, cv[0].weight, None, cv[1].weight, cv[1].bias, cv[1], False)
+        gc = fused.tap_chunk(C // 8)
+        w = fused.group_norm9(l, em[4], gc)
+        u = fused.AggTapFn.apply(v, w, 1, gc)
+        return fused.cot_tail(u, k, self.bn, self.se)
+
+    #: "tc" = tcgen05 kernels for the block's convolutions also when autograd is on; "cudnn" = cuDNN convolutions +
+    #: fused normalisation kernels.  Inference (no_grad, eval) always takes the tcgen05 path when the shape allows.
+    train_conv_backend = "cudnn"
+
     def forward(self, x):
         B, C, H, W = x.shape
         if self.kernel_size == 3 and fused.supported(x):
+            if self._tc_eval_ok(x):
+                return self._forward_tc_eval(x)
+            if self.train_conv_backend == "tc" and fused.tc_supported(x, self.dim):
+                return self._forward_tc_train(x)
             return self._forward_fused(x)
         k = self.key_embed(x)                                              # static context
         w = self.embed(torch.cat([x, k], dim=1))                           # logits, GroupNorm'ed, NOT softmaxed

@@ -478,6 +478,7 @@ struct Nhwc2Args {
   long long x_sn, x_sp, w_sn, w_sp, y_sn, y_sp;
 };
 template <typename T> int nhwc2_fwd(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);
+template <typename T> int agg_tma_fwd(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);   // agg_tma.cu
 template <typename T> int nhwc2_dx(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);
 template <typename T> int nhwc2_dw(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);
 // second-generation NCHW kernels (agg_nchw2.cu)
@@ -570,6 +571,7 @@ template <typename T>
 static int fwd_impl(const Geo& g, const T* x, const T* w, T* y, cudaStream_t st) {
   if (g.layout != COTB200_NCHW && is_same3(g, 3)) {
     int rc2 = 0;
+    if (agg_tma_fwd<T>(nhwc2_args(g), x, w, y, st, &rc2)) return rc2;     // persistent TMA-pipelined kernel (TAP layout)
     if (nhwc2_fwd<T>(nhwc2_args(g), x, w, y, st, &rc2)) return rc2;
   }
   if (g.layout == COTB200_NCHW && nofold(g) && fits32(g) && is_same3(g, 3)) {

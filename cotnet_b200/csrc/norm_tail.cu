@@ -22,6 +22,7 @@ struct RowsGeo {
   int cq;                // packets per row = C / VEC
   int ry;                // row lanes = NT_THREADS / cq_pad
   int cq_pad;            // power-of-two >= cq (thread x extent)
+  int ld;                // row pitch in elements (== C unless the columns are processed in chunks)
 };
 
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + __expf(-z)); }
@@ -59,9 +60,9 @@ col_stats_kernel(const T* __restrict__ x, float* __restrict__ sum, float* __rest
 #pragma unroll
   for (int i = 0; i < VEC; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
   if (active) {
-    const T* xp = x + ((long long)b * g.HW) * g.C + tx * VEC;
+    const T* xp = x + ((long long)b * g.HW) * g.ld + tx * VEC;
     for (int r = r0 + ty; r < r1; r += g.ry) {
-      const Pack<T, VEC> v = ld_pack<T, VEC>(xp + (long long)r * g.C);
+      const Pack<T, VEC> v = ld_pack<T, VEC>(xp + (long long)r * g.ld);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) { const float f = to_acc(v.v[i]); acc[0][i] += f; acc[1][i] = fmaf(f, f, acc[1][i]); }
     }
@@ -261,11 +262,11 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float*
   float sc[VEC], sh[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) { sc[i] = scale[tx * VEC + i]; sh[i] = shift[tx * VEC + i]; }
-  const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+  const long long base = ((long long)b * g.HW) * g.ld + tx * VEC;
   for (int r = r0 + ty; r < r1; r += g.ry) {
-    const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.C);
+    const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.ld);
     Pack<T, VEC> rv;
-    if (RES) rv = ld_pack<T, VEC>(res + base + (long long)r * g.C);
+    if (RES) rv = ld_pack<T, VEC>(res + base + (long long)r * g.ld);
     Pack<T, VEC> o;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -274,7 +275,7 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float*
       if (ACT == 1) z = fmaxf(z, 0.f);
       o.v[i] = Elem<T>::from(z);
     }
-    st_pack<T, VEC>(y + base + (long long)r * g.C, o);
+    st_pack<T, VEC>(y + base + (long long)r * g.ld, o);
   }
 }
 
@@ -291,12 +292,12 @@ bn_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* _
 #pragma unroll
   for (int i = 0; i < VEC; ++i) { acc[0][i] = acc[1][i] = 0.f; m[i] = active ? mu[tx * VEC + i] : 0.f; rs[i] = active ? rstd[tx * VEC + i] : 0.f; }
   if (active) {
-    const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+    const long long base = ((long long)b * g.HW) * g.ld + tx * VEC;
     for (int r = r0 + ty; r < r1; r += g.ry) {
-      const Pack<T, VEC> dv = ld_pack<T, VEC>(dy + base + (long long)r * g.C);
-      const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.C);
+      const Pack<T, VEC> dv = ld_pack<T, VEC>(dy + base + (long long)r * g.ld);
+      const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.ld);
       Pack<T, VEC> yv;
-      if (ACT == 1) yv = ld_pack<T, VEC>(y + base + (long long)r * g.C);
+      if (ACT == 1) yv = ld_pack<T, VEC>(y + base + (long long)r * g.ld);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         float dz = to_acc(dv.v[i]);
@@ -328,12 +329,12 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
     const int c = tx * VEC + i;
     sc[i] = scale[c]; m[i] = mu[c]; rs[i] = rstd[c]; k1[i] = c1 ? c1[c] : 0.f; k2[i] = c2 ? c2[c] : 0.f;
   }
-  const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+  const long long base = ((long long)b * g.HW) * g.ld + tx * VEC;
   for (int r = r0 + ty; r < r1; r += g.ry) {
-    const Pack<T, VEC> dv = ld_pack<T, VEC>(dy + base + (long long)r * g.C);
-    const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.C);
+    const Pack<T, VEC> dv = ld_pack<T, VEC>(dy + base + (long long)r * g.ld);
+    const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.ld);
     Pack<T, VEC> yv;
-    if (ACT == 1) yv = ld_pack<T, VEC>(y + base + (long long)r * g.C);
+    if (ACT == 1) yv = ld_pack<T, VEC>(y + base + (long long)r * g.ld);
     Pack<T, VEC> o, o2;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -342,8 +343,8 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
       o.v[i] = Elem<T>::from(sc[i] * (dz - k1[i] - (to_acc(xv.v[i]) - m[i]) * rs[i] * k2[i]));
       if (RES) o2.v[i] = Elem<T>::from(dz);
     }
-    st_pack<T, VEC>(dx + base + (long long)r * g.C, o);
-    if (RES) st_pack<T, VEC>(dres + base + (long long)r * g.C, o2);
+    st_pack<T, VEC>(dx + base + (long long)r * g.ld, o);
+    if (RES) st_pack<T, VEC>(dres + base + (long long)r * g.ld, o2);
   }
 }
 
@@ -529,7 +530,7 @@ static int pick_vec(int C, const void* p0, const void* p1 = nullptr, const void*
 
 static int make_geo(RowsGeo& g, int B, int HW, int C, int vec, int nsums, size_t* smem) {
   if (B <= 0 || HW <= 0 || C <= 0) { set_error("norm/tail kernel: non-positive dims"); return COTB200_EINVAL; }
-  g.B = B; g.HW = HW; g.C = C; g.cq = C / vec;
+  g.B = B; g.HW = HW; g.C = C; g.cq = C / vec; g.ld = C;
   g.cq_pad = 1;
   while (g.cq_pad < g.cq) g.cq_pad <<= 1;
   if (g.cq_pad > NT_THREADS) { set_error("norm/tail kernel: %d channels exceed the %d-packet row limit", C, NT_THREADS); return COTB200_EINVAL; }
@@ -545,6 +546,15 @@ static int make_geo(RowsGeo& g, int B, int HW, int C, int vec, int nsums, size_t
   g.rows_per_cta = rows;
   *smem = (size_t)nsums * g.ry * C * sizeof(float);
   if (*smem > 96 * 1024) { set_error("norm/tail kernel: shared memory %zu too large", *smem); return COTB200_EINVAL; }
+  return 0;
+}
+
+// Wide tensors (more than 256 packets per row, e.g. the 2048-channel bn3 of layer4 in fp32) are processed in equal
+// column chunks: returns the chunk width (a multiple of vec that divides C) or C itself.
+static int col_chunk(int C, int vec) {
+  if (C / vec <= NT_THREADS) return C;
+  for (int nz = 2; nz <= 64; ++nz)
+    if (C % nz == 0 && (C / nz) % vec == 0 && (C / nz) / vec <= NT_THREADS) return C / nz;
   return 0;
 }
 
@@ -578,13 +588,19 @@ extern "C" int cotb200_col_stats(int dtype, int B, int HW, int C, const void* x,
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
       const int vec = pick_vec<T>(C, x);
-      RowsGeo g; size_t smem;
-      int rc = make_geo(g, B, HW, C, vec, 2, &smem);
-      if (rc) return rc;
-      COTB200_PROF("col_stats");
-      NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(col_stats_kernel<T, V>, smem))) return rc;
-                             col_stats_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)x, sum, sq, g); });
-      return check_launch("col_stats");
+      const int cw = col_chunk(C, vec);
+      if (!cw) { set_error("col_stats: cannot tile %d channels", C); return COTB200_EINVAL; }
+      for (int c0 = 0; c0 < C; c0 += cw) {
+        RowsGeo g; size_t smem;
+        int rc = make_geo(g, B, HW, cw, vec, 2, &smem);
+        if (rc) return rc;
+        g.ld = C;
+        COTB200_PROF("col_stats");
+        NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(col_stats_kernel<T, V>, smem))) return rc;
+                               col_stats_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)x + c0, sum + c0, sq + c0, g); });
+        if ((rc = check_launch("col_stats"))) return rc;
+      }
+      return 0;
     }
   });
   return 0;
@@ -782,17 +798,24 @@ extern "C" int cotb200_bn_apply(int dtype, int B, int HW, int C, const void* x, 
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
       const int vec = pick_vec<T>(C, x, res, y);
-      RowsGeo g; size_t smem;
-      int rc = make_geo(g, B, HW, C, vec, 1, &smem);
-      if (rc) return rc;
-      COTB200_PROF("bn_apply");
-      NT_DISPATCH_VEC(vec, {
-        if (relu) { if (res) bn_apply_kernel<T, V, 1, true><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)x, (const T*)res, scale, shift, (T*)y, g);
-                    else bn_apply_kernel<T, V, 1, false><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)x, nullptr, scale, shift, (T*)y, g); }
-        else { if (res) bn_apply_kernel<T, V, 0, true><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)x, (const T*)res, scale, shift, (T*)y, g);
-               else bn_apply_kernel<T, V, 0, false><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)x, nullptr, scale, shift, (T*)y, g); }
-      });
-      return check_launch("bn_apply");
+      const int cw = col_chunk(C, vec);
+      if (!cw) { set_error("bn_apply: cannot tile %d channels", C); return COTB200_EINVAL; }
+      for (int c0 = 0; c0 < C; c0 += cw) {
+        RowsGeo g; size_t smem;
+        int rc = make_geo(g, B, HW, cw, vec, 1, &smem);
+        if (rc) return rc;
+        g.ld = C;
+        const T* xp = (const T*)x + c0; const T* rp = res ? (const T*)res + c0 : nullptr; T* yp = (T*)y + c0;
+        COTB200_PROF("bn_apply");
+        NT_DISPATCH_VEC(vec, {
+          if (relu) { if (res) bn_apply_kernel<T, V, 1, true><<<NT_GRID, NT_THREADS, 0, st>>>(xp, rp, scale + c0, shift + c0, yp, g);
+                      else bn_apply_kernel<T, V, 1, false><<<NT_GRID, NT_THREADS, 0, st>>>(xp, nullptr, scale + c0, shift + c0, yp, g); }
+          else { if (res) bn_apply_kernel<T, V, 0, true><<<NT_GRID, NT_THREADS, 0, st>>>(xp, rp, scale + c0, shift + c0, yp, g);
+                 else bn_apply_kernel<T, V, 0, false><<<NT_GRID, NT_THREADS, 0, st>>>(xp, nullptr, scale + c0, shift + c0, yp, g); }
+        });
+        if ((rc = check_launch("bn_apply"))) return rc;
+      }
+      return 0;
     }
   });
   return 0;
@@ -806,17 +829,24 @@ extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* 
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
       const int vec = pick_vec<T>(C, dy, x, y);
-      RowsGeo g; size_t smem;
-      int rc = make_geo(g, B, HW, C, vec, 2, &smem);
-      if (rc) return rc;
-      COTB200_PROF("bn_bwd_sums");
-      NT_DISPATCH_VEC(vec, {
-        if (relu) { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 1>, smem))) return rc;
-                    bn_bwd_sums_kernel<T, V, 1><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dy, (const T*)x, (const T*)y, mu, rstd, sum_dz, sum_dzx, g); }
-        else { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 0>, smem))) return rc;
-               bn_bwd_sums_kernel<T, V, 0><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dy, (const T*)x, nullptr, mu, rstd, sum_dz, sum_dzx, g); }
-      });
-      return check_launch("bn_bwd_sums");
+      const int cw = col_chunk(C, vec);
+      if (!cw) { set_error("bn_bwd_sums: cannot tile %d channels", C); return COTB200_EINVAL; }
+      for (int c0 = 0; c0 < C; c0 += cw) {
+        RowsGeo g; size_t smem;
+        int rc = make_geo(g, B, HW, cw, vec, 2, &smem);
+        if (rc) return rc;
+        g.ld = C;
+        const T* dp = (const T*)dy + c0; const T* xp = (const T*)x + c0; const T* yp = y ? (const T*)y + c0 : nullptr;
+        COTB200_PROF("bn_bwd_sums");
+        NT_DISPATCH_VEC(vec, {
+          if (relu) { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 1>, smem))) return rc;
+                      bn_bwd_sums_kernel<T, V, 1><<<NT_GRID, NT_THREADS, smem, st>>>(dp, xp, yp, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
+          else { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 0>, smem))) return rc;
+                 bn_bwd_sums_kernel<T, V, 0><<<NT_GRID, NT_THREADS, smem, st>>>(dp, xp, nullptr, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
+        });
+        if ((rc = check_launch("bn_bwd_sums"))) return rc;
+      }
+      return 0;
     }
   });
   return 0;
@@ -830,19 +860,28 @@ extern "C" int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void*
   cudaStream_t st = (cudaStream_t)stream;
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
-      const int vec = pick_vec<T>(C, dy, x, y, dx);
-      RowsGeo g; size_t smem;
-      int rc = make_geo(g, B, HW, C, (dres && ((uintptr_t)dres & (vec * sizeof(T) - 1))) ? 1 : vec, 1, &smem);
-      if (rc) return rc;
-      const int v2 = g.C / g.cq;
-      COTB200_PROF("bn_bwd_apply");
-      NT_DISPATCH_VEC(v2, {
-        if (relu) { if (dres) bn_bwd_apply_kernel<T, V, 1, true><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, scale, mu, rstd, c1, c2, (T*)dx, (T*)dres, g);
-                    else bn_bwd_apply_kernel<T, V, 1, false><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dy, (const T*)x, (const T*)y, scale, mu, rstd, c1, c2, (T*)dx, nullptr, g); }
-        else { if (dres) bn_bwd_apply_kernel<T, V, 0, true><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dy, (const T*)x, nullptr, scale, mu, rstd, c1, c2, (T*)dx, (T*)dres, g);
-               else bn_bwd_apply_kernel<T, V, 0, false><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dy, (const T*)x, nullptr, scale, mu, rstd, c1, c2, (T*)dx, nullptr, g); }
-      });
-      return check_launch("bn_bwd_apply");
+      int vec = pick_vec<T>(C, dy, x, y, dx);
+      if (dres && ((uintptr_t)dres & (vec * sizeof(T) - 1))) vec = 1;
+      const int cw = col_chunk(C, vec);
+      if (!cw) { set_error("bn_bwd_apply: cannot tile %d channels", C); return COTB200_EINVAL; }
+      for (int c0 = 0; c0 < C; c0 += cw) {
+        RowsGeo g; size_t smem;
+        int rc = make_geo(g, B, HW, cw, vec, 1, &smem);
+        if (rc) return rc;
+        g.ld = C;
+        const T* dp = (const T*)dy + c0; const T* xp = (const T*)x + c0; const T* yp = y ? (const T*)y + c0 : nullptr;
+        T* dxp = (T*)dx + c0; T* drp = dres ? (T*)dres + c0 : nullptr;
+        const float* k1 = c1 ? c1 + c0 : nullptr; const float* k2 = c2 ? c2 + c0 : nullptr;
+        COTB200_PROF("bn_bwd_apply");
+        NT_DISPATCH_VEC(vec, {
+          if (relu) { if (dres) bn_bwd_apply_kernel<T, V, 1, true><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, yp, scale + c0, mu + c0, rstd + c0, k1, k2, dxp, drp, g);
+                      else bn_bwd_apply_kernel<T, V, 1, false><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, yp, scale + c0, mu + c0, rstd + c0, k1, k2, dxp, nullptr, g); }
+          else { if (dres) bn_bwd_apply_kernel<T, V, 0, true><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, nullptr, scale + c0, mu + c0, rstd + c0, k1, k2, dxp, drp, g);
+                 else bn_bwd_apply_kernel<T, V, 0, false><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, nullptr, scale + c0, mu + c0, rstd + c0, k1, k2, dxp, nullptr, g); }
+        });
+        if ((rc = check_launch("bn_bwd_apply"))) return rc;
+      }
+      return 0;
     }
   });
   return 0;

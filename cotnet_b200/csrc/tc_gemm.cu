@@ -34,6 +34,7 @@ struct TcParams {
   int H, W, B, hbox, bbox;  // conv geometry
   int kc;                   // conv: 64-channel chunks per tap (= bn / 64)
   int relu;
+  int stages;               // smem ring depth actually used (<= TC_STAGES): short K loops take less smem -> more CTAs/SM
   long long ldd;            // D row pitch (elements)
   __nv_bfloat16* D;
   const float* scale;       // [N] or null (=1)
@@ -130,7 +131,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 3)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -188,8 +189,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1;
+        const int s = kb % p.stages;
+        const uint32_t ph = (kb / p.stages) & 1;
         mbar_wait(smem_u32(&s_empty[s]), ph ^ 1);
         const uint32_t full = smem_u32(&s_full[s]);
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
@@ -217,8 +218,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(p.bn);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1;
+        const int s = kb % p.stages;
+        const uint32_t ph = (kb / p.stages) & 1;
         mbar_wait(smem_u32(&s_full[s]), ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
@@ -347,10 +348,12 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, 
 }
 
 static int tc_launch(const CUtensorMap& a1, const CUtensorMap& b1, const CUtensorMap& a2, const CUtensorMap& b2,
-                     const TcParams& p, int m_tiles, cudaStream_t st, const char* what) {
+                     TcParams p, int m_tiles, cudaStream_t st, const char* what) {
   const int a_bytes = TC_BM * TC_BK * 2, b_bytes = p.bn * TC_BK * 2;
   const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
-  const int smem = TC_STAGES * stage_bytes + 1024;
+  const int nkb = p.mode == 0 ? p.kb1 + p.kb2 : 9 * p.kc;
+  p.stages = nkb < TC_STAGES ? nkb : TC_STAGES;
+  const int smem = p.stages * stage_bytes + 1024;
   static int configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -275,20 +275,22 @@ def _se_fp32(se, p):
     module's parameters / buffers; differentiable w.r.t. p and the parameters."""
     c0, b1, c3 = se[0], se[1], se[3]
     z = torch.nn.functional.linear(p, c0.weight.float().flatten(1), None if c0.bias is None else c0.bias.float())
+    w1, bb1 = b1.weight.float(), b1.bias.float()
     if b1.training or b1.running_mean is None:
-        rm = None if b1.running_mean is None else b1.running_mean.float()
-        rv = None if b1.running_var is None else b1.running_var.float()
-        if b1.num_batches_tracked is not None:
-            b1.num_batches_tracked += 1
-        mom = b1.momentum if b1.momentum is not None else 1.0 / float(b1.num_batches_tracked)
-        z = torch.nn.functional.batch_norm(z, rm, rv, b1.weight.float(), b1.bias.float(), True, mom, b1.eps)
-        if rm is not None:
+        # batch statistics written out with differentiable torch ops (no in-place update of tensors autograd saved)
+        n = z.shape[0]
+        mean = z.mean(0)
+        var = z.var(0, unbiased=False)
+        zn = (z - mean) * torch.rsqrt(var + b1.eps) * w1 + bb1
+        if b1.running_mean is not None and b1.track_running_stats:
             with torch.no_grad():
-                b1.running_mean.copy_(rm)
-                b1.running_var.copy_(rv)
+                b1.num_batches_tracked += 1
+                mom = b1.momentum if b1.momentum is not None else 1.0 / float(b1.num_batches_tracked)
+                b1.running_mean.mul_(1 - mom).add_(mean.detach().to(b1.running_mean.dtype), alpha=mom)
+                b1.running_var.mul_(1 - mom).add_((var.detach() * (n / max(n - 1.0, 1.0))).to(b1.running_var.dtype), alpha=mom)
+        z = zn
     else:
-        z = torch.nn.functional.batch_norm(z, b1.running_mean.float(), b1.running_var.float(), b1.weight.float(),
-                                           b1.bias.float(), False, 0.0, b1.eps)
+        z = (z - b1.running_mean.float()) * torch.rsqrt(b1.running_var.float() + b1.eps) * w1 + bb1
     z = torch.relu(z)
     return torch.nn.functional.linear(z, c3.weight.float().flatten(1), None if c3.bias is None else c3.bias.float())
 
@@ -300,3 +302,192 @@ def group_norm9(l, gn: torch.nn.GroupNorm, gc=0):
 def cot_tail(u, k, bn: torch.nn.BatchNorm2d, se: torch.nn.Module):
     params = [p for p in se.parameters()]
     return CotTailFn.apply(u, k, bn.weight, bn.bias, bn, se, *params)
+
+
+# ====================================================================================================================
+# Dense parts of the block on the tcgen05 kernels, with autograd.
+#   forward      : tc GEMM / implicit-GEMM conv; training-mode BatchNorm statistics come out of the GEMM epilogue
+#   data gradient: the same tc kernels (transposed weights; the 3x3 conv with flipped taps)
+#   weight grad  : cuBLAS / cuDNN through torch (the MN-major tcgen05 variant is future work, DESIGN.md section 6)
+# ====================================================================================================================
+from . import tc as _tc  # noqa: E402
+
+
+def _rows2d(t):
+    """[B,C,H,W] channels_last -> [B*H*W, C] view."""
+    B, C, H, W = t.shape
+    return t.permute(0, 2, 3, 1).reshape(B * H * W, C)
+
+
+def _bn_from_sums(sums, n, bn, weight, bias):
+    """(scale, shift, mean, rstd) from epilogue column sums; updates the running buffers like nn.BatchNorm2d."""
+    mean = sums[0] / n
+    var = (sums[1] / n - mean * mean).clamp_min_(0.0)
+    if bn.running_mean is not None and bn.track_running_stats:
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            bn.running_mean.mul_(1 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)
+            bn.running_var.mul_(1 - mom).add_((var * (n / max(n - 1.0, 1.0))).to(bn.running_var.dtype), alpha=mom)
+    rstd = torch.rsqrt(var + bn.eps).contiguous()
+    scale = (weight.detach().float() * rstd).contiguous()
+    shift = (bias.detach().float() - mean * scale).contiguous()
+    return scale, shift, mean.contiguous(), rstd
+
+
+def _bn_eval_fold(bn, weight, bias):
+    rstd = torch.rsqrt(bn.running_var.float() + bn.eps).contiguous()
+    scale = (weight.detach().float() * rstd).contiguous()
+    mean = bn.running_mean.float().contiguous()
+    return scale, (bias.detach().float() - mean * scale).contiguous(), mean, rstd
+
+
+class TcConv1x1Fn(Function):
+    """y = act(BN(conv1x1([a1 ; a2]))) or conv1x1 + bias, on channels_last bf16 activations.
+
+    a1 [B,K1,H,W], a2 [B,K2,H,W] or None (the concat-free embed.0 of models/cotnet.py:81,52), weight [N, K1+K2, 1, 1].
+    bn = nn.BatchNorm2d or None (then `cbias` is the conv bias or None)."""
+
+    @staticmethod
+    def forward(ctx, a1, a2, weight, cbias, bn_w, bn_b, bn, relu):
+        assert _is_cl(a1) and a1.dtype == torch.bfloat16 and (a2 is None or (_is_cl(a2) and a2.dtype == a1.dtype))
+        B, K1, H, W = a1.shape
+        K2 = 0 if a2 is None else a2.shape[1]
+        N = weight.shape[0]
+        M = B * H * W
+        lib, st, dt = _lib.load(), _lib.stream_ptr(a1), _lib.dtype_code(a1)
+        a1, a2 = a1.detach(), (None if a2 is None else a2.detach())
+        wb = weight.detach().reshape(N, K1 + K2).to(torch.bfloat16).contiguous()
+        b1, b2 = wb[:, :K1], (wb[:, K1:] if K2 else None)
+        out = torch.empty((B, N, H, W), dtype=torch.bfloat16, device=a1.device, memory_format=torch.channels_last)
+        out2d = _rows2d(out)
+        pre = scale = mean = rstd = None
+        batch = False
+        if bn is None:
+            _tc.gemm_bf16(a1, b1, a2, b2, shift=None if cbias is None else cbias.detach().float().contiguous(), relu=relu, out=out2d)
+        elif bn.training or bn.running_mean is None:
+            batch = True
+            sums = torch.zeros(2, N, dtype=torch.float32, device=a1.device)
+            pre = torch.empty_like(out, memory_format=torch.channels_last)
+            _tc.gemm_bf16(a1, b1, a2, b2, stats=(sums[0], sums[1]), out=_rows2d(pre))
+            scale, shift, mean, rstd = _bn_from_sums(sums, float(M), bn, bn_w, bn_b)
+            _lib.check(lib.cotb200_bn_apply(dt, B, H * W, N, pre.data_ptr(), None, scale.data_ptr(), shift.data_ptr(),
+                                            1 if relu else 0, out.data_ptr(), st), "bn_apply")
+        else:
+            scale, shift, mean, rstd = _bn_eval_fold(bn, bn_w, bn_b)
+            _tc.gemm_bf16(a1, b1, a2, b2, scale=scale, shift=shift, relu=relu, out=out2d)
+        need_bwd = any(ctx.needs_input_grad)
+        if need_bwd and bn is not None and pre is None:      # eval-mode module under grad: BN backward needs the raw conv output
+            pre = torch.empty_like(out, memory_format=torch.channels_last)
+            _tc.gemm_bf16(a1, b1, a2, b2, out=_rows2d(pre))
+        ctx.save_for_backward(a1, a2, wb, pre, out if relu else None, scale, mean, rstd)
+        ctx.cfg = (relu, batch, bn is not None, cbias is not None, weight.dtype, weight.shape,
+                   None if bn_w is None else bn_w.dtype, None if cbias is None else cbias.dtype, K1, K2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        a1, a2, wb, pre, y, scale, mean, rstd = ctx.saved_tensors
+        relu, batch, has_bn, has_bias, wdt, wshape, bndt, cbdt, K1, K2 = ctx.cfg
+        B, N, H, W = dy.shape
+        M = B * H * W
+        lib, st, dt = _lib.load(), _lib.stream_ptr(dy), _lib.BF16
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dgamma = dbeta = dcb = None
+        if has_bn:
+            sums = torch.zeros(2, N, dtype=torch.float32, device=dy.device)
+            _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), mean.data_ptr(),
+                                               rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
+                       "bn_bwd_sums")
+            c1 = c2 = None
+            if batch:
+                c1, c2 = (sums[0] / M).contiguous(), (sums[1] / M).contiguous()
+            dpre = torch.empty_like(dy, memory_format=torch.channels_last)
+            _lib.check(lib.cotb200_bn_bwd_apply(dt, B, H * W, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
+                                                mean.data_ptr(), rstd.data_ptr(), _lib.ptr(c1), _lib.ptr(c2), 1 if relu else 0,
+                                                dpre.data_ptr(), None, st), "bn_bwd_apply")
+            dgamma, dbeta = sums[1].to(bndt), sums[0].to(bndt)
+        else:
+            dpre = dy if not relu else dy * (y > 0)
+            if has_bias:
+                dcb = _rows2d(dpre).float().sum(0).to(cbdt)
+        d2 = _rows2d(dpre)
+        da1 = da2 = None
+        wt = wb.t().contiguous()                                  # [K1+K2, N]: B operand of the data-gradient GEMM
+        if ctx.needs_input_grad[0]:
+            da1 = torch.empty_like(a1, memory_format=torch.channels_last)
+            _tc.gemm_bf16(dpre, wt[:K1], out=_rows2d(da1))
+        if a2 is not None and ctx.needs_input_grad[1]:
+            da2 = torch.empty_like(a2, memory_format=torch.channels_last)
+            _tc.gemm_bf16(dpre, wt[K1:], out=_rows2d(da2))
+        dw = None
+        if ctx.needs_input_grad[2]:
+            parts = [torch.mm(d2.t(), _rows2d(a1))]               # weight gradient: cuBLAS (see module docstring)
+            if a2 is not None:
+                parts.append(torch.mm(d2.t(), _rows2d(a2)))
+            dw = torch.cat(parts, 1).reshape(wshape).to(wdt)
+        return da1, da2, dw, dcb, dgamma, dbeta, None, None
+
+
+class TcConv3x3Fn(Function):
+    """k = ReLU(BN(conv3x3 grouped(x))) -- key_embed of models/cotnet.py:43-47 -- on channels_last bf16."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bn_w, bn_b, bn, groups, relu):
+        assert _is_cl(x) and x.dtype == torch.bfloat16
+        B, C, H, W = x.shape
+        M = B * H * W
+        lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.BF16
+        x = x.detach()
+        wp, bnt = _tc.prepare_conv3x3_weight(weight, groups)
+        out = torch.empty_like(x, memory_format=torch.channels_last)
+        pre = None
+        batch = bn.training or bn.running_mean is None
+        if batch:
+            sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)
+            pre = torch.empty_like(x, memory_format=torch.channels_last)
+            _tc.conv3x3_bf16(x, wp, bnt, stats=(sums[0], sums[1]), out=pre)
+            scale, shift, mean, rstd = _bn_from_sums(sums, float(M), bn, bn_w, bn_b)
+            _lib.check(lib.cotb200_bn_apply(dt, B, H * W, C, pre.data_ptr(), None, scale.data_ptr(), shift.data_ptr(),
+                                            1 if relu else 0, out.data_ptr(), st), "bn_apply")
+        else:
+            scale, shift, mean, rstd = _bn_eval_fold(bn, bn_w, bn_b)
+            _tc.conv3x3_bf16(x, wp, bnt, scale=scale, shift=shift, relu=relu, out=out)
+            if any(ctx.needs_input_grad):
+                pre = _tc.conv3x3_bf16(x, wp, bnt)
+        ctx.save_for_backward(x, weight.detach(), pre, out if relu else None, scale, mean, rstd)
+        ctx.cfg = (relu, batch, groups, bn_w.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, pre, y, scale, mean, rstd = ctx.saved_tensors
+        relu, batch, groups, bndt = ctx.cfg
+        B, C, H, W = x.shape
+        M = B * H * W
+        lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.BF16
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)
+        _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), mean.data_ptr(),
+                                           rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
+                   "bn_bwd_sums")
+        c1 = c2 = None
+        if batch:
+            c1, c2 = (sums[0] / M).contiguous(), (sums[1] / M).contiguous()
+        dpre = torch.empty_like(dy, memory_format=torch.channels_last)
+        _lib.check(lib.cotb200_bn_bwd_apply(dt, B, H * W, C, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
+                                            mean.data_ptr(), rstd.data_ptr(), _lib.ptr(c1), _lib.ptr(c2), 1 if relu else 0,
+                                            dpre.data_ptr(), None, st), "bn_bwd_apply")
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            wpt, bnt = _tc.prepare_conv3x3_weight(weight, groups, transpose_for_dgrad=True)
+            dx = _tc.conv3x3_bf16(dpre, wpt, bnt)
+        if ctx.needs_input_grad[1]:
+            # weight gradient: cuDNN grouped wgrad through torch (DESIGN.md section 6)
+            dw = torch.nn.grad.conv2d_weight(x, weight.shape, dpre, stride=1, padding=1, dilation=1, groups=groups).to(weight.dtype)
+        return dx, dw, sums[1].to(bndt), sums[0].to(bndt), None, None, None
+
+
+def tc_supported(x, dim):
+    return (x.is_cuda and x.dtype == torch.bfloat16 and _is_cl(x) and not x.is_contiguous() and dim % 64 == 0
+            and _tc.conv_tile(dim, 4) is not None and x.shape[3] <= 128)

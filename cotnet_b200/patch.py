@@ -10,8 +10,11 @@ imports to the mirrors in this package and (optionally) swaps the layer classes 
 import sys
 import types
 
-from . import aggregation_zeropad as _agg
-from . import aggregation_zeropad_mix as _mix
+import importlib
+
+# NB: the package re-exports functions named like these sub-modules, so fetch the MODULES explicitly
+_agg = importlib.import_module(__package__ + ".aggregation_zeropad")
+_mix = importlib.import_module(__package__ + ".aggregation_zeropad_mix")
 
 # variants imported by lr_net / botnet / flops_counter but constructed by no registered model
 _UNUSED_VARIANTS = {

@@ -126,3 +126,28 @@ def test_backbone_matches_oracle_model_fp32():
         got_cl = m.to(memory_format=torch.channels_last)(x.cuda().contiguous(memory_format=torch.channels_last))
     assert torch.allclose(got.cpu(), want, atol=1e-3, rtol=1e-3)
     assert torch.allclose(got_cl.cpu(), want, atol=1e-3, rtol=1e-3)
+
+
+@pytest.mark.parametrize("dim,H", [(64, 28), (128, 14), (256, 14), (512, 7)])
+def test_tc_training_backend_vs_oracle(dim, H):
+    """train_conv_backend='tc': every convolution of the block on the tcgen05 kernels, forward + backward, vs the oracle."""
+    gen = torch.Generator().manual_seed(dim)
+    sd64 = cot_ref.init_state_dict("cot", dim, gen, dtype=torch.float64, perturb=True)
+    dtype = torch.bfloat16
+    sd64 = {k: (v.to(dtype).double() if v.dtype.is_floating_point else v) for k, v in sd64.items()}
+    B = 16
+    x64 = torch.relu(torch.randn(B, dim, H, H, generator=gen, dtype=torch.float64)).to(dtype).double()
+    m = _mods().CotLayer(dim, 3)
+    m.load_state_dict(sd64, strict=True)
+    m = m.to(dtype).cuda().to(memory_format=torch.channels_last).train()
+    m.train_conv_backend = "tc"
+    x = x64.to(dtype).cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    out = m(x)
+    out.float().sum().backward()
+    xr = x64.clone().requires_grad_(True)
+    want = cot_ref.cot_layer(xr, {k: v.clone() for k, v in sd64.items()}, training=True)
+    want.sum().backward()
+    scale = max(1.0, want.abs().max().item())
+    assert (out.double().cpu() - want.detach()).abs().max().item() <= 0.1 * scale
+    gs = max(1.0, xr.grad.abs().max().item())
+    assert (x.grad.double().cpu() - xr.grad).abs().max().item() <= 0.15 * gs

@@ -76,3 +76,71 @@ def test_conv3x3(C, groups, H, B):
     dx = tc.conv3x3_bf16(gy, wpt, bnt)
     want_dx = torch.nn.grad.conv2d_input(x.shape, w.float(), gy.float(), 1, 1, 1, groups)
     _close(dx, want_dx)
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("training", [False, True])
+@pytest.mark.parametrize("two", [False, True])
+def test_tc_conv1x1_fn_autograd(training, two):
+    """TcConv1x1Fn (tcgen05 forward + data gradient, BN statistics from the epilogue) vs eager conv+BN+ReLU in fp32."""
+    import copy
+    import torch.nn as nn
+    from cotnet_b200 import fused
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, K1, K2, N, H = 8, 64, (64 if two else 0), 32, 14
+    conv = nn.Conv2d(K1 + K2, N, 1, bias=False).cuda()
+    bn = nn.BatchNorm2d(N).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.bfloat16().float())
+        bn.weight.uniform_(0.5, 1.5, generator=g); bn.bias.normal_(0, 0.3, generator=g)
+        bn.running_mean.normal_(0, 0.3, generator=g); bn.running_var.uniform_(0.5, 2, generator=g)
+    conv_r, bn_r = copy.deepcopy(conv), copy.deepcopy(bn)
+    bn.train(training); bn_r.train(training)
+    a1 = _cl(torch.randn(B, K1, H, H, generator=g, device="cuda").bfloat16()).requires_grad_(True)
+    a2 = _cl(torch.randn(B, K2, H, H, generator=g, device="cuda").bfloat16()).requires_grad_(True) if two else None
+    cot = _cl(torch.randn(B, N, H, H, generator=g, device="cuda").bfloat16())
+    y = fused.TcConv1x1Fn.apply(a1, a2, conv.weight, None, bn.weight, bn.bias, bn, True)
+    ins = [a1, conv.weight, bn.weight, bn.bias] + ([a2] if two else [])
+    grads = torch.autograd.grad(y, ins, cot)
+    a1r = a1.detach().float().requires_grad_(True)
+    a2r = a2.detach().float().requires_grad_(True) if two else None
+    xin = torch.cat([a1r, a2r], 1) if two else a1r
+    yr = torch.relu(bn_r(conv_r(xin)))
+    grads_r = torch.autograd.grad(yr, [a1r, conv_r.weight, bn_r.weight, bn_r.bias] + ([a2r] if two else []), cot.float())
+    _close(y, yr, 3e-2)
+    for a, b in zip(grads, grads_r):
+        err = (a.float() - b).abs().max().item()
+        assert err <= 4e-2 * max(1.0, b.abs().max().item()), err
+    if training:
+        assert torch.allclose(bn.running_mean, bn_r.running_mean, atol=2e-2)
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_tc_conv3x3_fn_autograd(training):
+    import copy
+    import torch.nn as nn
+    from cotnet_b200 import fused
+    g = torch.Generator(device="cuda").manual_seed(4)
+    B, C, H = 6, 128, 14
+    conv = nn.Conv2d(C, C, 3, padding=1, groups=4, bias=False).cuda()
+    bn = nn.BatchNorm2d(C).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.bfloat16().float())
+        bn.weight.uniform_(0.5, 1.5, generator=g); bn.bias.normal_(0, 0.3, generator=g)
+        bn.running_mean.normal_(0, 0.3, generator=g); bn.running_var.uniform_(0.5, 2, generator=g)
+    conv_r, bn_r = copy.deepcopy(conv), copy.deepcopy(bn)
+    bn.train(training); bn_r.train(training)
+    x = _cl(torch.randn(B, C, H, H, generator=g, device="cuda").bfloat16()).requires_grad_(True)
+    cot = _cl(torch.randn(B, C, H, H, generator=g, device="cuda").bfloat16())
+    y = fused.TcConv3x3Fn.apply(x, conv.weight, bn.weight, bn.bias, bn, 4, True)
+    grads = torch.autograd.grad(y, [x, conv.weight, bn.weight, bn.bias], cot)
+    xr = x.detach().float().requires_grad_(True)
+    yr = torch.relu(bn_r(conv_r(xr)))
+    grads_r = torch.autograd.grad(yr, [xr, conv_r.weight, bn_r.weight, bn_r.bias], cot.float())
+    _close(y, yr, 3e-2)
+    for a, b in zip(grads, grads_r):
+        err = (a.float() - b).abs().max().item()
+        assert err <= 4e-2 * max(1.0, b.abs().max().item()), err

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from cotnet_b200 import _lib, aggregation_zeropad, aggregation_zeropad_mix  # noqa: E402
+from cotnet_b200 import _lib, aggregation_zeropad, aggregation_zeropad_mix, fused  # noqa: E402
 
 STAGES = [(64, 8, 56), (128, 16, 28), (256, 32, 14), (512, 64, 7)]
 
@@ -62,7 +62,7 @@ def main():
     for si in [int(s) for s in a.stages.split(",")]:
         C, wc, HW = STAGES[si]
         for dtype, es in ((torch.bfloat16, 2), (torch.float32, 4)):
-            for layout in ("nhwc", "nchw"):
+            for layout in ("tap", "nhwc", "nchw"):
                 if a.only and a.only != layout:
                     continue
                 elems = (2 * C + 9 * wc) * HW * HW * B
@@ -72,6 +72,10 @@ def main():
                     x = torch.randn(B, C, HW, HW, device=dev, dtype=dtype)
                     w = torch.randn(B, 1, wc, 9, HW, HW, device=dev, dtype=dtype)
                     g = torch.randn(B, C, HW, HW, device=dev, dtype=dtype)
+                    if layout == "tap":      # block-internal order: w [B, 9*wc, H, W] channels_last, tap-major chunks of 8
+                        x = x.contiguous(memory_format=torch.channels_last)
+                        g = g.contiguous(memory_format=torch.channels_last)
+                        w = torch.randn(B, 9 * wc, HW, HW, device=dev, dtype=dtype).contiguous(memory_format=torch.channels_last)
                     if layout == "nhwc":
                         x = x.contiguous(memory_format=torch.channels_last)
                         g = g.contiguous(memory_format=torch.channels_last)
@@ -80,7 +84,10 @@ def main():
                 ys = [None] * nsets
 
                 def fwd(i):
-                    ys[i] = aggregation_zeropad(xs[i], ws[i], 3, 1, 1, 1)
+                    if layout == "tap":
+                        ys[i] = fused.AggTapFn.apply(xs[i], ws[i], 1, 8)
+                    else:
+                        ys[i] = aggregation_zeropad(xs[i], ws[i], 3, 1, 1, 1)
 
                 def bwd(i):
                     torch.autograd.grad(ys[i], (xs[i], ws[i]), gs[i], retain_graph=True)
