@@ -102,46 +102,6 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- algorithmic bytes
-def cot_layer_shapes(model, batch, res):
-    """(C, H, W, fold) of every CoT layer call in one forward, by running shape hooks on a meta-free dry pass."""
-    from cotnet_b200.cot_layer import CotLayer, CoXtLayer
-    shapes = []
-    H = res // 4
-    for name, mod in model.named_modules():
-        if isinstance(mod, (CotLayer, CoXtLayer)):
-            stage = int(name.split(".")[0][-1])           # layer1..4 -> 56,28,14,7 at 224 (CoT runs after the avd pool)
-            h = res // (4 * 2 ** (stage - 1))
-            shapes.append((mod.dim, h, h, 2 if isinstance(mod, CoXtLayer) else 1))
-    return shapes
-
-
-# ALGORITHMIC elements moved per pixel by each libcotb200 kernel, in units of (C, J=9C/8); DESIGN.md section 4
-_KERNEL_ELEMS = {
-    # LocalConv: read x (C) + w (J), write y (C)   [dX: dy, w -> dx ; dW: x, dy -> dw]
-    "agg3_fwd_nhwc2": (2, 1), "agg3_dx_nhwc2": (2, 1), "agg3_dw_nhwc2": (2, 1),
-    "agg3_fwd_nhwc": (2, 1), "agg3_dx_nhwc": (2, 1), "agg3_dw_nhwc": (2, 1),
-    "agg3_fwd_nchw2": (2, 1), "agg3_bwd_nchw2_dx": (2, 1), "agg3_bwd_nchw2_dw": (2, 1), "agg3_bwd_nchw2_dxdw": (3, 2),
-    "agg_fwd_nchw_k3": (2, 1), "agg_bwd_nchw_dx": (2, 1), "agg_bwd_nchw_dw": (2, 1), "agg_bwd_nchw_dxdw": (3, 2),
-    "agg_fwd_generic": (2, 1), "agg_dx_generic": (2, 1), "agg_dw_generic": (2, 1),
-    # BatchNorm statistics of u; bn+SiLU+pool; recombination; their backward passes
-    "col_stats": (1, 0), "tail_pool": (2, 0), "tail_combine": (3, 0),
-    "tail_bwd_sums": (3, 0), "tail_bwd_dz_sums": (2, 0), "tail_bwd_apply": (4, 0),
-    # GroupNorm over the 9 taps
-    "gn9_stats": (0, 1), "gn9_apply": (0, 2), "gn9_bwd_sums": (0, 2), "gn9_bwd_apply": (0, 3),
-}
-
-
-def algorithmic_bytes(kernel, shapes, batch, esize):
-    """SURVEY.md section 8(d) / BASELINE.md section 3, summed over the step's launches of `kernel` (one per CoT layer)."""
-    if kernel not in _KERNEL_ELEMS:
-        return None
-    nc, nj = _KERNEL_ELEMS[kernel]
-    tot = 0
-    for (C, H, W, fold) in shapes:
-        tot += (nc * C + nj * (9 * C // 8)) * H * W * batch * esize
-    return tot
-
-
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -324,19 +284,20 @@ def main_ours(a):
     prof = _lib.prof_report()
     _lib.prof_enable(False)
     if prof and rank == 0:
-        top = max(prof.items(), key=lambda kv: kv[1][1])
-        kname, (cnt, tot_ms) = top
-        shapes = cot_layer_shapes(model, B, R)
-        bytes_step = algorithmic_bytes(kname, shapes, B, 2)       # bf16 activations under autocast
+        # dominant kernel = most device time among OUR kernels; algorithmic bytes are recorded by the library per launch
+        # (DESIGN.md section 4 formulas evaluated on the actual launch dimensions)
+        kname, (cnt, tot_ms, tot_bytes) = max(prof.items(), key=lambda kv: kv[1][1])
         peak, src = measured_peaks()
-        if bytes_step is not None:
-            ach = bytes_step * 2 / (tot_ms / 1e3) / 1e9           # 2 profiled steps
-            traffic = ncu_traffic(kname)
+        if tot_bytes > 0 and tot_ms > 0:
+            ach = tot_bytes / (tot_ms / 1e3) / 1e9
             roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "peak_source": src, "traffic": traffic, "launches_per_step": cnt // 2,
-                    "avg_launch_us": 1e3 * tot_ms / cnt,
+                    "peak_source": src, "traffic": ncu_traffic(kname), "launches_per_step": cnt // 2,
+                    "avg_launch_us": 1e3 * tot_ms / cnt, "algorithmic_bytes_per_launch": tot_bytes / cnt,
                     "kernel_share_of_step": (tot_ms / 2) / (ms / a.steps),
-                    "all_kernels_ms_per_step": {k: v[1] / 2 for k, v in sorted(prof.items())}}
+                    "our_kernels_share_of_step": sum(v[1] for v in prof.values()) / 2 / (ms / a.steps),
+                    "all_kernels": {k: {"ms_per_step": round(v[1] / 2, 4), "launches_per_step": v[0] // 2,
+                                        "GBps": round(v[2] / (v[1] / 1e3) / 1e9, 1) if v[1] > 0 else None}
+                                    for k, v in sorted(prof.items())}}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -354,7 +315,8 @@ def main_ours(a):
                        "global_batch": B * world, "parallelism": "dp%d" % world,
                        "l2": "per-step working set (activations, several GB) >> 126 MB L2; no explicit flush needed",
                        "cot_path": "libcotb200: LocalConv fwd/dX/dW, GroupNorm(9 taps) fwd/bwd, bn+SiLU+pool+radix-2 "
-                                   "recombination fwd/bwd; the block's convolutions and the trunk: PyTorch/cuDNN"},
+                                   "recombination fwd/bwd, fused BatchNorm(+ReLU,+residual) of the block and of the "
+                                   "enclosing bottleneck; convolutions: cuDNN (training) / tcgen05 (inference path)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -128,13 +128,13 @@ def prof_enable(on: bool):
 
 
 def prof_report():
-    """{kernel name: (launches, total_ms)} of the launches recorded since prof_enable(True)."""
+    """{kernel name: (launches, total_ms, total ALGORITHMIC bytes)} of the launches recorded since prof_enable(True)."""
     lib = load()
     n = lib.cotb200_prof_report(None, 0)
     buf = ctypes.create_string_buffer(n + 16)
     lib.cotb200_prof_report(buf, n + 16)
     out = {}
     for line in buf.value.decode().splitlines():
-        name, cnt, ms = line.rsplit(" ", 2)
-        out[name] = (int(cnt), float(ms))
+        name, cnt, ms, nbytes = line.rsplit(" ", 3)
+        out[name] = (int(cnt), float(ms), float(nbytes))
     return out

@@ -220,7 +220,7 @@ int nchw2_fwd(int N, int C, int H, int W, int wc, long long y_sn, const T* x, co
     const int pxv = nchw2_pxv<T>(W, H * W, x, w, y, nullptr, nullptr);
     if (!pxv || (long long)N * wc > 65535 || (y_sn * (long long)sizeof(T)) % (pxv * sizeof(T))) return 0;
     dim3 grid((H * (W / pxv) + 255) / 256, N * wc);
-    COTB200_PROF("agg3_fwd_nchw2");
+    COTB200_PROF_B("agg3_fwd_nchw2", ((double)N * H * W) * (2.0 * C + 9.0 * wc) * sizeof(T));
     if (pxv == 4) agg3_fwd_nchw2_kernel<T, 4><<<grid, 256, 0, st>>>(x, w, y, C, H, W, wc, C / wc, y_sn);
     else agg3_fwd_nchw2_kernel<T, 2><<<grid, 256, 0, st>>>(x, w, y, C, H, W, wc, C / wc, y_sn);
     *rc = check_launch("agg3_fwd_nchw2");
@@ -236,7 +236,7 @@ int nchw2_bwd(int N, int C, int H, int W, int wc, long long dy_sn, const T* dy, 
     if (!pxv || (long long)N * wc > 65535 || (dy_sn * (long long)sizeof(T)) % (pxv * sizeof(T))) return 0;
     dim3 grid((H * (W / pxv) + 255) / 256, N * wc);
     const int rep = C / wc;
-    COTB200_PROF(dx && dw ? "agg3_bwd_nchw2_dxdw" : (dx ? "agg3_bwd_nchw2_dx" : "agg3_bwd_nchw2_dw"));
+    COTB200_PROF_B(dx && dw ? "agg3_bwd_nchw2_dxdw" : (dx ? "agg3_bwd_nchw2_dx" : "agg3_bwd_nchw2_dw"), ((double)N * H * W) * ((dx && dw ? 3.0 : 2.0) * C + (dx && dw ? 18.0 : 9.0) * wc) * sizeof(T));
 #define NCHW2_LAUNCH(P)                                                                                              \
   if (dx && dw) agg3_bwd_nchw2_kernel<T, P, true, true><<<grid, 256, 0, st>>>(dy, x, w, dx, dw, C, H, W, wc, rep, dy_sn); \
   else if (dx) agg3_bwd_nchw2_kernel<T, P, true, false><<<grid, 256, 0, st>>>(dy, x, w, dx, dw, C, H, W, wc, rep, dy_sn); \

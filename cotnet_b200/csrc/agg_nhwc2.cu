@@ -267,7 +267,7 @@ int nhwc2_fwd(const Nhwc2Args& a, const T* x, const T* w, T* y, cudaStream_t st,
     if (grid.y > 65535) {   // fold rows into x when the batch is huge
       return 0;
     }
-    COTB200_PROF("agg3_fwd_nhwc2");
+    COTB200_PROF_B("agg3_fwd_nhwc2", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T));
     if (px == 2) {
       if (tap) agg3_nhwc2_kernel<T, VEC, 2, true, 0><<<grid, 256, 0, st>>>(x, w, y, g);
       else agg3_nhwc2_kernel<T, VEC, 2, false, 0><<<grid, 256, 0, st>>>(x, w, y, g);
@@ -290,7 +290,7 @@ int nhwc2_dx(const Nhwc2Args& a, const T* dy, const T* w, T* dx, cudaStream_t st
     const int px = (a.W % 2 == 0) ? 2 : 1;
     dim3 grid((((a.W + px - 1) / px) * CQ + 255) / 256, a.N * a.H);
     if (grid.y > 65535) return 0;
-    COTB200_PROF("agg3_dx_nhwc2");
+    COTB200_PROF_B("agg3_dx_nhwc2", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T));
     if (px == 2) agg3_nhwc2_kernel<T, VEC, 2, true, 1><<<grid, 256, 0, st>>>(dy, w, dx, g);
     else agg3_nhwc2_kernel<T, VEC, 1, true, 1><<<grid, 256, 0, st>>>(dy, w, dx, g);
     *rc = check_launch("agg3_dx_nhwc2");
@@ -313,7 +313,7 @@ int nhwc2_dw(const Nhwc2Args& a, const T* dy, const T* x, T* dw, cudaStream_t st
     const int witems = ((a.W + pxw - 1) / pxw) * (GQ / gqw);       // warps per image row
     dim3 grid((witems + 7) / 8, a.N * a.H);
     if (grid.y > 65535) return 0;
-    COTB200_PROF("agg3_dw_nhwc2");
+    COTB200_PROF_B("agg3_dw_nhwc2", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T));
     if (gqw == 1) agg3_dw_nhwc2_kernel<T, VEC, 1><<<grid, 256, 0, st>>>(dy, x, dw, g, GQ);
     else if (gqw == 2) agg3_dw_nhwc2_kernel<T, VEC, 2><<<grid, 256, 0, st>>>(dy, x, dw, g, GQ);
     else agg3_dw_nhwc2_kernel<T, VEC, 4><<<grid, 256, 0, st>>>(dy, x, dw, g, GQ);

@@ -54,6 +54,11 @@ struct AggTmaP {
   int total_tiles;
   long long y_sn;         // output batch stride (elements)
   int y_sp;               // output pixel stride (elements)
+  int mode;               // 0 forward, 1 dX (weights fetched WITH halo), 2 dW (second operand = dY band, output = dW)
+  int whalo;              // 1: weight tile is (TH+2) x (W+2) rows
+  int wrows;              // rows of the weight tile = (TH + 2*whalo) * (W + 2*whalo)
+  int b_slab_bytes;       // dW: bytes of one 128-byte-wide dY slab [TH][W] rounded to 1024
+  int GQ;                 // dW: weight packets per pixel
 };
 
 __device__ __forceinline__ uint32_t at_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,14 +91,51 @@ __device__ __forceinline__ void at_tma_4d(uint32_t dst, const CUtensorMap* map, 
       : "memory");
 }
 
+__device__ __forceinline__ void at_tma_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+// explicit 16-byte shared-memory load from a 32-bit shared address (a generic LD would pay address translation)
 template <typename T, int VEC>
-__device__ __forceinline__ Pack<T, VEC> lds_pack(const uint8_t* p) {
+__device__ __forceinline__ Pack<T, VEC> lds_pack(uint32_t saddr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(saddr));
   Pack<T, VEC> r;
-  *reinterpret_cast<uint4*>(&r) = *reinterpret_cast<const uint4*>(p);
+  *reinterpret_cast<uint4*>(&r) = u;
   return r;
 }
 
 template <typename T>
+__device__ __forceinline__ void at_producer(const CUtensorMap& mapX, const CUtensorMap& mapW, const AggTmaP& p, uint8_t* smem,
+                                            uint64_t* s_full, uint64_t* s_empty, int lane) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        at_mbar_wait(at_smem_u32(&s_empty[s]), ph ^ 1);
+        const int n = tile / p.bands, h0 = (tile - n * p.bands) * p.TH;
+        const uint32_t full = at_smem_u32(&s_full[s]);
+        const uint32_t base = at_smem_u32(smem + (size_t)s * p.stage_bytes);
+        at_mbar_expect_tx(full, (uint32_t)(p.x_bytes_tx + p.w_bytes_tx));
+        for (int sl = 0; sl < p.slabs; ++sl)      // input band + halo; OOB (w = -1 / W, h = -1 / H) zero-filled
+          at_tma_4d(base + sl * p.slab_bytes, &mapX, full, sl * (128 / (int)sizeof(T)), -1, h0 - 1, n);
+        const uint32_t wbase = base + p.slabs * p.slab_bytes;
+        if (p.mode == 2) {        // dW: second operand = dY band (no halo), one box per 128-byte channel slab
+          for (int sl = 0; sl < p.slabs; ++sl)
+            at_tma_4d(wbase + sl * p.b_slab_bytes, &mapW, full, sl * (128 / (int)sizeof(T)), 0, h0, n);
+        } else {                  // weights: [rows][J]; dX needs them at the neighbour pixels -> haloed band
+          // one 5-D box {jbox, jboxes, W(+2), TH(+2), 1}: the J = jboxes*jbox weights of a pixel land contiguously
+          at_tma_5d(wbase, &mapW, full, 0, 0, -p.whalo, h0 - p.whalo, n);
+        }
+      }
+    }
+}
+
+template <typename T, int MODE>
 __global__ void __launch_bounds__(1024, 1)
 agg3_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, T* __restrict__ y,
                     const AggTmaP p) {
@@ -112,29 +154,105 @@ agg3_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
   __syncthreads();
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        at_mbar_wait(at_smem_u32(&s_empty[s]), ph ^ 1);
-        const int n = tile / p.bands, h0 = (tile - n * p.bands) * p.TH;
-        const uint32_t full = at_smem_u32(&s_full[s]);
-        const uint32_t base = at_smem_u32(smem + (size_t)s * p.stage_bytes);
-        at_mbar_expect_tx(full, (uint32_t)(p.x_bytes_tx + p.w_bytes_tx));
-        for (int sl = 0; sl < p.slabs; ++sl)      // input band + halo; OOB (w = -1 / W, h = -1 / H) zero-filled
-          at_tma_4d(base + sl * p.slab_bytes, &mapX, full, sl * (128 / (int)sizeof(T)), -1, h0 - 1, n);
-        const uint32_t wbase = base + p.slabs * p.slab_bytes;
-        for (int jb = 0; jb < p.jboxes; ++jb)
-          at_tma_4d(wbase + jb * (p.TH * p.W * p.jbox * (int)sizeof(T)), &mapW, full, jb * p.jbox, 0, h0, n);
-      }
-    }
+    at_producer<T>(mapX, mapW, p, smem, s_full, s_empty, lane);
   } else {
     // ===================== consumers: thread = (pixel of the band, 16-byte channel packet) =====================
+    // The tile geometry is the same for every tile, so all index arithmetic (div/mod by runtime sizes) is done ONCE per
+    // thread here; inside the tile loop an item costs 9 x (2 LDS.128 + 8 FMA) plus a handful of address adds.
     const int ct = threadIdx.x - 32, nct = ncw * 32;
     const int CQ = p.C / VEC;
     const int items = p.TH * p.W * CQ;
+    const int Wp = p.W + 2;
+    constexpr int MAXI = 2;                 // items per thread (host guarantees items <= MAXI * consumers)
+    int i_hl[MAXI], i_rc[MAXI], i_xb[MAXI], i_ch[MAXI], i_wb[MAXI], i_ob[MAXI];
+#pragma unroll
+    for (int k = 0; k < MAXI; ++k) {
+      const int item = ct + k * nct;
+      i_hl[k] = -1;
+      if (item < items) {
+        const int q = item % CQ, px = item / CQ;
+        const int hl = px / p.W, wl = px - hl * p.W;
+        const int c0 = q * VEC;
+        const int g0 = (c0 / p.Cf) * p.wcf + (c0 % p.Cf) % p.wcf;
+        const int cb = c0 * (int)sizeof(T);
+        const int e0 = (g0 / p.gc) * 9 * p.gc + g0 % p.gc;
+        i_hl[k] = hl;
+        i_rc[k] = (hl + 1) * Wp + wl + 1;                     // centre row of the haloed band
+        i_xb[k] = (cb >> 7) * p.slab_bytes;
+        i_ch[k] = (cb >> 4) & 7;
+        i_wb[k] = (MODE == 0 ? (px * p.J + e0) : e0) * (int)sizeof(T);
+        i_ob[k] = (hl * p.W + wl) * p.y_sp + c0;
+      }
+    }
+    const uint32_t smem_base = at_smem_u32(smem);
+    const int wtap = p.gc * (int)sizeof(T);                    // bytes between the packets of consecutive taps
+    const int wrow = p.J * (int)sizeof(T);                     // bytes of one pixel's weight row
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      at_mbar_wait(at_smem_u32(&s_full[s]), ph);
+      const int n = tile / p.bands, h0 = (tile - n * p.bands) * p.TH;
+      const uint32_t xs = smem_base + (uint32_t)(s * p.stage_bytes);
+      const uint32_t ws = xs + (uint32_t)(p.slabs * p.slab_bytes);
+      T* yt = y + n * p.y_sn + (long long)h0 * p.W * p.y_sp;
+#pragma unroll
+      for (int k = 0; k < MAXI; ++k) {
+        if (i_hl[k] < 0 || h0 + i_hl[k] >= p.H) continue;
+        const uint32_t xb = xs + (uint32_t)i_xb[k];
+        const uint32_t wb = ws + (uint32_t)i_wb[k];
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          // forward: neighbour (h+dh, w+dw) with the centre pixel's weights;  dX: neighbour (h-dh, w-dw) AND its weights
+          const int dr = (t / 3 - 1) * Wp + (t % 3 - 1);
+          const int r = MODE == 0 ? i_rc[k] + dr : i_rc[k] - dr;
+          const Pack<T, VEC> wv = lds_pack<T, VEC>(wb + t * wtap + (MODE == 0 ? 0 : r * wrow));
+          const Pack<T, VEC> xv = lds_pack<T, VEC>(xb + r * 128 + ((i_ch[k] ^ (r & 7)) << 4));
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] = MixT<T>::fma(wv.v[i], xv.v[i], acc[i]);
+        }
+        Pack<T, VEC> o;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.v[i] = Elem<T>::from(acc[i]);
+        st_pack<T, VEC>(yt + i_ob[k], o);
+      }
+      __syncwarp();
+      if (lane == 0) at_mbar_arrive(at_smem_u32(&s_empty[s]));   // this warp is done reading the stage
+    }
+  }
+}
+
+// dW[p, (g0+i), t] = sum_{8 sharers j} x[p + off_t][cb_j + i] * dY[p][cb_j + i]          (TAP layout output)
+// Warp lane = gvl + GQW*j + 8*GQW*slot (slot = pixel inside the warp); butterfly transpose-reduce over the j lanes.
+template <typename T, int GQW>
+__global__ void __launch_bounds__(512, 1)
+agg3_dw_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapG, T* __restrict__ dw,
+                   const AggTmaP p) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  constexpr int PXW = 32 / (8 * GQW);
+  extern __shared__ __align__(1024) uint8_t at_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t s_full[AT_MAX_STAGES], s_empty[AT_MAX_STAGES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncw = (blockDim.x >> 5) - 1;
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapG) : "memory");
+    for (int s = 0; s < p.stages; ++s) { at_mbar_init(at_smem_u32(&s_full[s]), 1); at_mbar_init(at_smem_u32(&s_empty[s]), ncw); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) {
+    at_producer<T>(mapX, mapG, p, smem, s_full, s_empty, lane);
+  } else {
+    const int cwarp = warp - 1;
+    const int gvl = lane % GQW, j = (lane / GQW) % 8, slot = lane / (8 * GQW);
+    const int gvgroups = p.GQ / GQW;
+    const int pxgroups = (p.TH * p.W + PXW - 1) / PXW;
+    const int witems = pxgroups * gvgroups;
     const int Wp = p.W + 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -142,38 +260,62 @@ agg3_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
       const uint32_t ph = (it / p.stages) & 1;
       at_mbar_wait(at_smem_u32(&s_full[s]), ph);
       const int n = tile / p.bands, h0 = (tile - n * p.bands) * p.TH;
-      const uint8_t* xs = smem + (size_t)s * p.stage_bytes;
-      const uint8_t* ws = xs + (size_t)p.slabs * p.slab_bytes;
-      for (int item = ct; item < items; item += nct) {
-        const int q = item % CQ, px = item / CQ;
+      const uint32_t xs = at_smem_u32(smem) + (uint32_t)(s * p.stage_bytes);
+      const uint32_t gs = xs + (uint32_t)(p.slabs * p.slab_bytes);
+      for (int wi = cwarp; wi < witems; wi += ncw) {
+        const int gvg = wi % gvgroups, pg = wi / gvgroups;
+        const int px = pg * PXW + slot;
         const int hl = px / p.W, wl = px - hl * p.W;
-        if (h0 + hl >= p.H) continue;
-        const int c0 = q * VEC;
-        const int g0 = (c0 / p.Cf) * p.wcf + (c0 % p.Cf) % p.wcf;
-        const int cb = c0 * (int)sizeof(T);                 // byte offset of the packet inside the pixel
+        const bool active = px < p.TH * p.W && h0 + hl < p.H;
+        const int g0 = (gvg * GQW + gvl) * VEC;
+        const int cb = ((g0 / p.wcf) * p.Cf + g0 % p.wcf + j * p.wcf) * (int)sizeof(T);      // byte offset of this lane's packet
         const int slab = cb >> 7, chunk = (cb >> 4) & 7;
-        // weights: [jb][TH*W][jbox] boxes; packet of tap t at element ((g0/gc)*9 + t)*gc + g0%gc of the pixel's J row
-        const int e0 = (g0 / p.gc) * 9 * p.gc + g0 % p.gc;
-        float acc[VEC];
+        float part[9][VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const int e = e0 + t * p.gc;
-          const int jb = e / p.jbox, ej = e - jb * p.jbox;
-          const Pack<T, VEC> wv = lds_pack<T, VEC>(ws + ((size_t)(jb * p.TH * p.W + px) * p.jbox + ej) * sizeof(T));
-          const int r = (hl + t / 3) * Wp + (wl + t % 3);   // row of the haloed band: (hl + dh + 1, wl + dw + 1)
-          const Pack<T, VEC> xv = lds_pack<T, VEC>(xs + (size_t)slab * p.slab_bytes + r * 128 + ((chunk ^ (r & 7)) << 4));
+          for (int i = 0; i < VEC; ++i) part[t][i] = 0.f;
+        if (active) {
+          const Pack<T, VEC> gv = lds_pack<T, VEC>(gs + (uint32_t)(slab * p.b_slab_bytes + px * 128 + ((chunk ^ (px & 7)) << 4)));
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) acc[i] = MixT<T>::fma(wv.v[i], xv.v[i], acc[i]);
+          for (int t = 0; t < 9; ++t) {
+            const int r = (hl + t / 3) * Wp + (wl + t % 3);
+            const Pack<T, VEC> xv = lds_pack<T, VEC>(xs + (uint32_t)(slab * p.slab_bytes + r * 128 + ((chunk ^ (r & 7)) << 4)));
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) part[t][i] = MixT<T>::fma(xv.v[i], gv.v[i], 0.f);
+          }
         }
-        Pack<T, VEC> o;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) o.v[i] = Elem<T>::from(acc[i]);
-        st_pack<T, VEC>(y + n * p.y_sn + (long long)((h0 + hl) * p.W + wl) * p.y_sp + c0, o);
+        for (int off = 4; off >= 1; off >>= 1) {
+          const bool upper = (j & off) != 0;
+#pragma unroll
+          for (int t = 0; t < off; ++t)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+              const float send = upper ? part[t][i] : part[t + off][i];
+              const float keep = upper ? part[t + off][i] : part[t][i];
+              part[t][i] = keep + __shfl_xor_sync(0xffffffffu, send, off * GQW);
+            }
+        }
+#pragma unroll
+        for (int off = 4; off >= 1; off >>= 1)
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) part[8][i] += __shfl_xor_sync(0xffffffffu, part[8][i], off * GQW);
+        if (active) {
+          T* wr = dw + n * p.y_sn + (long long)((h0 + hl) * p.W + wl) * p.y_sp + (g0 / p.gc) * 9 * p.gc + g0 % p.gc;
+          Pack<T, VEC> o;
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) o.v[i] = Elem<T>::from(part[0][i]);
+          st_pack<T, VEC>(wr + j * p.gc, o);                       // lane j owns tap j
+          if (j == 0) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o.v[i] = Elem<T>::from(part[8][i]);
+            st_pack<T, VEC>(wr + 8 * p.gc, o);
+          }
+        }
       }
       __syncwarp();
-      if (lane == 0) at_mbar_arrive(at_smem_u32(&s_empty[s]));   // this warp is done reading the stage
+      if (lane == 0) at_mbar_arrive(at_smem_u32(&s_empty[s]));
     }
   }
 }
@@ -213,14 +355,30 @@ static bool at_make_map(CUtensorMap* m, const void* base, int N, int H, int W, i
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// weights [N,H,W,J] as 5-D {jbox, jboxes, W, H, N}; box {jbox, jboxes, bw, bh, 1} -> smem [bh][bw][J]
+template <typename T>
+static bool at_make_map_w(CUtensorMap* m, const void* base, int N, int H, int W, int jbox, int jboxes, long long sp, long long sn,
+                          int bw, int bh) {
+  AtEncodeFn enc = at_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)jbox, (cuuint64_t)jboxes, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)jbox * sizeof(T), (cuuint64_t)sp * sizeof(T), (cuuint64_t)sp * sizeof(T) * W,
+                           (cuuint64_t)sn * sizeof(T)};
+  cuuint32_t box[5] = {(cuuint32_t)jbox, (cuuint32_t)jboxes, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  return enc(m, at_dtype<T>(), 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct Nhwc2Args {
   int N, C, H, W, wc, fold, layout, gc, dtype;
   long long x_sn, x_sp, w_sn, w_sp, y_sn, y_sp;
 };
 
+// mode 0: a = x, b = w, out = y      mode 1: a = dy, b = w, out = dx      mode 2: a = x, b = dy, out = dw
 // returns 1 if handled (rc in *rc), 0 if the caller should use the register-resident kernels
 template <typename T>
-int agg_tma_fwd(const Nhwc2Args& a, const T* x, const T* w, T* y, cudaStream_t st, int* rc) {
+static int agg_tma_launch(int mode, const Nhwc2Args& a, const T* A, const T* Bp, T* out, cudaStream_t st, int* rc) {
   if constexpr (std::is_same<T, double>::value) { return 0; } else {
     constexpr int VEC = 16 / (int)sizeof(T);
     static int disabled = -1;
@@ -229,66 +387,121 @@ int agg_tma_fwd(const Nhwc2Args& a, const T* x, const T* w, T* y, cudaStream_t s
     if (a.layout != COTB200_NHWC_TAP) return 0;
     const int Cf = a.C / a.fold, wcf = a.wc / a.fold;
     if ((a.C * (int)sizeof(T)) % 128 || wcf % VEC || a.gc < VEC || a.gc % VEC || a.wc % a.gc) return 0;
-    if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) return 0;
-    if ((a.x_sp * sizeof(T)) % 16 || (a.w_sp * sizeof(T)) % 16 || (a.y_sp * sizeof(T)) % 16 || (a.x_sn * sizeof(T)) % 16 ||
-        (a.w_sn * sizeof(T)) % 16 || (a.y_sn * sizeof(T)) % 16) return 0;
-    if (a.W + 2 > 256 || a.y_sp > 2147483647LL) return 0;
+    if (((uintptr_t)A | (uintptr_t)Bp | (uintptr_t)out) & 15) return 0;
+    const long long strides[6] = {a.x_sn, a.x_sp, a.w_sn, a.w_sp, a.y_sn, a.y_sp};
+    for (long long sv : strides) if ((sv * (long long)sizeof(T)) % 16) return 0;
+    if (a.W + 2 > 256) return 0;
     AggTmaP p{};
     p.N = a.N; p.C = a.C; p.H = a.H; p.W = a.W; p.wc = a.wc; p.Cf = Cf; p.wcf = wcf; p.gc = a.gc; p.J = 9 * a.wc;
+    p.mode = mode; p.whalo = mode == 1 ? 1 : 0;
     p.slabs = a.C * (int)sizeof(T) / 128;
     p.jboxes = (p.J + 255) / 256;
     while (p.J % p.jboxes) ++p.jboxes;
     p.jbox = p.J / p.jboxes;
     if ((p.jbox * (int)sizeof(T)) % 16) return 0;
-    p.y_sn = a.y_sn; p.y_sp = (int)a.y_sp;
-    // choose TH: about 100 KB per stage at most, at least ~512 work items, bands tile H as evenly as possible
+    p.GQ = a.wc / VEC;
+    int gqw = 1;
+    if (mode == 2) {
+      if (a.C / a.wc != 8) return 0;                      // butterfly over the 8 sharers (share_planes = 8)
+      gqw = p.GQ >= 4 ? 4 : p.GQ;
+      if (p.GQ % gqw || (gqw != 1 && gqw != 2 && gqw != 4)) return 0;
+      if (a.fold > 1 && wcf % (gqw * VEC)) return 0;
+    }
+    // output strides: y (fwd), dx (dX: same layout as x), dw (dW: same layout as w)
+    const long long o_sn = mode == 0 ? a.y_sn : (mode == 1 ? a.x_sn : a.w_sn);
+    const long long o_sp = mode == 0 ? a.y_sp : (mode == 1 ? a.x_sp : a.w_sp);
+    if (o_sp > 2147483647LL) return 0;
+    p.y_sn = o_sn; p.y_sp = (int)o_sp;
+    // tile height: stage <= 72 KB, stop growing once a tile has ~900 work items
     const int CQ = a.C / VEC;
     int best_th = 0;
     for (int th = 1; th <= a.H && th <= 254; ++th) {
       const long long xb = (long long)p.slabs * ((((long long)(th + 2) * (a.W + 2) * 128) + 1023) / 1024 * 1024);
-      const long long wb = (((long long)th * a.W * p.J * sizeof(T)) + 127) / 128 * 128;
-      if (xb + wb > 72 * 1024) break;
+      long long bb;
+      if (mode == 2) bb = (long long)p.slabs * ((((long long)th * a.W * 128) + 1023) / 1024 * 1024);
+      else bb = ((long long)(th + 2 * p.whalo) * (a.W + 2 * p.whalo) * p.J * sizeof(T) + 1023) / 1024 * 1024;
+      if (xb + bb > 72 * 1024) break;
+      if (mode != 2 && (long long)th * a.W * CQ > 2 * 896) break;      // at most 2 work items per consumer thread
       best_th = th;
       if ((long long)th * a.W * CQ >= 896) break;
     }
     if (!best_th) return 0;
     p.TH = best_th;
+    p.wrows = (p.TH + 2 * p.whalo) * (a.W + 2 * p.whalo);
     p.slab_bytes = (int)((((long long)(p.TH + 2) * (a.W + 2) * 128) + 1023) / 1024 * 1024);
     p.x_bytes_tx = p.slabs * (p.TH + 2) * (a.W + 2) * 128;
-    p.w_bytes_tx = p.TH * a.W * p.J * (int)sizeof(T);
-    p.w_stage_bytes = (p.w_bytes_tx + 1023) / 1024 * 1024;
+    if (mode == 2) {
+      p.b_slab_bytes = (int)((((long long)p.TH * a.W * 128) + 1023) / 1024 * 1024);
+      p.w_bytes_tx = p.slabs * p.TH * a.W * 128;
+      p.w_stage_bytes = p.slabs * p.b_slab_bytes;
+    } else {
+      p.w_bytes_tx = p.wrows * p.J * (int)sizeof(T);
+      p.w_stage_bytes = (p.w_bytes_tx + 1023) / 1024 * 1024;
+    }
     p.stage_bytes = p.slabs * p.slab_bytes + p.w_stage_bytes;
     p.stages = (int)((200 * 1024) / p.stage_bytes);
     if (p.stages > AT_MAX_STAGES) p.stages = AT_MAX_STAGES;
     if (p.stages < 2) return 0;
-    if (p.jboxes > 1 && ((long long)p.TH * a.W * p.jbox * sizeof(T)) % 128) return 0;   // TMA destinations are 128-byte aligned
     p.bands = (a.H + p.TH - 1) / p.TH;
     p.total_tiles = a.N * p.bands;
-    CUtensorMap mx, mw;
-    if (!at_make_map<T>(&mx, x, a.N, a.H, a.W, a.C, a.x_sp, a.x_sn, 128 / (int)sizeof(T), a.W + 2, p.TH + 2, true)) return 0;
-    if (!at_make_map<T>(&mw, w, a.N, a.H, a.W, p.J, a.w_sp, a.w_sn, p.jbox, a.W, p.TH, false)) return 0;
-    const int items = p.TH * a.W * CQ;
-    int cw = (items + 31) / 32;                          // consumer warps
-    if (cw > 28) cw = 28;
-    if (cw < 4) cw = 4;
+    CUtensorMap ma, mb;
+    const long long a_sp = mode == 1 ? a.y_sp : a.x_sp, a_sn = mode == 1 ? a.y_sn : a.x_sn;
+    if (!at_make_map<T>(&ma, A, a.N, a.H, a.W, a.C, a_sp, a_sn, 128 / (int)sizeof(T), a.W + 2, p.TH + 2, true)) return 0;
+    if (mode == 2) {
+      if (!at_make_map<T>(&mb, Bp, a.N, a.H, a.W, a.C, a.y_sp, a.y_sn, 128 / (int)sizeof(T), a.W, p.TH, true)) return 0;
+    } else {
+      if (!at_make_map_w<T>(&mb, Bp, a.N, a.H, a.W, p.jbox, p.jboxes, a.w_sp, a.w_sn, a.W + 2 * p.whalo, p.TH + 2 * p.whalo)) return 0;
+    }
+    int work_warps;
+    if (mode == 2) work_warps = ((p.TH * a.W + (32 / (8 * gqw)) - 1) / (32 / (8 * gqw))) * (p.GQ / gqw);
+    else work_warps = (p.TH * a.W * CQ + 31) / 32;
+    int cw = work_warps > 28 ? 28 : (work_warps < 4 ? 4 : work_warps);
+    if (mode != 2 && (long long)p.TH * a.W * CQ > 2LL * cw * 32) return 0;
+    if (mode == 2 && cw > 15) cw = 15;                 // the butterfly holds 72 partial sums per thread: 512 threads x <=128 regs
     const int threads = (cw + 1) * 32;
     const int smem = p.stages * p.stage_bytes + 1024;
-    static int configured = 0;
-    if (configured < smem) {
-      cudaError_t e = cudaFuncSetAttribute(agg3_fwd_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(agg3_fwd_tma): %s", cudaGetErrorString(e)); *rc = (int)e; return 1; }
-      configured = 220 * 1024;
-    }
     int grid = num_sms();
     if (grid > p.total_tiles) grid = p.total_tiles;
-    COTB200_PROF("agg3_fwd_tma");
-    agg3_fwd_tma_kernel<T><<<grid, threads, smem, st>>>(mx, mw, y, p);
-    *rc = check_launch("agg3_fwd_tma");
+    cudaError_t e = cudaSuccess;
+    static bool cfg[8] = {false, false, false, false, false, false, false, false};
+#define AT_CFG(idx, fn) if (!cfg[idx]) { e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); cfg[idx] = (e == cudaSuccess); }
+    if (mode == 0) {
+      AT_CFG(0, (agg3_fwd_tma_kernel<T, 0>));
+      if (e == cudaSuccess) { COTB200_PROF_B("agg3_fwd_tma", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T)); agg3_fwd_tma_kernel<T, 0><<<grid, threads, smem, st>>>(ma, mb, out, p); }
+    } else if (mode == 1) {
+      AT_CFG(1, (agg3_fwd_tma_kernel<T, 1>));
+      if (e == cudaSuccess) { COTB200_PROF_B("agg3_dx_tma", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T)); agg3_fwd_tma_kernel<T, 1><<<grid, threads, smem, st>>>(ma, mb, out, p); }
+    } else if (gqw == 1) {
+      AT_CFG(2, (agg3_dw_tma_kernel<T, 1>));
+      if (e == cudaSuccess) { COTB200_PROF_B("agg3_dw_tma", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T)); agg3_dw_tma_kernel<T, 1><<<grid, threads, smem, st>>>(ma, mb, out, p); }
+    } else if (gqw == 2) {
+      AT_CFG(3, (agg3_dw_tma_kernel<T, 2>));
+      if (e == cudaSuccess) { COTB200_PROF_B("agg3_dw_tma", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T)); agg3_dw_tma_kernel<T, 2><<<grid, threads, smem, st>>>(ma, mb, out, p); }
+    } else {
+      AT_CFG(4, (agg3_dw_tma_kernel<T, 4>));
+      if (e == cudaSuccess) { COTB200_PROF_B("agg3_dw_tma", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T)); agg3_dw_tma_kernel<T, 4><<<grid, threads, smem, st>>>(ma, mb, out, p); }
+    }
+#undef AT_CFG
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(agg tma): %s", cudaGetErrorString(e)); *rc = (int)e; return 1; }
+    *rc = check_launch("agg3_tma");
     return 1;
   }
 }
 
-#define COTB200_INST3(T) template int agg_tma_fwd<T>(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);
+template <typename T> int agg_tma_fwd(const Nhwc2Args& a, const T* x, const T* w, T* y, cudaStream_t st, int* rc) {
+  return agg_tma_launch<T>(0, a, x, w, y, st, rc);
+}
+template <typename T> int agg_tma_dx(const Nhwc2Args& a, const T* dy, const T* w, T* dx, cudaStream_t st, int* rc) {
+  return agg_tma_launch<T>(1, a, dy, w, dx, st, rc);
+}
+template <typename T> int agg_tma_dw(const Nhwc2Args& a, const T* dy, const T* x, T* dw, cudaStream_t st, int* rc) {
+  return agg_tma_launch<T>(2, a, x, dy, dw, st, rc);
+}
+
+#define COTB200_INST3(T)                                                                              \
+  template int agg_tma_fwd<T>(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);          \
+  template int agg_tma_dx<T>(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);           \
+  template int agg_tma_dw<T>(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);
 COTB200_INST3(float) COTB200_INST3(double) COTB200_INST3(__nv_bfloat16) COTB200_INST3(__half)
 
 }  // namespace cotb200

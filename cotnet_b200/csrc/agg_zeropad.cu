@@ -479,6 +479,8 @@ struct Nhwc2Args {
 };
 template <typename T> int nhwc2_fwd(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);
 template <typename T> int agg_tma_fwd(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);   // agg_tma.cu
+template <typename T> int agg_tma_dx(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);
+template <typename T> int agg_tma_dw(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);
 template <typename T> int nhwc2_dx(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);
 template <typename T> int nhwc2_dw(const Nhwc2Args&, const T*, const T*, T*, cudaStream_t, int*);
 // second-generation NCHW kernels (agg_nchw2.cu)
@@ -582,7 +584,7 @@ static int fwd_impl(const Geo& g, const T* x, const T* w, T* y, cudaStream_t st)
     if constexpr (!std::is_same<T, double>::value) {
       const int total = g.N * g.wc * g.H * g.W;
       const int grid = grid_for(total, 256);
-      COTB200_PROF(g.KH == 3 ? "agg_fwd_nchw_k3" : "agg_fwd_nchw_k5");
+      COTB200_PROF_B(g.KH == 3 ? "agg_fwd_nchw_k3" : "agg_fwd_nchw_k5", ((double)g.N * g.C * g.H * g.W + (double)g.N * g.heads * g.wc * g.K2 * g.HO * g.WO + (double)g.N * g.heads * g.C * g.HO * g.WO) * sizeof(T));
       if (g.KH == 3) agg_fwd_nchw_fast<T, 3><<<grid, 256, 0, st>>>(x, w, y, g.N, g.C, g.H, g.W, g.wc, g.rep, g.y_sn, total);
       else agg_fwd_nchw_fast<T, 5><<<grid, 256, 0, st>>>(x, w, y, g.N, g.C, g.H, g.W, g.wc, g.rep, g.y_sn, total);
       return check_launch("agg_fwd_nchw_fast");
@@ -595,7 +597,7 @@ static int fwd_impl(const Geo& g, const T* x, const T* w, T* y, cudaStream_t st)
         const int total = g.N * g.H * g.W * (g.C / vec);
         const int grid = grid_for(total, 256);
         const bool tap = g.layout == COTB200_NHWC_TAP;
-        COTB200_PROF("agg3_fwd_nhwc");
+        COTB200_PROF_B("agg3_fwd_nhwc", ((double)g.N * g.C * g.H * g.W + (double)g.N * g.heads * g.wc * g.K2 * g.HO * g.WO + (double)g.N * g.heads * g.C * g.HO * g.WO) * sizeof(T));
 #define COTB200_LAUNCH_FWD(V)                                                                                     \
   if (vec == V) {                                                                                                 \
     if (tap) agg3_fwd_nhwc_fast<T, V, true><<<grid, 256, 0, st>>>(x, w, y, g.N, g.C, g.H, g.W, g.Cf, g.wcf, g.x_sn, \
@@ -611,7 +613,7 @@ static int fwd_impl(const Geo& g, const T* x, const T* w, T* y, cudaStream_t st)
     }
   }
   const long long total = (long long)g.N * g.heads * g.C * g.HO * g.WO;
-  COTB200_PROF("agg_fwd_generic");
+  COTB200_PROF_B("agg_fwd_generic", ((double)g.N * g.C * g.H * g.W + (double)g.N * g.heads * g.wc * g.K2 * g.HO * g.WO + (double)g.N * g.heads * g.C * g.HO * g.WO) * sizeof(T));
   agg_fwd_generic<T><<<grid_for(total, 256, 16), 256, 0, st>>>(x, w, y, g, total);
   return check_launch("agg_fwd_generic");
 }
@@ -627,7 +629,7 @@ static int bwd_impl(const Geo& g, const T* dy, const T* x, const T* w, T* dx, T*
     if constexpr (!std::is_same<T, double>::value) {
       const int total = g.N * g.wc * g.H * g.W;
       const int grid = grid_for(total, 256);
-      COTB200_PROF(dx && dw ? "agg_bwd_nchw_dxdw" : (dx ? "agg_bwd_nchw_dx" : "agg_bwd_nchw_dw"));
+      COTB200_PROF_B(dx && dw ? "agg_bwd_nchw_dxdw" : (dx ? "agg_bwd_nchw_dx" : "agg_bwd_nchw_dw"), (dx && dw ? 1.0 : 0.0) * ((double)g.N * g.C * g.H * g.W + (double)g.N * g.wc * g.K2 * g.HO * g.WO) * sizeof(T) + ((double)g.N * g.C * g.H * g.W + (double)g.N * g.heads * g.wc * g.K2 * g.HO * g.WO + (double)g.N * g.heads * g.C * g.HO * g.WO) * sizeof(T));
 #define COTB200_LAUNCH_BWD(K, DX, DW, ACC)                                                                          \
   agg_bwd_nchw_fast<T, K, DX, DW, ACC><<<grid, 256, 0, st>>>(dy, x, w, dx, dw, g.N, g.C, g.H, g.W, g.wc, g.rep,      \
                                                             g.y_sn, total)
@@ -647,6 +649,8 @@ static int bwd_impl(const Geo& g, const T* dy, const T* x, const T* w, T* dx, T*
   if (g.layout == COTB200_NHWC_TAP && !acc_dx && is_same3(g, 3)) {
     // second-generation kernels; whatever they do not take falls through to the first-generation ones below
     int rc2 = 0;
+    if (dx && agg_tma_dx<T>(nhwc2_args(g), dy, w, dx, st, &rc2)) { if (rc2) return rc2; dx = nullptr; }
+    if (dw && agg_tma_dw<T>(nhwc2_args(g), dy, x, dw, st, &rc2)) { if (rc2) return rc2; dw = nullptr; }
     if (dx && nhwc2_dx<T>(nhwc2_args(g), dy, w, dx, st, &rc2)) { if (rc2) return rc2; dx = nullptr; }
     if (dw && nhwc2_dw<T>(nhwc2_args(g), dy, x, dw, st, &rc2)) { if (rc2) return rc2; dw = nullptr; }
     if (!dx && !dw) return 0;
@@ -663,7 +667,7 @@ static int bwd_impl(const Geo& g, const T* dy, const T* x, const T* w, T* dx, T*
     if (dx) {                                                                                                        \
       const int total = g.N * g.H * g.W * (g.C / V);                                                                 \
       const int grid = grid_for(total, 256);                                                                         \
-      COTB200_PROF("agg3_dx_nhwc");                                                                                 \
+      COTB200_PROF_B("agg3_dx_nhwc", ((double)g.N * g.C * g.H * g.W + (double)g.N * g.heads * g.wc * g.K2 * g.HO * g.WO + (double)g.N * g.heads * g.C * g.HO * g.WO) * sizeof(T));                                                                                 \
       if (tap) agg3_dx_nhwc_fast<T, V, true><<<grid, 256, 0, st>>>(dy, w, dx, g.N, g.C, g.H, g.W, g.Cf, g.wcf, g.x_sn, \
                                                                     g.x_sw, g.w_sn, g.w_sw, g.y_sn, g.y_sw, total);  \
       else agg3_dx_nhwc_fast<T, V, false><<<grid, 256, 0, st>>>(dy, w, dx, g.N, g.C, g.H, g.W, g.Cf, g.wcf, g.x_sn, g.x_sw, \
@@ -674,7 +678,7 @@ static int bwd_impl(const Geo& g, const T* dy, const T* x, const T* w, T* dx, T*
     if (dw) {                                                                                                        \
       const int total = g.N * g.H * g.W * (g.wc / V);                                                                \
       const int grid = grid_for(total, 256);                                                                         \
-      COTB200_PROF("agg3_dw_nhwc");                                                                                 \
+      COTB200_PROF_B("agg3_dw_nhwc", ((double)g.N * g.C * g.H * g.W + (double)g.N * g.heads * g.wc * g.K2 * g.HO * g.WO + (double)g.N * g.heads * g.C * g.HO * g.WO) * sizeof(T));                                                                                 \
       if (tap) agg3_dw_nhwc_fast<T, V, true><<<grid, 256, 0, st>>>(dy, x, dw, g.N, g.C, g.H, g.W, g.wc, g.Cf, g.wcf, g.rep, \
                                                                     g.x_sn, g.x_sw, g.w_sn, g.w_sw, g.y_sn, g.y_sw,  \
                                                                     total);                                          \
@@ -693,7 +697,7 @@ static int bwd_impl(const Geo& g, const T* dy, const T* x, const T* w, T* dx, T*
   int rc = 0;
   if (dx) {
     const long long total = (long long)g.N * g.C * g.H * g.W;
-    COTB200_PROF("agg_dx_generic");
+    COTB200_PROF_B("agg_dx_generic", ((double)g.N * g.C * g.H * g.W + (double)g.N * g.heads * g.wc * g.K2 * g.HO * g.WO + (double)g.N * g.heads * g.C * g.HO * g.WO) * sizeof(T));
     if (acc_dx) agg_dx_generic<T, true><<<grid_for(total, 256, 16), 256, 0, st>>>(dy, w, dx, g, total);
     else agg_dx_generic<T, false><<<grid_for(total, 256, 16), 256, 0, st>>>(dy, w, dx, g, total);
     rc = check_launch("agg_dx_generic");
@@ -701,7 +705,7 @@ static int bwd_impl(const Geo& g, const T* dy, const T* x, const T* w, T* dx, T*
   }
   if (dw) {
     const long long total = (long long)g.N * g.heads * g.wc * g.K2 * g.HO * g.WO;
-    COTB200_PROF("agg_dw_generic");
+    COTB200_PROF_B("agg_dw_generic", ((double)g.N * g.C * g.H * g.W + (double)g.N * g.heads * g.wc * g.K2 * g.HO * g.WO + (double)g.N * g.heads * g.C * g.HO * g.WO) * sizeof(T));
     agg_dw_generic<T><<<grid_for(total, 256, 16), 256, 0, st>>>(dy, x, dw, g, total);
     rc = check_launch("agg_dw_generic");
   }

@@ -30,11 +30,13 @@ inline int check_launch(const char* what) {
 // Optional per-launch timing (cotb200_prof_enable): CUDA events recorded on the launch stream around each kernel.
 // Disabled by default (zero overhead beyond one relaxed atomic load); never enable under graph capture.
 struct ProfScope {
-  const char* name; cudaStream_t st; cudaEvent_t e0; bool on;
-  ProfScope(const char* n, cudaStream_t s);
+  const char* name; cudaStream_t st; cudaEvent_t e0; bool on; double bytes;
+  ProfScope(const char* n, cudaStream_t s, double algorithmic_bytes = 0.0);
   ~ProfScope();
 };
+// `bytes` = ALGORITHMIC bytes of the launch: what the kernel must move, not what it happened to.
 #define COTB200_PROF(name) cotb200::ProfScope _prof_scope(name, st)
+#define COTB200_PROF_B(name, bytes) cotb200::ProfScope _prof_scope(name, st, (double)(bytes))
 
 inline int num_sms() {
   static int sms = 0;

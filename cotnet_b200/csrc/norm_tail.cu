@@ -595,7 +595,7 @@ extern "C" int cotb200_col_stats(int dtype, int B, int HW, int C, const void* x,
         int rc = make_geo(g, B, HW, cw, vec, 2, &smem);
         if (rc) return rc;
         g.ld = C;
-        COTB200_PROF("col_stats");
+        COTB200_PROF_B("col_stats", (double)B * HW * cw * sizeof(T));
         NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(col_stats_kernel<T, V>, smem))) return rc;
                                col_stats_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)x + c0, sum + c0, sq + c0, g); });
         if ((rc = check_launch("col_stats"))) return rc;
@@ -617,7 +617,7 @@ extern "C" int cotb200_tail_pool(int dtype, int B, int HW, int C, const void* u,
       RowsGeo g; size_t smem;
       int rc = make_geo(g, B, HW, C, vec, 1, &smem);
       if (rc) return rc;
-      COTB200_PROF("tail_pool");
+      COTB200_PROF_B("tail_pool", (double)B * HW * C * 2 * sizeof(T));
       NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(tail_pool_kernel<T, V>, smem))) return rc;
                              tail_pool_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)u, (const T*)k, scale, shift, psum, g); });
       return check_launch("tail_pool");
@@ -637,7 +637,7 @@ extern "C" int cotb200_tail_combine(int dtype, int B, int HW, int C, const void*
       RowsGeo g; size_t smem;
       int rc = make_geo(g, B, HW, C, vec, 1, &smem);
       if (rc) return rc;
-      COTB200_PROF("tail_combine");
+      COTB200_PROF_B("tail_combine", (double)B * HW * C * 3 * sizeof(T));
       NT_DISPATCH_VEC(vec, { tail_combine_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)u, (const T*)k, scale, shift, a, (T*)out, g); });
       return check_launch("tail_combine");
     }
@@ -656,7 +656,7 @@ extern "C" int cotb200_tail_bwd_sums(int dtype, int B, int HW, int C, const void
       RowsGeo g; size_t smem;
       int rc = make_geo(g, B, HW, C, vec, 2, &smem);
       if (rc) return rc;
-      COTB200_PROF("tail_bwd_sums");
+      COTB200_PROF_B("tail_bwd_sums", (double)B * HW * C * 3 * sizeof(T));
       NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(tail_bwd_sums_kernel<T, V>, smem))) return rc;
                              tail_bwd_sums_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dout, (const T*)u, (const T*)k, scale, shift, S, g); });
       return check_launch("tail_bwd_sums");
@@ -677,7 +677,7 @@ extern "C" int cotb200_tail_bwd_dz_sums(int dtype, int B, int HW, int C, const v
       RowsGeo g; size_t smem;
       int rc = make_geo(g, B, HW, C, vec, 2, &smem);
       if (rc) return rc;
-      COTB200_PROF("tail_bwd_dz_sums");
+      COTB200_PROF_B("tail_bwd_dz_sums", (double)B * HW * C * 2 * sizeof(T));
       NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(tail_bwd_dz_sums_kernel<T, V>, smem))) return rc;
                              tail_bwd_dz_sums_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dout, (const T*)u, scale, shift, mu, rstd, a, dpn, sum_dz, sum_dzx, g); });
       return check_launch("tail_bwd_dz_sums");
@@ -698,7 +698,7 @@ extern "C" int cotb200_tail_bwd_apply(int dtype, int B, int HW, int C, const voi
       RowsGeo g; size_t smem;
       int rc = make_geo(g, B, HW, C, vec, 1, &smem);
       if (rc) return rc;
-      COTB200_PROF("tail_bwd_apply");
+      COTB200_PROF_B("tail_bwd_apply", (double)B * HW * C * 4 * sizeof(T));
       NT_DISPATCH_VEC(vec, { tail_bwd_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dout, (const T*)u, scale, shift, mu, rstd, a, dpn, c1, c2, (T*)du, (T*)dk, g); });
       return check_launch("tail_bwd_apply");
     }
@@ -718,7 +718,7 @@ extern "C" int cotb200_gn9_stats(int dtype, int B, int HW, int wc, int gc, const
       RowsGeo g; size_t smem;
       int rc = make_geo(g, B, HW, J, vec, 2, &smem);
       if (rc) return rc;
-      COTB200_PROF("gn9_stats");
+      COTB200_PROF_B("gn9_stats", (double)B * HW * J * sizeof(T));
       NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(gn_stats_kernel<T, V>, smem))) return rc;
                              gn_stats_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)l, gsum, gsq, g, wc); });
       return check_launch("gn9_stats");
@@ -739,7 +739,7 @@ extern "C" int cotb200_gn9_apply(int dtype, int B, int HW, int wc, int gc, const
       RowsGeo g; size_t smem;
       int rc = make_geo(g, B, HW, J, vec, 1, &smem);
       if (rc) return rc;
-      COTB200_PROF("gn9_apply");
+      COTB200_PROF_B("gn9_apply", (double)B * HW * J * 2 * sizeof(T));
       NT_DISPATCH_VEC(vec, { gn_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)l, mean, rstd, gamma, beta, (T*)out, g, wc, gc); });
       return check_launch("gn9_apply");
     }
@@ -760,7 +760,7 @@ extern "C" int cotb200_gn9_bwd_sums(int dtype, int B, int HW, int wc, int gc, co
       RowsGeo g; size_t smem;
       int rc = make_geo(g, B, HW, J, vec, 2, &smem);
       if (rc) return rc;
-      COTB200_PROF("gn9_bwd_sums");
+      COTB200_PROF_B("gn9_bwd_sums", (double)B * HW * J * 2 * sizeof(T));
       NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(gn_bwd_sums_kernel<T, V>, smem))) return rc;
                              gn_bwd_sums_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dg, (const T*)l, mean, rstd, gamma, s1, s2, dgamma, dbeta, g, wc, gc); });
       return check_launch("gn9_bwd_sums");
@@ -782,7 +782,7 @@ extern "C" int cotb200_gn9_bwd_apply(int dtype, int B, int HW, int wc, int gc, c
       RowsGeo g; size_t smem;
       int rc = make_geo(g, B, HW, J, vec, 1, &smem);
       if (rc) return rc;
-      COTB200_PROF("gn9_bwd_apply");
+      COTB200_PROF_B("gn9_bwd_apply", (double)B * HW * J * 3 * sizeof(T));
       NT_DISPATCH_VEC(vec, { gn_bwd_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dg, (const T*)l, mean, rstd, gamma, s1, s2, (T*)dl, g, wc, gc); });
       return check_launch("gn9_bwd_apply");
     }
@@ -806,7 +806,7 @@ extern "C" int cotb200_bn_apply(int dtype, int B, int HW, int C, const void* x, 
         if (rc) return rc;
         g.ld = C;
         const T* xp = (const T*)x + c0; const T* rp = res ? (const T*)res + c0 : nullptr; T* yp = (T*)y + c0;
-        COTB200_PROF("bn_apply");
+        COTB200_PROF_B("bn_apply", (double)B * HW * cw * (2 + (res ? 1 : 0)) * sizeof(T));
         NT_DISPATCH_VEC(vec, {
           if (relu) { if (res) bn_apply_kernel<T, V, 1, true><<<NT_GRID, NT_THREADS, 0, st>>>(xp, rp, scale + c0, shift + c0, yp, g);
                       else bn_apply_kernel<T, V, 1, false><<<NT_GRID, NT_THREADS, 0, st>>>(xp, nullptr, scale + c0, shift + c0, yp, g); }
@@ -837,7 +837,7 @@ extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* 
         if (rc) return rc;
         g.ld = C;
         const T* dp = (const T*)dy + c0; const T* xp = (const T*)x + c0; const T* yp = y ? (const T*)y + c0 : nullptr;
-        COTB200_PROF("bn_bwd_sums");
+        COTB200_PROF_B("bn_bwd_sums", (double)B * HW * cw * (2 + (relu ? 1 : 0)) * sizeof(T));
         NT_DISPATCH_VEC(vec, {
           if (relu) { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 1>, smem))) return rc;
                       bn_bwd_sums_kernel<T, V, 1><<<NT_GRID, NT_THREADS, smem, st>>>(dp, xp, yp, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
@@ -872,7 +872,7 @@ extern "C" int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void*
         const T* dp = (const T*)dy + c0; const T* xp = (const T*)x + c0; const T* yp = y ? (const T*)y + c0 : nullptr;
         T* dxp = (T*)dx + c0; T* drp = dres ? (T*)dres + c0 : nullptr;
         const float* k1 = c1 ? c1 + c0 : nullptr; const float* k2 = c2 ? c2 + c0 : nullptr;
-        COTB200_PROF("bn_bwd_apply");
+        COTB200_PROF_B("bn_bwd_apply", (double)B * HW * cw * (3 + (relu ? 1 : 0) + (dres ? 1 : 0)) * sizeof(T));
         NT_DISPATCH_VEC(vec, {
           if (relu) { if (dres) bn_bwd_apply_kernel<T, V, 1, true><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, yp, scale + c0, mu + c0, rstd + c0, k1, k2, dxp, drp, g);
                       else bn_bwd_apply_kernel<T, V, 1, false><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, yp, scale + c0, mu + c0, rstd + c0, k1, k2, dxp, nullptr, g); }

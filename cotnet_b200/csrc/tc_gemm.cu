@@ -34,6 +34,7 @@ struct TcParams {
   int H, W, B, hbox, bbox;  // conv geometry
   int kc;                   // conv: 64-channel chunks per tap (= bn / 64)
   int relu;
+  int m_tiles;              // number of row tiles (persistent CTAs loop over m_tiles * n_tiles)
   int stages;               // smem ring depth actually used (<= TC_STAGES): short K loops take less smem -> more CTAs/SM
   long long ldd;            // D row pitch (elements)
   __nv_bfloat16* D;
@@ -131,26 +132,14 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(TC_THREADS, 3)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
-               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const TcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int a_bytes = TC_BM * TC_BK * 2;             // 16 KB
-  const int b_bytes = p.bn * TC_BK * 2;
-  const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
-  __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_accum;
-  __shared__ uint32_t s_tmem;
-  __shared__ float s_sum[256], s_sq[256];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x, n0 = blockIdx.y * p.bn;
-  const int nkb = p.mode == 0 ? p.kb1 + p.kb2 : 9 * p.kc;
-
-  // tile -> first pixel row
-  int b0 = 0, h0 = 0;
-  long long m0;
-  int rows_valid;
+// Persistent: every CTA loops over output tiles.  Three pipelines run concurrently --
+//   TMA producer  -> smem ring (full/empty mbarriers, continuous across tiles)
+//   MMA issuer    -> two TMEM accumulator buffers (tmem_full/tmem_empty mbarriers)
+//   epilogue warps drain buffer i while the MMAs of tile i+1 fill the other one.
+// (The first version launched one CTA per tile: ncu showed ~5 us of fixed per-CTA cost -- barrier init, TMEM alloc,
+//  a cold TMA round trip -- dominating tiles with 1-2 k-blocks; profiles/r01_tma_tc_ncu.md.)
+__device__ __forceinline__ void tc_tile_origin(const TcParams& p, int tile_m, int& b0, int& h0, long long& m0, int& rows_valid) {
+  b0 = 0; h0 = 0;
   if (p.mode == 0) {
     m0 = (long long)tile_m * TC_BM;
     rows_valid = (int)min((long long)TC_BM, (long long)p.M - m0);
@@ -164,16 +153,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     m0 = (long long)b0 * p.H * p.W;
     rows_valid = min(p.bbox, p.B - b0) * p.H * p.W;
   }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_bytes = TC_BM * TC_BK * 2;             // 16 KB
+  const int b_bytes = p.bn * TC_BK * 2;
+  const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
+  __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_tfull[2], s_tempty[2];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_sum[256], s_sq[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = p.mode == 0 ? p.kb1 + p.kb2 : 9 * p.kc;
+  const int n_tiles = (p.N + p.bn - 1) / p.bn;
+  const int total_tiles = p.m_tiles * n_tiles;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB1) : "memory");
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
-    mbar_init(smem_u32(&s_accum), 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&s_tfull[a]), 1); mbar_init(smem_u32(&s_tempty[a]), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   uint32_t ncols = 32;
-  while ((int)ncols < p.bn) ncols <<= 1;
+  while ((int)ncols < 2 * p.bn) ncols <<= 1;           // two accumulator buffers
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(ncols)
                  : "memory");
@@ -188,28 +195,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (kb / p.stages) & 1;
-        mbar_wait(smem_u32(&s_empty[s]), ph ^ 1);
-        const uint32_t full = smem_u32(&s_full[s]);
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
-        // TMA counts the whole box (zero-filled elements included): conv boxes hold rows_per_tile <= 128 rows
-        mbar_expect_tx(full, (uint32_t)(p.rows_per_tile * TC_BK * 2 + b_bytes));
-        if (p.mode == 0) {
-          if (kb < p.kb1) {
-            tma_load_2d(sa, &mapA1, full, kb * TC_BK, (int)m0);
-            tma_load_2d(sb, &mapB1, full, kb * TC_BK, n0);
+      int kbc = 0;                                      // k-block counter, continuous across tiles
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tile_m = tile % p.m_tiles, n0 = (tile / p.m_tiles) * p.bn;
+        int b0, h0, rows_valid; long long m0;
+        tc_tile_origin(p, tile_m, b0, h0, m0, rows_valid);
+        for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+          const int s = kbc % p.stages;
+          const uint32_t ph = (kbc / p.stages) & 1;
+          mbar_wait(smem_u32(&s_empty[s]), ph ^ 1);
+          const uint32_t full = smem_u32(&s_full[s]);
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
+          // TMA counts the whole box (zero-filled elements included): conv boxes hold rows_per_tile <= 128 rows
+          mbar_expect_tx(full, (uint32_t)(p.rows_per_tile * TC_BK * 2 + b_bytes));
+          if (p.mode == 0) {
+            if (kb < p.kb1) {
+              tma_load_2d(sa, &mapA1, full, kb * TC_BK, (int)m0);
+              tma_load_2d(sb, &mapB1, full, kb * TC_BK, n0);
+            } else {
+              tma_load_2d(sa, &mapA2, full, (kb - p.kb1) * TC_BK, (int)m0);
+              tma_load_2d(sb, &mapB2, full, (kb - p.kb1) * TC_BK, n0);
+            }
           } else {
-            tma_load_2d(sa, &mapA2, full, (kb - p.kb1) * TC_BK, (int)m0);
-            tma_load_2d(sb, &mapB2, full, (kb - p.kb1) * TC_BK, n0);
+            const int tap = kb / p.kc, cc = kb % p.kc;
+            const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+            // A: 4-D box {64 ch, W, hbox, bbox}; negative / overflowing coordinates are zero-filled == zero padding
+            tma_load_4d(sa, &mapA1, full, n0 + cc * TC_BK, dw, h0 + dh, b0);
+            tma_load_2d(sb, &mapB1, full, kb * TC_BK, n0);
           }
-        } else {
-          const int tap = kb / p.kc, cc = kb % p.kc;
-          const int dh = tap / 3 - 1, dw = tap % 3 - 1;
-          // A: 4-D box {64 ch, W, hbox, bbox}; negative / overflowing coordinates are zero-filled == zero padding
-          tma_load_4d(sa, &mapA1, full, n0 + cc * TC_BK, dw, h0 + dh, b0);
-          tma_load_2d(sb, &mapB1, full, kb * TC_BK, n0);
         }
       }
     }
@@ -217,76 +230,98 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(p.bn);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (kb / p.stages) & 1;
-        mbar_wait(smem_u32(&s_full[s]), ph);
+      int kbc = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const int acc = ti & 1;
+        const uint32_t use = (uint32_t)(ti >> 1);
+        mbar_wait(smem_u32(&s_tempty[acc]), (use & 1) ^ 1);      // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
-        const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.bn);
+        for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+          const int s = kbc % p.stages;
+          const uint32_t ph = (kbc / p.stages) & 1;
+          mbar_wait(smem_u32(&s_full[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          // advance 16 bf16 = 32 B inside the 128 B swizzle atom: start-address field += 2
-          umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle atom: start-address field += 2
+            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(smem_u32(&s_empty[s]));           // frees the smem stage when the MMAs above retire
         }
-        umma_commit(smem_u32(&s_empty[s]));           // frees the smem stage when the MMAs above retire
+        umma_commit(smem_u32(&s_tfull[acc]));            // accumulator of this tile complete
       }
-      umma_commit(smem_u32(&s_accum));                // accumulator complete
     }
   } else {
     // ===================== epilogue (4 warps, TMEM lane quadrant = warp % 4) =====================
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
-    const bool row_ok = r < rows_valid && (m0 + r) < p.M;
-    mbar_wait(smem_u32(&s_accum), 0);
-    __syncwarp();
-    tc_fence_after();
     const bool stats = p.col_sum != nullptr;
-    __nv_bfloat16* drow = p.D + (m0 + r) * p.ldd + n0;
-    for (int c = 0; c * 32 < p.bn; ++c) {
-      uint32_t raw[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), raw);
-      float v[32];
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int tile_m = tile % p.m_tiles, n0 = (tile / p.m_tiles) * p.bn;
+      int b0, h0, rows_valid; long long m0;
+      tc_tile_origin(p, tile_m, b0, h0, m0, rows_valid);
+      const int acc = ti & 1;
+      const uint32_t use = (uint32_t)(ti >> 1);
+      const bool row_ok = r < rows_valid && (m0 + r) < p.M;
+      mbar_wait(smem_u32(&s_tfull[acc]), use & 1);
+      __syncwarp();
+      tc_fence_after();
+      __nv_bfloat16* drow = p.D + (m0 + r) * p.ldd + n0;
+      for (int c = 0; c * 32 < p.bn; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn + c * 32), raw);
+        float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-      if (stats) {
-        float a[32], b[32];
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        if (stats) {
+          float a[32], b[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { a[j] = row_ok ? v[j] : 0.f; b[j] = a[j] * a[j]; }
-        const float cs = warp_colsum32(a);
-        const float cq = warp_colsum32(b);
-        atomicAdd(&s_sum[c * 32 + lane], cs);
-        atomicAdd(&s_sq[c * 32 + lane], cq);
-      }
-      if (row_ok) {
+          for (int j = 0; j < 32; ++j) { a[j] = row_ok ? v[j] : 0.f; b[j] = a[j] * a[j]; }
+          const float cs = warp_colsum32(a);
+          const float cq = warp_colsum32(b);
+          atomicAdd(&s_sum[c * 32 + lane], cs);
+          atomicAdd(&s_sq[c * 32 + lane], cq);
+        }
+        if (row_ok) {
 #pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          const int nb = n0 + c * 32 + j8 * 8;
-          if (nb < p.N && c * 32 + j8 * 8 < p.bn) {
-            uint32_t pk[4];
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const int nb = n0 + c * 32 + j8 * 8;
+            if (nb < p.N && c * 32 + j8 * 8 < p.bn) {
+              uint32_t pk[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float lo = v[j8 * 8 + 2 * e], hi = v[j8 * 8 + 2 * e + 1];
-              const int n = nb + 2 * e;
-              if (p.scale) { lo *= __ldg(p.scale + n); hi *= __ldg(p.scale + n + 1); }
-              if (p.shift) { lo += __ldg(p.shift + n); hi += __ldg(p.shift + n + 1); }
-              if (p.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+              for (int e = 0; e < 4; ++e) {
+                float lo = v[j8 * 8 + 2 * e], hi = v[j8 * 8 + 2 * e + 1];
+                const int n = nb + 2 * e;
+                if (p.scale) { lo *= __ldg(p.scale + n); hi *= __ldg(p.scale + n + 1); }
+                if (p.shift) { lo += __ldg(p.shift + n); hi += __ldg(p.shift + n + 1); }
+                if (p.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(drow + c * 32 + j8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
-            *reinterpret_cast<uint4*>(drow + c * 32 + j8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
       }
-    }
-    if (stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");    // the 4 epilogue warps only
-      const int t = threadIdx.x - 64;
-      for (int j = t; j < p.bn; j += 128) {
-        if (n0 + j < p.N) {
-          atomicAdd(p.col_sum + n0 + j, s_sum[j]);
-          atomicAdd(p.col_sqsum + n0 + j, s_sq[j]);
+      // accumulator buffer drained: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tempty[acc])) : "memory");
+      if (stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");    // the 4 epilogue warps only
+        const int t = threadIdx.x - 64;
+        for (int j = t; j < p.bn; j += 128) {
+          if (n0 + j < p.N) {
+            atomicAdd(p.col_sum + n0 + j, s_sum[j]);
+            atomicAdd(p.col_sqsum + n0 + j, s_sq[j]);
+          }
+          s_sum[j] = 0.f; s_sq[j] = 0.f;
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }
   }
@@ -348,11 +383,12 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, 
 }
 
 static int tc_launch(const CUtensorMap& a1, const CUtensorMap& b1, const CUtensorMap& a2, const CUtensorMap& b2,
-                     TcParams p, int m_tiles, cudaStream_t st, const char* what) {
+                     TcParams p, int m_tiles, cudaStream_t st, const char* what, double alg_bytes) {
   const int a_bytes = TC_BM * TC_BK * 2, b_bytes = p.bn * TC_BK * 2;
   const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
-  const int nkb = p.mode == 0 ? p.kb1 + p.kb2 : 9 * p.kc;
-  p.stages = nkb < TC_STAGES ? nkb : TC_STAGES;
+  p.m_tiles = m_tiles;
+  p.stages = TC_STAGES;
+  while (p.stages > 2 && p.stages * stage_bytes > 96 * 1024) --p.stages;     // two CTAs per SM
   const int smem = p.stages * stage_bytes + 1024;
   static int configured = 0;
   if (configured < smem) {
@@ -360,8 +396,10 @@ static int tc_launch(const CUtensorMap& a1, const CUtensorMap& b1, const CUtenso
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured = 200 * 1024;
   }
-  dim3 grid(m_tiles, (p.N + p.bn - 1) / p.bn);
-  COTB200_PROF(what);
+  const int total = m_tiles * ((p.N + p.bn - 1) / p.bn);
+  int grid = 2 * num_sms();
+  if (grid > total) grid = total;
+  COTB200_PROF_B(what, alg_bytes);
   tc_gemm_kernel<<<grid, TC_THREADS, smem, st>>>(a1, b1, a2, b2, p);
   return check_launch(what);
 }
@@ -399,7 +437,8 @@ extern "C" int cotb200_gemm_bf16(int M, int N, int K1, const void* A1, long long
     if ((rc = make_map_2d(&a2, A2, M, K2, lda2, TC_BM))) return rc;
     if ((rc = make_map_2d(&b2, B2, N, K2, ldb2, p.bn))) return rc;
   } else { a2 = a1; b2 = b1; }
-  return tc_launch(a1, b1, a2, b2, p, (M + TC_BM - 1) / TC_BM, st, "tc_gemm_1x1");
+  return tc_launch(a1, b1, a2, b2, p, (M + TC_BM - 1) / TC_BM, st, "tc_gemm_1x1",
+                   2.0 * ((double)M * (K1 + K2 + N) + (double)N * (K1 + K2)));
 }
 
 // 3x3 / pad 1 / stride 1 convolution, NHWC bf16, with dense-per-N-tile prepared weights
@@ -434,5 +473,5 @@ extern "C" int cotb200_conv3x3_bf16(int B, int H, int W, int C, const void* X, l
   int rc;
   if ((rc = make_map_nhwc(&a1, X, B, H, W, C, ldx, p.hbox, p.bbox))) return rc;
   if ((rc = make_map_2d(&b1, Wp, C, 9LL * bn, 9LL * bn, bn))) return rc;
-  return tc_launch(a1, b1, a1, b1, p, m_tiles, st, "tc_conv3x3");
+  return tc_launch(a1, b1, a1, b1, p, m_tiles, st, "tc_conv3x3", 2.0 * (2.0 * (double)B * H * W * C + 9.0 * (double)C * bn));
 }

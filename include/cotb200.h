@@ -72,7 +72,7 @@ const char* cotb200_last_error(void);
 long long cotb200_launch_count(void);
 
 /* Per-kernel device timing for the bench's roofline line: when enabled every launch of this library is
- * bracketed by CUDA events on its stream; cotb200_prof_report writes "<kernel> <launches> <total_ms>" lines
+ * bracketed by CUDA events on its stream; cotb200_prof_report writes "<kernel> <launches> <total_ms> <algorithmic bytes>" lines
  * (returns the length needed).  Off by default; do not enable during CUDA-graph capture. */
 void cotb200_prof_enable(int on);
 int cotb200_prof_report(char* buf, int len);
