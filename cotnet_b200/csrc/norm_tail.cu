@@ -173,7 +173,7 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(NT_THREADS)
 tail_bwd_dz_sums_kernel(const T* __restrict__ dout, const T* __restrict__ u, const float* __restrict__ scale,
                         const float* __restrict__ shift, const float* __restrict__ mu, const float* __restrict__ rstd,
-                        const float* __restrict__ a, const float* __restrict__ dpn, float* __restrict__ sum_dz,
+                        const float* __restrict__ a, const float* __restrict__ dpn, float pscale, float* __restrict__ sum_dz,
                         float* __restrict__ sum_dzx, RowsGeo g) {
   extern __shared__ float sm[];
   const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
@@ -185,7 +185,7 @@ tail_bwd_dz_sums_kernel(const T* __restrict__ dout, const T* __restrict__ u, con
     const int c = tx * VEC + i;
     acc[0][i] = acc[1][i] = 0.f;
     sc[i] = active ? scale[c] : 0.f; sh[i] = active ? shift[c] : 0.f; m[i] = active ? mu[c] : 0.f; rs[i] = active ? rstd[c] : 0.f;
-    a0[i] = active ? a[((long long)b * g.C + c) * 2] : 0.f; dp[i] = active ? dpn[(long long)b * g.C + c] : 0.f;
+    a0[i] = active ? a[((long long)b * g.C + c) * 2] : 0.f; dp[i] = active ? dpn[(long long)b * g.C + c] * pscale : 0.f;
   }
   if (active) {
     const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(NT_THREADS)
 tail_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ u, const float* __restrict__ scale,
                       const float* __restrict__ shift, const float* __restrict__ mu, const float* __restrict__ rstd,
                       const float* __restrict__ a, const float* __restrict__ dpn, const float* __restrict__ c1,
-                      const float* __restrict__ c2, T* __restrict__ du, T* __restrict__ dk, RowsGeo g) {
+                      const float* __restrict__ c2, float inv_n, float pscale, T* __restrict__ du, T* __restrict__ dk, RowsGeo g) {
   const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
   if (!(tx < g.cq && ty < g.ry)) return;
   const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
@@ -226,8 +226,8 @@ tail_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ u, const
   for (int i = 0; i < VEC; ++i) {
     const int c = tx * VEC + i;
     sc[i] = scale[c]; sh[i] = shift[c]; m[i] = mu[c]; rs[i] = rstd[c];
-    a0[i] = a[((long long)b * g.C + c) * 2]; a1[i] = a[((long long)b * g.C + c) * 2 + 1]; dp[i] = dpn[(long long)b * g.C + c];
-    k1[i] = c1 ? c1[c] : 0.f; k2[i] = c2 ? c2[c] : 0.f;
+    a0[i] = a[((long long)b * g.C + c) * 2]; a1[i] = a[((long long)b * g.C + c) * 2 + 1]; dp[i] = dpn[(long long)b * g.C + c] * pscale;
+    k1[i] = c1 ? c1[c] * inv_n : 0.f; k2[i] = c2 ? c2[c] * inv_n : 0.f;
   }
   const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
   for (int r = r0 + ty; r < r1; r += g.ry) {
@@ -319,7 +319,7 @@ template <typename T, int VEC, int ACT, bool RES>
 __global__ void __launch_bounds__(NT_THREADS)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ scale,
                     const float* __restrict__ mu, const float* __restrict__ rstd, const float* __restrict__ c1,
-                    const float* __restrict__ c2, T* __restrict__ dx, T* __restrict__ dres, RowsGeo g) {
+                    const float* __restrict__ c2, float inv_n, T* __restrict__ dx, T* __restrict__ dres, RowsGeo g) {
   const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
   if (!(tx < g.cq && ty < g.ry)) return;
   const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
@@ -327,7 +327,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const int c = tx * VEC + i;
-    sc[i] = scale[c]; m[i] = mu[c]; rs[i] = rstd[c]; k1[i] = c1 ? c1[c] : 0.f; k2[i] = c2 ? c2[c] : 0.f;
+    sc[i] = scale[c]; m[i] = mu[c]; rs[i] = rstd[c]; k1[i] = c1 ? c1[c] * inv_n : 0.f; k2[i] = c2 ? c2[c] * inv_n : 0.f;
   }
   const long long base = ((long long)b * g.HW) * g.ld + tx * VEC;
   for (int r = r0 + ty; r < r1; r += g.ry) {
@@ -346,6 +346,36 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
     st_pack<T, VEC>(dx + base + (long long)r * g.ld, o);
     if (RES) st_pack<T, VEC>(dres + base + (long long)r * g.ld, o2);
   }
+}
+
+// One tiny launch instead of ~12 eager ops: batch mean / biased var from the column sums, scale/shift for the apply
+// pass, mean/rstd for the backward pass, and the nn.BatchNorm2d running-buffer update (momentum, unbiased variance).
+// use_batch == 0: eval mode, statistics come from the running buffers.
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sq, const float* __restrict__ weight,
+                                   const float* __restrict__ bias, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float n, float eps, float momentum, int use_batch,
+                                   int update_running, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (use_batch) {
+    mean = sum[c] / n;
+    var = fmaxf(sq[c] / n - mean * mean, 0.f);
+    if (update_running) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (n / fmaxf(n - 1.f, 1.f));
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float rstd = rsqrtf(var + eps);
+  const float sc = (weight ? weight[c] : 1.f) * rstd;
+  scale[c] = sc;
+  shift[c] = (bias ? bias[c] : 0.f) - mean * sc;
+  mean_out[c] = mean;
+  rstd_out[c] = rstd;
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm(9 taps)
@@ -667,7 +697,7 @@ extern "C" int cotb200_tail_bwd_sums(int dtype, int B, int HW, int C, const void
 
 extern "C" int cotb200_tail_bwd_dz_sums(int dtype, int B, int HW, int C, const void* dout, const void* u, const float* scale,
                                         const float* shift, const float* mu, const float* rstd, const float* a,
-                                        const float* dpn, float* sum_dz, float* sum_dzx, void* stream) {
+                                        const float* dpn, float pscale, float* sum_dz, float* sum_dzx, void* stream) {
   if (!dout || !u || !scale || !shift || !mu || !rstd || !a || !dpn || !sum_dz || !sum_dzx) { set_error("tail_bwd_dz_sums: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("tail_bwd_dz_sums: fp64 not supported"); return COTB200_EDTYPE; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -679,7 +709,7 @@ extern "C" int cotb200_tail_bwd_dz_sums(int dtype, int B, int HW, int C, const v
       if (rc) return rc;
       COTB200_PROF_B("tail_bwd_dz_sums", (double)B * HW * C * 2 * sizeof(T));
       NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(tail_bwd_dz_sums_kernel<T, V>, smem))) return rc;
-                             tail_bwd_dz_sums_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dout, (const T*)u, scale, shift, mu, rstd, a, dpn, sum_dz, sum_dzx, g); });
+                             tail_bwd_dz_sums_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dout, (const T*)u, scale, shift, mu, rstd, a, dpn, pscale, sum_dz, sum_dzx, g); });
       return check_launch("tail_bwd_dz_sums");
     }
   });
@@ -688,7 +718,8 @@ extern "C" int cotb200_tail_bwd_dz_sums(int dtype, int B, int HW, int C, const v
 
 extern "C" int cotb200_tail_bwd_apply(int dtype, int B, int HW, int C, const void* dout, const void* u, const float* scale,
                                       const float* shift, const float* mu, const float* rstd, const float* a,
-                                      const float* dpn, const float* c1, const float* c2, void* du, void* dk, void* stream) {
+                                      const float* dpn, const float* c1, const float* c2, float inv_n, float pscale, void* du, void* dk,
+                                      void* stream) {
   if (!dout || !u || !scale || !shift || !mu || !rstd || !a || !dpn || !du || !dk) { set_error("tail_bwd_apply: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("tail_bwd_apply: fp64 not supported"); return COTB200_EDTYPE; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -699,7 +730,7 @@ extern "C" int cotb200_tail_bwd_apply(int dtype, int B, int HW, int C, const voi
       int rc = make_geo(g, B, HW, C, vec, 1, &smem);
       if (rc) return rc;
       COTB200_PROF_B("tail_bwd_apply", (double)B * HW * C * 4 * sizeof(T));
-      NT_DISPATCH_VEC(vec, { tail_bwd_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dout, (const T*)u, scale, shift, mu, rstd, a, dpn, c1, c2, (T*)du, (T*)dk, g); });
+      NT_DISPATCH_VEC(vec, { tail_bwd_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dout, (const T*)u, scale, shift, mu, rstd, a, dpn, c1, c2, inv_n, pscale, (T*)du, (T*)dk, g); });
       return check_launch("tail_bwd_apply");
     }
   });
@@ -854,7 +885,7 @@ extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* 
 
 extern "C" int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y,
                                     const float* scale, const float* mu, const float* rstd, const float* c1, const float* c2,
-                                    int relu, void* dx, void* dres, void* stream) {
+                                    float inv_n, int relu, void* dx, void* dres, void* stream) {
   if (!dy || !x || !scale || !mu || !rstd || !dx || (relu && !y)) { set_error("bn_bwd_apply: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("bn_bwd_apply: fp64 not supported"); return COTB200_EDTYPE; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -874,10 +905,10 @@ extern "C" int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void*
         const float* k1 = c1 ? c1 + c0 : nullptr; const float* k2 = c2 ? c2 + c0 : nullptr;
         COTB200_PROF_B("bn_bwd_apply", (double)B * HW * cw * (3 + (relu ? 1 : 0) + (dres ? 1 : 0)) * sizeof(T));
         NT_DISPATCH_VEC(vec, {
-          if (relu) { if (dres) bn_bwd_apply_kernel<T, V, 1, true><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, yp, scale + c0, mu + c0, rstd + c0, k1, k2, dxp, drp, g);
-                      else bn_bwd_apply_kernel<T, V, 1, false><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, yp, scale + c0, mu + c0, rstd + c0, k1, k2, dxp, nullptr, g); }
-          else { if (dres) bn_bwd_apply_kernel<T, V, 0, true><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, nullptr, scale + c0, mu + c0, rstd + c0, k1, k2, dxp, drp, g);
-                 else bn_bwd_apply_kernel<T, V, 0, false><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, nullptr, scale + c0, mu + c0, rstd + c0, k1, k2, dxp, nullptr, g); }
+          if (relu) { if (dres) bn_bwd_apply_kernel<T, V, 1, true><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, yp, scale + c0, mu + c0, rstd + c0, k1, k2, inv_n, dxp, drp, g);
+                      else bn_bwd_apply_kernel<T, V, 1, false><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, yp, scale + c0, mu + c0, rstd + c0, k1, k2, inv_n, dxp, nullptr, g); }
+          else { if (dres) bn_bwd_apply_kernel<T, V, 0, true><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, nullptr, scale + c0, mu + c0, rstd + c0, k1, k2, inv_n, dxp, drp, g);
+                 else bn_bwd_apply_kernel<T, V, 0, false><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, nullptr, scale + c0, mu + c0, rstd + c0, k1, k2, inv_n, dxp, nullptr, g); }
         });
         if ((rc = check_launch("bn_bwd_apply"))) return rc;
       }
@@ -885,4 +916,18 @@ extern "C" int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void*
     }
   });
   return 0;
+}
+
+extern "C" int cotb200_bn_finalize(int C, const float* sum, const float* sq, const float* weight, const float* bias,
+                                   float* running_mean, float* running_var, float n, float eps, float momentum, int use_batch,
+                                   int update_running, float* scale, float* shift, float* mean, float* rstd, void* stream) {
+  if (!scale || !shift || !mean || !rstd || (use_batch && (!sum || !sq)) || ((!use_batch || update_running) && (!running_mean || !running_var))) {
+    set_error("bn_finalize: NULL pointer"); return COTB200_ENULL;
+  }
+  if (C <= 0) { set_error("bn_finalize: C <= 0"); return COTB200_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  COTB200_PROF("bn_finalize");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sum, sq, weight, bias, running_mean, running_var, n, eps, momentum, use_batch,
+                                                     update_running, scale, shift, mean, rstd, C);
+  return check_launch("bn_finalize");
 }

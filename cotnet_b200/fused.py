@@ -28,30 +28,52 @@ def _f32(t):
     return t.detach().float().contiguous()
 
 
-def _bn_batch_stats(x, bn, lib, st, dt):
-    """(mean, biased var) of a channels_last tensor; training mode updates the module's running buffers exactly like
-    nn.BatchNorm2d (momentum, unbiased running variance, num_batches_tracked)."""
+def _bn_prepare(bn, weight, bias, C, n, sums, device, st):
+    """[4, C] fp32 = (scale, shift, mean, rstd) in ONE launch (cotb200_bn_finalize).  `sums` = [2, C] column sums of the
+    batch (training mode) or None (eval: running statistics).  Training updates the module's running buffers exactly like
+    nn.BatchNorm2d (momentum, unbiased variance, num_batches_tracked)."""
+    lib = _lib.load()
+    out = torch.empty(4, C, dtype=torch.float32, device=device)
+    use_batch = sums is not None
+    update = bool(use_batch and bn.running_mean is not None and bn.track_running_stats)
+    mom = 0.0
+    rm = rv = None
+    if update:
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+        mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+    if update or not use_batch:
+        rm, rv = bn.running_mean, bn.running_var
+        if rm.dtype != torch.float32:
+            rm, rv = rm.float(), rv.float()
+    w32 = None if weight is None else weight.detach().float().contiguous()
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    _lib.check(lib.cotb200_bn_finalize(C, _lib.ptr(sums[0]) if use_batch else None, _lib.ptr(sums[1]) if use_batch else None,
+                                       _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(rm), _lib.ptr(rv), float(n), float(bn.eps),
+                                       float(mom), 1 if use_batch else 0, 1 if update else 0, out[0].data_ptr(),
+                                       out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), st), "bn_finalize")
+    if update and rm is not bn.running_mean:
+        with torch.no_grad():
+            bn.running_mean.copy_(rm)
+            bn.running_var.copy_(rv)
+    return out
+
+
+def _bn_batch_stats(x, bn, weight, bias, lib, st, dt):
+    """Statistics pass (training) + finalize -> ([4,C] scale/shift/mean/rstd, used_batch_stats)."""
     B, C, H, W = x.shape
-    n = float(B * H * W)
     if bn.training or bn.running_mean is None:
-        stats = torch.zeros(2, C, dtype=torch.float32, device=x.device)
-        _lib.check(lib.cotb200_col_stats(dt, B, H * W, C, x.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), st), "col_stats")
-        mean = stats[0] / n
-        var = (stats[1] / n - mean * mean).clamp_min_(0.0)
-        if bn.running_mean is not None and bn.track_running_stats:
-            with torch.no_grad():
-                bn.num_batches_tracked += 1
-                mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-                bn.running_mean.mul_(1 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)
-                bn.running_var.mul_(1 - mom).add_((var * (n / max(n - 1.0, 1.0))).to(bn.running_var.dtype), alpha=mom)
-        return mean, var, True
-    return bn.running_mean.float(), bn.running_var.float(), False
+        sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)
+        _lib.check(lib.cotb200_col_stats(dt, B, H * W, C, x.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), st), "col_stats")
+        return _bn_prepare(bn, weight, bias, C, float(B * H * W), sums, x.device, st), True
+    return _bn_prepare(bn, weight, bias, C, float(B * H * W), None, x.device, st), False
 
 
 class BNActFn(Function):
-    """y = act(BatchNorm2d(x) (+ res)) on channels_last tensors: col_stats + bn_apply forward, bn_bwd_sums + bn_bwd_apply
-    backward.  Replaces the nn.BatchNorm2d / nn.ReLU (/ residual add) modules of models/cotnet.py:45-46,53-54,61-62 and
-    :231-235,:249-262 -- ATen's channels_last batch-norm kernels are the largest single cost of the eager step."""
+    """y = act(BatchNorm2d(x) (+ res)) on channels_last tensors: col_stats + bn_finalize + bn_apply forward,
+    bn_bwd_sums + bn_bwd_apply backward.  Replaces the nn.BatchNorm2d / nn.ReLU (/ residual add) modules of
+    models/cotnet.py:45-46,53-54,61-62 and :231-235,:249-262 -- ATen's channels_last batch-norm kernels are the largest
+    single cost of the eager step."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, res, bn, relu):
@@ -59,42 +81,33 @@ class BNActFn(Function):
         B, C, H, W = x.shape
         lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.dtype_code(x)
         x = x.detach()
-        mean, var, batch = _bn_batch_stats(x, bn, lib, st, dt)
-        rstd = torch.rsqrt(var + bn.eps).contiguous()
-        scale = (weight.detach().float() * rstd).contiguous()
-        shift = (bias.detach().float() - mean * scale).contiguous()
+        ss, batch = _bn_batch_stats(x, bn, weight, bias, lib, st, dt)      # [4,C]: scale, shift, mean, rstd
         y = torch.empty_like(x, memory_format=torch.channels_last)
-        _lib.check(lib.cotb200_bn_apply(dt, B, H * W, C, x.data_ptr(), _lib.ptr(res), scale.data_ptr(), shift.data_ptr(),
+        _lib.check(lib.cotb200_bn_apply(dt, B, H * W, C, x.data_ptr(), _lib.ptr(res), ss[0].data_ptr(), ss[1].data_ptr(),
                                         1 if relu else 0, y.data_ptr(), st), "bn_apply")
-        ctx.save_for_backward(x, y if relu else None, scale, mean.contiguous(), rstd)
+        ctx.save_for_backward(x, y if relu else None, ss)
         ctx.cfg = (relu, batch, res is not None, weight.dtype, bias.dtype)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, scale, mean, rstd = ctx.saved_tensors
+        x, y, ss = ctx.saved_tensors
         relu, batch, has_res, wdt, bdt = ctx.cfg
         B, C, H, W = x.shape
-        n = float(B * H * W)
         lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.dtype_code(x)
         dy = dy.contiguous(memory_format=torch.channels_last)
         sums = None
         if batch or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)
-            _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), x.data_ptr(), _lib.ptr(y), mean.data_ptr(),
-                                               rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
+            _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), x.data_ptr(), _lib.ptr(y), ss[2].data_ptr(),
+                                               ss[3].data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
                        "bn_bwd_sums")
-        c1 = c2 = None
-        if batch:
-            c1, c2 = (sums[0] / n).contiguous(), (sums[1] / n).contiguous()
-        dx = torch.empty_like(x, memory_format=torch.channels_last) if ctx.needs_input_grad[0] else None
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
         dres = torch.empty_like(x, memory_format=torch.channels_last) if (has_res and ctx.needs_input_grad[3]) else None
-        if dx is not None or dres is not None:
-            if dx is None:
-                dx = torch.empty_like(x, memory_format=torch.channels_last)
-            _lib.check(lib.cotb200_bn_bwd_apply(dt, B, H * W, C, dy.data_ptr(), x.data_ptr(), _lib.ptr(y), scale.data_ptr(),
-                                                mean.data_ptr(), rstd.data_ptr(), _lib.ptr(c1), _lib.ptr(c2), 1 if relu else 0,
-                                                dx.data_ptr(), _lib.ptr(dres), st), "bn_bwd_apply")
+        _lib.check(lib.cotb200_bn_bwd_apply(dt, B, H * W, C, dy.data_ptr(), x.data_ptr(), _lib.ptr(y), ss[0].data_ptr(),
+                                            ss[2].data_ptr(), ss[3].data_ptr(), _lib.ptr(sums[0]) if batch else None,
+                                            _lib.ptr(sums[1]) if batch else None, 1.0 / float(B * H * W), 1 if relu else 0,
+                                            dx.data_ptr(), _lib.ptr(dres), st), "bn_bwd_apply")
         dgamma = sums[1].to(wdt) if ctx.needs_input_grad[1] else None
         dbeta = sums[0].to(bdt) if ctx.needs_input_grad[2] else None
         return dx, dgamma, dbeta, dres, None, None
@@ -118,10 +131,11 @@ class GroupNorm9Fn(Function):
         l = l.detach()
         stats = torch.zeros(2, B, wc, dtype=torch.float32, device=l.device)
         _lib.check(lib.cotb200_gn9_stats(dt, B, HW, wc, gc, l.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), st), "gn9_stats")
-        n = 9.0 * HW
-        mean = stats[0] / n
-        var = (stats[1] / n - mean * mean).clamp_min_(0.0)
-        rstd = torch.rsqrt(var + eps)
+        fin = torch.empty(4, B * wc, dtype=torch.float32, device=l.device)      # (rstd, -mean*rstd, mean, rstd)
+        _lib.check(lib.cotb200_bn_finalize(B * wc, stats[0].data_ptr(), stats[1].data_ptr(), None, None, None, None, 9.0 * HW,
+                                           float(eps), 0.0, 1, 0, fin[0].data_ptr(), fin[1].data_ptr(), fin[2].data_ptr(),
+                                           fin[3].data_ptr(), st), "bn_finalize")
+        mean, rstd = fin[2], fin[3]
         g32, b32 = _f32(gamma), _f32(beta)
         out = torch.empty_like(l, memory_format=torch.channels_last)
         _lib.check(lib.cotb200_gn9_apply(dt, B, HW, wc, gc, l.data_ptr(), mean.data_ptr(), rstd.data_ptr(), g32.data_ptr(),
@@ -163,11 +177,8 @@ class CotTailFn(Function):
         HW, n = H * W, float(B * H * W)
         lib, st, dt = _lib.load(), _lib.stream_ptr(u), _lib.dtype_code(u)
         u, k = u.detach(), k.detach()
-        mean, var, training = _bn_batch_stats(u, bn, lib, st, dt)
-        rstd = torch.rsqrt(var + bn.eps)
-        scale = (bn_weight.detach().float() * rstd).contiguous()
-        shift = (bn_bias.detach().float() - mean * scale).contiguous()
-        mean, rstd = mean.contiguous(), rstd.contiguous()
+        ss, training = _bn_batch_stats(u, bn, bn_weight, bn_bias, lib, st, dt)     # [4,C]: scale, shift, mean, rstd
+        scale, shift, mean, rstd = ss[0], ss[1], ss[2], ss[3]
         psum = torch.zeros(B, C, dtype=torch.float32, device=u.device)
         _lib.check(lib.cotb200_tail_pool(dt, B, HW, C, u.data_ptr(), k.data_ptr(), scale.data_ptr(), shift.data_ptr(),
                                          psum.data_ptr(), st), "tail_pool")
@@ -199,22 +210,22 @@ class CotTailFn(Function):
         _lib.check(lib.cotb200_tail_bwd_sums(dt, B, HW, C, dout.data_ptr(), u.data_ptr(), k.data_ptr(), scale.data_ptr(),
                                              shift.data_ptr(), S.data_ptr(), st), "tail_bwd_sums")
         grads = torch.autograd.grad(a, [p_leaf] + se_params, grad_outputs=S, allow_unused=True)
-        dpn = (grads[0] / HW).contiguous()
+        dpn = grads[0].contiguous()                      # d/d(pooled mean); the kernels apply the 1/HW (pscale)
         se_grads = [None if g is None else g for g in grads[1:]]
         sums = torch.zeros(2, C, dtype=torch.float32, device=u.device)
         need_param = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         if ctx.training or need_param:
             _lib.check(lib.cotb200_tail_bwd_dz_sums(dt, B, HW, C, dout.data_ptr(), u.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                                                    mean.data_ptr(), rstd.data_ptr(), a_c.data_ptr(), dpn.data_ptr(),
+                                                    mean.data_ptr(), rstd.data_ptr(), a_c.data_ptr(), dpn.data_ptr(), 1.0 / HW,
                                                     sums[0].data_ptr(), sums[1].data_ptr(), st), "tail_bwd_dz_sums")
         c1 = c2 = None
         if ctx.training:
-            c1, c2 = (sums[0] / n).contiguous(), (sums[1] / n).contiguous()
+            c1, c2 = sums[0], sums[1]
         du = torch.empty_like(u, memory_format=torch.channels_last)
         dk = torch.empty_like(u, memory_format=torch.channels_last)
         _lib.check(lib.cotb200_tail_bwd_apply(dt, B, HW, C, dout.data_ptr(), u.data_ptr(), scale.data_ptr(), shift.data_ptr(),
                                               mean.data_ptr(), rstd.data_ptr(), a_c.data_ptr(), dpn.data_ptr(), _lib.ptr(c1),
-                                              _lib.ptr(c2), du.data_ptr(), dk.data_ptr(), st), "tail_bwd_apply")
+                                              _lib.ptr(c2), 1.0 / n, 1.0 / HW, du.data_ptr(), dk.data_ptr(), st), "tail_bwd_apply")
         dgamma = sums[1].to(ctx.bn_dtypes[0]) if ctx.needs_input_grad[2] else None
         dbeta = sums[0].to(ctx.bn_dtypes[1]) if ctx.needs_input_grad[3] else None
         ctx.graph = None
@@ -321,25 +332,14 @@ def _rows2d(t):
 
 def _bn_from_sums(sums, n, bn, weight, bias):
     """(scale, shift, mean, rstd) from epilogue column sums; updates the running buffers like nn.BatchNorm2d."""
-    mean = sums[0] / n
-    var = (sums[1] / n - mean * mean).clamp_min_(0.0)
-    if bn.running_mean is not None and bn.track_running_stats:
-        with torch.no_grad():
-            bn.num_batches_tracked += 1
-            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-            bn.running_mean.mul_(1 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)
-            bn.running_var.mul_(1 - mom).add_((var * (n / max(n - 1.0, 1.0))).to(bn.running_var.dtype), alpha=mom)
-    rstd = torch.rsqrt(var + bn.eps).contiguous()
-    scale = (weight.detach().float() * rstd).contiguous()
-    shift = (bias.detach().float() - mean * scale).contiguous()
-    return scale, shift, mean.contiguous(), rstd
+    ss = _bn_prepare(bn, weight, bias, sums.shape[1], n, sums, sums.device, torch.cuda.current_stream(sums.device).cuda_stream)
+    return ss[0], ss[1], ss[2], ss[3]
 
 
 def _bn_eval_fold(bn, weight, bias):
-    rstd = torch.rsqrt(bn.running_var.float() + bn.eps).contiguous()
-    scale = (weight.detach().float() * rstd).contiguous()
-    mean = bn.running_mean.float().contiguous()
-    return scale, (bias.detach().float() - mean * scale).contiguous(), mean, rstd
+    ss = _bn_prepare(bn, weight, bias, weight.shape[0], 1.0, None, weight.device,
+                     torch.cuda.current_stream(weight.device).cuda_stream)
+    return ss[0], ss[1], ss[2], ss[3]
 
 
 class TcConv1x1Fn(Function):
@@ -399,12 +399,10 @@ class TcConv1x1Fn(Function):
             _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), mean.data_ptr(),
                                                rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
                        "bn_bwd_sums")
-            c1 = c2 = None
-            if batch:
-                c1, c2 = (sums[0] / M).contiguous(), (sums[1] / M).contiguous()
             dpre = torch.empty_like(dy, memory_format=torch.channels_last)
             _lib.check(lib.cotb200_bn_bwd_apply(dt, B, H * W, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
-                                                mean.data_ptr(), rstd.data_ptr(), _lib.ptr(c1), _lib.ptr(c2), 1 if relu else 0,
+                                                mean.data_ptr(), rstd.data_ptr(), _lib.ptr(sums[0]) if batch else None,
+                                                _lib.ptr(sums[1]) if batch else None, 1.0 / M, 1 if relu else 0,
                                                 dpre.data_ptr(), None, st), "bn_bwd_apply")
             dgamma, dbeta = sums[1].to(bndt), sums[0].to(bndt)
         else:
@@ -471,12 +469,10 @@ class TcConv3x3Fn(Function):
         _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), mean.data_ptr(),
                                            rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
                    "bn_bwd_sums")
-        c1 = c2 = None
-        if batch:
-            c1, c2 = (sums[0] / M).contiguous(), (sums[1] / M).contiguous()
         dpre = torch.empty_like(dy, memory_format=torch.channels_last)
         _lib.check(lib.cotb200_bn_bwd_apply(dt, B, H * W, C, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
-                                            mean.data_ptr(), rstd.data_ptr(), _lib.ptr(c1), _lib.ptr(c2), 1 if relu else 0,
+                                            mean.data_ptr(), rstd.data_ptr(), _lib.ptr(sums[0]) if batch else None,
+                                            _lib.ptr(sums[1]) if batch else None, 1.0 / M, 1 if relu else 0,
                                             dpre.data_ptr(), None, st), "bn_bwd_apply")
         dx = dw = None
         if ctx.needs_input_grad[0]:

@@ -118,11 +118,12 @@ int cotb200_tail_bwd_sums(int dtype, int B, int HW, int C, const void* dout, con
 /* dz = (a0*dout + dpn)*silu'(z); sum_dz[c] += sum dz, sum_dzx[c] += sum dz*xhat (BatchNorm backward reductions) */
 int cotb200_tail_bwd_dz_sums(int dtype, int B, int HW, int C, const void* dout, const void* u, const float* scale,
                              const float* shift, const float* mu, const float* rstd, const float* a, const float* dpn,
-                             float* sum_dz, float* sum_dzx, void* stream);
-/* du = scale*(dz - c1 - xhat*c2) (c1,c2 NULL in eval mode), dk = a1*dout + dpn */
+                             float pscale, float* sum_dz, float* sum_dzx, void* stream);
+/* du = scale*(dz - c1*inv_n - xhat*c2*inv_n) (c1,c2 = the raw sums above, NULL in eval mode), dk = a1*dout + dpn*pscale.
+ * dpn is the gradient w.r.t. the pooled descriptor [B,C]; pscale = 1/HW turns it into the per-pixel term. */
 int cotb200_tail_bwd_apply(int dtype, int B, int HW, int C, const void* dout, const void* u, const float* scale,
                            const float* shift, const float* mu, const float* rstd, const float* a, const float* dpn,
-                           const float* c1, const float* c2, void* du, void* dk, void* stream);
+                           const float* c1, const float* c2, float inv_n, float pscale, void* du, void* dk, void* stream);
 /* BatchNorm2d (+ReLU) (+residual add) on NHWC tensors: y = act(x*scale + shift (+ res)).  With cotb200_col_stats this
  * replaces nn.BatchNorm2d / nn.ReLU pairs of the block (models/cotnet.py:45-46,53-54,61-62) and of the enclosing
  * bottleneck (models/cotnet.py:231-235,:249-262) in 2 forward + 2 backward HBM passes.  relu: 0/1; res may be NULL. */
@@ -131,10 +132,17 @@ int cotb200_bn_apply(int dtype, int B, int HW, int C, const void* x, const void*
 /* dz = dy*[y>0] (relu) ; sum_dz[c] += sum dz ; sum_dzx[c] += sum dz*xhat      (y may be NULL when relu == 0) */
 int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y, const float* mu,
                         const float* rstd, int relu, float* sum_dz, float* sum_dzx, void* stream);
-/* dx = scale*(dz - c1 - xhat*c2) (c1,c2 NULL in eval mode) ; dres = dz when dres != NULL (gradient of the residual) */
+/* dx = scale*(dz - c1*inv_n - xhat*c2*inv_n) (c1,c2 = the raw sums of cotb200_bn_bwd_sums, NULL in eval mode) ;
+ * dres = dz when dres != NULL (gradient of the residual) */
 int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y, const float* scale,
-                         const float* mu, const float* rstd, const float* c1, const float* c2, int relu, void* dx,
-                         void* dres, void* stream);
+                         const float* mu, const float* rstd, const float* c1, const float* c2, float inv_n, int relu,
+                         void* dx, void* dres, void* stream);
+/* One launch for the BatchNorm bookkeeping: from the column sums of cotb200_col_stats (or a GEMM epilogue) compute
+ * scale = gamma*rstd, shift = beta - mean*scale, mean, rstd, and update running_mean / running_var like nn.BatchNorm2d
+ * (momentum, unbiased variance).  use_batch = 0: eval mode, statistics read from the running buffers. */
+int cotb200_bn_finalize(int C, const float* sum, const float* sq, const float* weight, const float* bias,
+                        float* running_mean, float* running_var, float n, float eps, float momentum, int use_batch,
+                        int update_running, float* scale, float* shift, float* mean, float* rstd, void* stream);
 
 /* GroupNorm(num_groups = wc, channels = 9*wc) of the attention logits (models/cotnet.py:56): group g = the 9 taps of
  * weight channel g.  The logits l / dl are always in the reference channel order j = g*9 + t; `gc` is the storage order

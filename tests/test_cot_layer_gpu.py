@@ -147,7 +147,9 @@ def test_tc_training_backend_vs_oracle(dim, H):
     xr = x64.clone().requires_grad_(True)
     want = cot_ref.cot_layer(xr, {k: v.clone() for k, v in sd64.items()}, training=True)
     want.sum().backward()
-    scale = max(1.0, want.abs().max().item())
-    assert (out.double().cpu() - want.detach()).abs().max().item() <= 0.1 * scale
-    gs = max(1.0, xr.grad.abs().max().item())
-    assert (x.grad.double().cpu() - xr.grad).abs().max().item() <= 0.15 * gs
+    # bf16 activations between the stages: ReLU masks come from rounded pre-activations, a few near-zero elements flip and
+    # dominate max-abs; judge the Frobenius error (see tests/test_tc_gemm_gpu.py::_rel_l2)
+    rel_o = ((out.double().cpu() - want.detach()).norm() / want.detach().norm()).item()
+    rel_g = ((x.grad.double().cpu() - xr.grad).norm() / xr.grad.norm()).item()
+    assert rel_o <= 3e-2, "forward relative L2 %.3e" % rel_o
+    assert rel_g <= 8e-2, "dX relative L2 %.3e" % rel_g

