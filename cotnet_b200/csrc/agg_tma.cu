@@ -225,14 +225,16 @@ agg3_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
   }
 }
 
-// dW[p, (g0+i), t] = sum_{8 sharers j} x[p + off_t][cb_j + i] * dY[p][cb_j + i]          (TAP layout output)
-// Warp lane = gvl + GQW*j + 8*GQW*slot (slot = pixel inside the warp); butterfly transpose-reduce over the j lanes.
-template <typename T, int GQW>
+// dW[p, (g0+i), t] = sum_{sharers j} x[p + off_t][cb_j + i] * dY[p][cb_j + i]          (TAP layout output)
+// Thread = (pixel, weight packet) and loops over the `rep` sharers itself: 72 fp32 accumulators in registers, no
+// cross-lane reduction at all.  Lanes are consecutive pixels; their 16-byte reads hit different 128-byte rows, which the
+// TMA 128B swizzle spreads over all banks (chunk ^ row%8), so the all-sharers mapping that was L1-bound on global
+// memory (first generation) is conflict-free here.
+template <typename T>
 __global__ void __launch_bounds__(512, 1)
 agg3_dw_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapG, T* __restrict__ dw,
                    const AggTmaP p) {
   constexpr int VEC = 16 / (int)sizeof(T);
-  constexpr int PXW = 32 / (8 * GQW);
   extern __shared__ __align__(1024) uint8_t at_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t s_full[AT_MAX_STAGES], s_empty[AT_MAX_STAGES];
@@ -248,70 +250,52 @@ agg3_dw_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
   if (warp == 0) {
     at_producer<T>(mapX, mapG, p, smem, s_full, s_empty, lane);
   } else {
-    const int cwarp = warp - 1;
-    const int gvl = lane % GQW, j = (lane / GQW) % 8, slot = lane / (8 * GQW);
-    const int gvgroups = p.GQ / GQW;
-    const int pxgroups = (p.TH * p.W + PXW - 1) / PXW;
-    const int witems = pxgroups * gvgroups;
+    const int ct = threadIdx.x - 32, nct = ncw * 32;
+    const int items = p.TH * p.W * p.GQ;
     const int Wp = p.W + 2;
+    const int rep = p.Cf / p.wcf;                      // sharers per weight channel
+    const uint32_t smem_base = at_smem_u32(smem);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int s = it % p.stages;
       const uint32_t ph = (it / p.stages) & 1;
       at_mbar_wait(at_smem_u32(&s_full[s]), ph);
       const int n = tile / p.bands, h0 = (tile - n * p.bands) * p.TH;
-      const uint32_t xs = at_smem_u32(smem) + (uint32_t)(s * p.stage_bytes);
+      const uint32_t xs = smem_base + (uint32_t)(s * p.stage_bytes);
       const uint32_t gs = xs + (uint32_t)(p.slabs * p.slab_bytes);
-      for (int wi = cwarp; wi < witems; wi += ncw) {
-        const int gvg = wi % gvgroups, pg = wi / gvgroups;
-        const int px = pg * PXW + slot;
+      for (int item = ct; item < items; item += nct) {
+        const int px = item % (p.TH * p.W), gv = item / (p.TH * p.W);      // lanes = consecutive pixels
         const int hl = px / p.W, wl = px - hl * p.W;
-        const bool active = px < p.TH * p.W && h0 + hl < p.H;
-        const int g0 = (gvg * GQW + gvl) * VEC;
-        const int cb = ((g0 / p.wcf) * p.Cf + g0 % p.wcf + j * p.wcf) * (int)sizeof(T);      // byte offset of this lane's packet
-        const int slab = cb >> 7, chunk = (cb >> 4) & 7;
-        float part[9][VEC];
+        if (h0 + hl >= p.H) continue;
+        const int g0 = gv * VEC;
+        const int cb0 = ((g0 / p.wcf) * p.Cf + g0 % p.wcf) * (int)sizeof(T);   // byte offset of sharer 0's packet
+        const int cstep = p.wcf * (int)sizeof(T);
+        const int rc = (hl + 1) * Wp + wl + 1;
+        float acc[9][VEC];
 #pragma unroll
         for (int t = 0; t < 9; ++t)
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) part[t][i] = 0.f;
-        if (active) {
-          const Pack<T, VEC> gv = lds_pack<T, VEC>(gs + (uint32_t)(slab * p.b_slab_bytes + px * 128 + ((chunk ^ (px & 7)) << 4)));
+          for (int i = 0; i < VEC; ++i) acc[t][i] = 0.f;
+        for (int j = 0; j < rep; ++j) {
+          const int cb = cb0 + j * cstep;
+          const int slab = cb >> 7, chunk = (cb >> 4) & 7;
+          const Pack<T, VEC> gvv = lds_pack<T, VEC>(gs + (uint32_t)(slab * p.b_slab_bytes + px * 128 + ((chunk ^ (px & 7)) << 4)));
+          const uint32_t xb = xs + (uint32_t)(slab * p.slab_bytes);
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            const int r = (hl + t / 3) * Wp + (wl + t % 3);
-            const Pack<T, VEC> xv = lds_pack<T, VEC>(xs + (uint32_t)(slab * p.slab_bytes + r * 128 + ((chunk ^ (r & 7)) << 4)));
+            const int r = rc + (t / 3 - 1) * Wp + (t % 3 - 1);
+            const Pack<T, VEC> xv = lds_pack<T, VEC>(xb + (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4)));
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) part[t][i] = MixT<T>::fma(xv.v[i], gv.v[i], 0.f);
+            for (int i = 0; i < VEC; ++i) acc[t][i] = MixT<T>::fma(xv.v[i], gvv.v[i], acc[t][i]);
           }
         }
+        T* wr = dw + n * p.y_sn + (long long)((h0 + hl) * p.W + wl) * p.y_sp + (g0 / p.gc) * 9 * p.gc + g0 % p.gc;
 #pragma unroll
-        for (int off = 4; off >= 1; off >>= 1) {
-          const bool upper = (j & off) != 0;
-#pragma unroll
-          for (int t = 0; t < off; ++t)
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-              const float send = upper ? part[t][i] : part[t + off][i];
-              const float keep = upper ? part[t + off][i] : part[t][i];
-              part[t][i] = keep + __shfl_xor_sync(0xffffffffu, send, off * GQW);
-            }
-        }
-#pragma unroll
-        for (int off = 4; off >= 1; off >>= 1)
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) part[8][i] += __shfl_xor_sync(0xffffffffu, part[8][i], off * GQW);
-        if (active) {
-          T* wr = dw + n * p.y_sn + (long long)((h0 + hl) * p.W + wl) * p.y_sp + (g0 / p.gc) * 9 * p.gc + g0 % p.gc;
+        for (int t = 0; t < 9; ++t) {
           Pack<T, VEC> o;
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) o.v[i] = Elem<T>::from(part[0][i]);
-          st_pack<T, VEC>(wr + j * p.gc, o);                       // lane j owns tap j
-          if (j == 0) {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) o.v[i] = Elem<T>::from(part[8][i]);
-            st_pack<T, VEC>(wr + 8 * p.gc, o);
-          }
+          for (int i = 0; i < VEC; ++i) o.v[i] = Elem<T>::from(acc[t][i]);
+          st_pack<T, VEC>(wr + t * p.gc, o);
         }
       }
       __syncwarp();
@@ -400,13 +384,7 @@ static int agg_tma_launch(int mode, const Nhwc2Args& a, const T* A, const T* Bp,
     p.jbox = p.J / p.jboxes;
     if ((p.jbox * (int)sizeof(T)) % 16) return 0;
     p.GQ = a.wc / VEC;
-    int gqw = 1;
-    if (mode == 2) {
-      if (a.C / a.wc != 8) return 0;                      // butterfly over the 8 sharers (share_planes = 8)
-      gqw = p.GQ >= 4 ? 4 : p.GQ;
-      if (p.GQ % gqw || (gqw != 1 && gqw != 2 && gqw != 4)) return 0;
-      if (a.fold > 1 && wcf % (gqw * VEC)) return 0;
-    }
+
     // output strides: y (fwd), dx (dX: same layout as x), dw (dW: same layout as w)
     const long long o_sn = mode == 0 ? a.y_sn : (mode == 1 ? a.x_sn : a.w_sn);
     const long long o_sp = mode == 0 ? a.y_sp : (mode == 1 ? a.x_sp : a.w_sp);
@@ -453,11 +431,11 @@ static int agg_tma_launch(int mode, const Nhwc2Args& a, const T* A, const T* Bp,
       if (!at_make_map_w<T>(&mb, Bp, a.N, a.H, a.W, p.jbox, p.jboxes, a.w_sp, a.w_sn, a.W + 2 * p.whalo, p.TH + 2 * p.whalo)) return 0;
     }
     int work_warps;
-    if (mode == 2) work_warps = ((p.TH * a.W + (32 / (8 * gqw)) - 1) / (32 / (8 * gqw))) * (p.GQ / gqw);
+    if (mode == 2) work_warps = (p.TH * a.W * p.GQ + 31) / 32;
     else work_warps = (p.TH * a.W * CQ + 31) / 32;
     int cw = work_warps > 28 ? 28 : (work_warps < 4 ? 4 : work_warps);
     if (mode != 2 && (long long)p.TH * a.W * CQ > 2LL * cw * 32) return 0;
-    if (mode == 2 && cw > 15) cw = 15;                 // the butterfly holds 72 partial sums per thread: 512 threads x <=128 regs
+    if (mode == 2 && cw > 15) cw = 15;                 // 72 accumulators per thread: 512 threads x <= 128 registers
     const int threads = (cw + 1) * 32;
     const int smem = p.stages * p.stage_bytes + 1024;
     int grid = num_sms();
@@ -471,15 +449,9 @@ static int agg_tma_launch(int mode, const Nhwc2Args& a, const T* A, const T* Bp,
     } else if (mode == 1) {
       AT_CFG(1, (agg3_fwd_tma_kernel<T, 1>));
       if (e == cudaSuccess) { COTB200_PROF_B("agg3_dx_tma", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T)); agg3_fwd_tma_kernel<T, 1><<<grid, threads, smem, st>>>(ma, mb, out, p); }
-    } else if (gqw == 1) {
-      AT_CFG(2, (agg3_dw_tma_kernel<T, 1>));
-      if (e == cudaSuccess) { COTB200_PROF_B("agg3_dw_tma", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T)); agg3_dw_tma_kernel<T, 1><<<grid, threads, smem, st>>>(ma, mb, out, p); }
-    } else if (gqw == 2) {
-      AT_CFG(3, (agg3_dw_tma_kernel<T, 2>));
-      if (e == cudaSuccess) { COTB200_PROF_B("agg3_dw_tma", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T)); agg3_dw_tma_kernel<T, 2><<<grid, threads, smem, st>>>(ma, mb, out, p); }
     } else {
-      AT_CFG(4, (agg3_dw_tma_kernel<T, 4>));
-      if (e == cudaSuccess) { COTB200_PROF_B("agg3_dw_tma", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T)); agg3_dw_tma_kernel<T, 4><<<grid, threads, smem, st>>>(ma, mb, out, p); }
+      AT_CFG(2, (agg3_dw_tma_kernel<T>));
+      if (e == cudaSuccess) { COTB200_PROF_B("agg3_dw_tma", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T)); agg3_dw_tma_kernel<T><<<grid, threads, smem, st>>>(ma, mb, out, p); }
     }
 #undef AT_CFG
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(agg tma): %s", cudaGetErrorString(e)); *rc = (int)e; return 1; }

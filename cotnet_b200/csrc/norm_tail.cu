@@ -61,6 +61,7 @@ col_stats_kernel(const T* __restrict__ x, float* __restrict__ sum, float* __rest
   for (int i = 0; i < VEC; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
   if (active) {
     const T* xp = x + ((long long)b * g.HW) * g.ld + tx * VEC;
+#pragma unroll 4
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> v = ld_pack<T, VEC>(xp + (long long)r * g.ld);
 #pragma unroll
@@ -89,6 +90,7 @@ tail_pool_kernel(const T* __restrict__ u, const T* __restrict__ k, const float* 
   for (int i = 0; i < VEC; ++i) { acc[0][i] = 0.f; sc[i] = active ? scale[tx * VEC + i] : 0.f; sh[i] = active ? shift[tx * VEC + i] : 0.f; }
   if (active) {
     const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+#pragma unroll 4
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
       const Pack<T, VEC> kv = ld_pack<T, VEC>(k + base + (long long)r * g.C);
@@ -119,6 +121,7 @@ tail_combine_kernel(const T* __restrict__ u, const T* __restrict__ k, const floa
     a0[i] = a[((long long)b * g.C + c) * 2]; a1[i] = a[((long long)b * g.C + c) * 2 + 1];
   }
   const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+#pragma unroll 2
   for (int r = r0 + ty; r < r1; r += g.ry) {
     const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
     const Pack<T, VEC> kv = ld_pack<T, VEC>(k + base + (long long)r * g.C);
@@ -147,6 +150,7 @@ tail_bwd_sums_kernel(const T* __restrict__ dout, const T* __restrict__ u, const 
   for (int i = 0; i < VEC; ++i) { acc[0][i] = acc[1][i] = 0.f; sc[i] = active ? scale[tx * VEC + i] : 0.f; sh[i] = active ? shift[tx * VEC + i] : 0.f; }
   if (active) {
     const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+#pragma unroll 4
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> dv = ld_pack<T, VEC>(dout + base + (long long)r * g.C);
       const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
@@ -189,6 +193,7 @@ tail_bwd_dz_sums_kernel(const T* __restrict__ dout, const T* __restrict__ u, con
   }
   if (active) {
     const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+#pragma unroll 4
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> dv = ld_pack<T, VEC>(dout + base + (long long)r * g.C);
       const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
@@ -230,6 +235,7 @@ tail_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ u, const
     k1[i] = c1 ? c1[c] * inv_n : 0.f; k2[i] = c2 ? c2[c] * inv_n : 0.f;
   }
   const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+#pragma unroll 2
   for (int r = r0 + ty; r < r1; r += g.ry) {
     const Pack<T, VEC> dv = ld_pack<T, VEC>(dout + base + (long long)r * g.C);
     const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
@@ -263,6 +269,7 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float*
 #pragma unroll
   for (int i = 0; i < VEC; ++i) { sc[i] = scale[tx * VEC + i]; sh[i] = shift[tx * VEC + i]; }
   const long long base = ((long long)b * g.HW) * g.ld + tx * VEC;
+#pragma unroll 2
   for (int r = r0 + ty; r < r1; r += g.ry) {
     const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.ld);
     Pack<T, VEC> rv;
@@ -293,6 +300,7 @@ bn_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* _
   for (int i = 0; i < VEC; ++i) { acc[0][i] = acc[1][i] = 0.f; m[i] = active ? mu[tx * VEC + i] : 0.f; rs[i] = active ? rstd[tx * VEC + i] : 0.f; }
   if (active) {
     const long long base = ((long long)b * g.HW) * g.ld + tx * VEC;
+#pragma unroll 4
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> dv = ld_pack<T, VEC>(dy + base + (long long)r * g.ld);
       const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.ld);
@@ -330,6 +338,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
     sc[i] = scale[c]; m[i] = mu[c]; rs[i] = rstd[c]; k1[i] = c1 ? c1[c] * inv_n : 0.f; k2[i] = c2 ? c2[c] * inv_n : 0.f;
   }
   const long long base = ((long long)b * g.HW) * g.ld + tx * VEC;
+#pragma unroll 2
   for (int r = r0 + ty; r < r1; r += g.ry) {
     const Pack<T, VEC> dv = ld_pack<T, VEC>(dy + base + (long long)r * g.ld);
     const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.ld);
@@ -408,6 +417,7 @@ gn_stats_kernel(const T* __restrict__ l, float* __restrict__ gsum, float* __rest
   for (int i = 0; i < VEC; ++i) { acc[0][i] = acc[1][i] = 0.f; }
   if (active) {
     const T* lp = l + ((long long)b * g.HW) * g.C + tx * VEC;
+#pragma unroll 4
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> v = ld_pack<T, VEC>(lp + (long long)r * g.C);
 #pragma unroll
@@ -443,6 +453,7 @@ gn_apply_kernel(const T* __restrict__ l, const float* __restrict__ mean, const f
     Bc[i] = beta[j] - mn * A[i];
   }
   const long long base = ((long long)b * g.HW) * g.C;
+#pragma unroll 2
   for (int r = r0 + ty; r < r1; r += g.ry) {
     const T* lr = l + base + (long long)r * g.C;
     Pack<T, VEC> o;
@@ -480,6 +491,7 @@ gn_bwd_sums_kernel(const T* __restrict__ dg, const T* __restrict__ l, const floa
   }
   if (active) {
     const long long base = ((long long)b * g.HW) * g.C;
+#pragma unroll 4
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const T* dr = dg + base + (long long)r * g.C;
       const Pack<T, VEC> lv = ld_pack<T, VEC>(l + base + (long long)r * g.C + tx * VEC);
@@ -530,6 +542,7 @@ gn_bwd_apply_kernel(const T* __restrict__ dg, const T* __restrict__ l, const flo
     k1[i] = s1[(long long)b * wc + gi] * inv_n; k2[i] = s2[(long long)b * wc + gi] * inv_n;
   }
   const long long base = ((long long)b * g.HW) * g.C;
+#pragma unroll 2
   for (int r = r0 + ty; r < r1; r += g.ry) {
     const T* dr = dg + base + (long long)r * g.C;
     const Pack<T, VEC> lv = ld_pack<T, VEC>(l + base + (long long)r * g.C + tx * VEC);

@@ -157,15 +157,18 @@ __device__ __forceinline__ void tc_tile_origin(const TcParams& p, int tile_m, in
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
-               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const TcParams p) {
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2,
+               const __grid_constant__ CUtensorMap mapD, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int a_bytes = TC_BM * TC_BK * 2;             // 16 KB
   const int b_bytes = p.bn * TC_BK * 2;
   const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
+  uint8_t* out_tile = smem + (size_t)p.stages * stage_bytes;      // [bn/64 slabs][128 rows][128 B], 128B-swizzled
   __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_tfull[2], s_tempty[2];
   __shared__ uint32_t s_tmem;
   __shared__ float s_sum[256], s_sq[256];
+  __shared__ __align__(16) float s_scale[256], s_shift[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.mode == 0 ? p.kb1 + p.kb2 : 9 * p.kc;
@@ -256,10 +259,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     }
   } else {
     // ===================== epilogue (4 warps, TMEM lane quadrant = warp % 4) =====================
+    // TMEM -> registers -> (scale/shift/ReLU, bf16) -> 128B-swizzled smem tile -> ONE TMA store per 64-column slab.
+    // (The first version stored 16 B per thread straight to global: rows are ldd*2 bytes apart, so every warp-wide store
+    //  touched 32 lines and the epilogue, not HBM, set the pace -- profiles/r01_tma_tc_ncu_v2.md.)
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
+    const int et = threadIdx.x - 64;                     // 0..127 among the epilogue threads
     const bool stats = p.col_sum != nullptr;
-    int ti = 0;
+    const uint32_t out_base = smem_u32(out_tile);
+    const int nslab = (p.bn + 63) / 64;
+    int ti = 0, last_n0 = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int tile_m = tile % p.m_tiles, n0 = (tile / p.m_tiles) * p.bn;
       int b0, h0, rows_valid; long long m0;
@@ -267,10 +276,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       const int acc = ti & 1;
       const uint32_t use = (uint32_t)(ti >> 1);
       const bool row_ok = r < rows_valid && (m0 + r) < p.M;
+      if (n0 != last_n0) {                               // per-column epilogue constants of this N tile -> smem
+        for (int j = et; j < p.bn; j += 128) {
+          const bool in = n0 + j < p.N;
+          s_scale[j] = (p.scale && in) ? __ldg(p.scale + n0 + j) : 1.f;
+          s_shift[j] = (p.shift && in) ? __ldg(p.shift + n0 + j) : 0.f;
+        }
+        last_n0 = n0;
+      }
+      // the previous tile's TMA store must have finished READING the smem tile before it is overwritten
+      if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(smem_u32(&s_tfull[acc]), use & 1);
       __syncwarp();
       tc_fence_after();
-      __nv_bfloat16* drow = p.D + (m0 + r) * p.ldd + n0;
       for (int c = 0; c * 32 < p.bn; ++c) {
         uint32_t raw[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn + c * 32), raw);
@@ -286,24 +305,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
           atomicAdd(&s_sum[c * 32 + lane], cs);
           atomicAdd(&s_sq[c * 32 + lane], cq);
         }
-        if (row_ok) {
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            const int nb = n0 + c * 32 + j8 * 8;
-            if (nb < p.N && c * 32 + j8 * 8 < p.bn) {
-              uint32_t pk[4];
+        for (int j8 = 0; j8 < 4; ++j8) {
+          const int col = c * 32 + j8 * 8;               // column inside the N tile
+          if (col < p.bn) {
+            const float4 sc0 = *reinterpret_cast<const float4*>(&s_scale[col]), sc1 = *reinterpret_cast<const float4*>(&s_scale[col + 4]);
+            const float4 sh0 = *reinterpret_cast<const float4*>(&s_shift[col]), sh1 = *reinterpret_cast<const float4*>(&s_shift[col + 4]);
+            const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+            const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+            uint32_t pk[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float lo = v[j8 * 8 + 2 * e], hi = v[j8 * 8 + 2 * e + 1];
-                const int n = nb + 2 * e;
-                if (p.scale) { lo *= __ldg(p.scale + n); hi *= __ldg(p.scale + n + 1); }
-                if (p.shift) { lo += __ldg(p.shift + n); hi += __ldg(p.shift + n + 1); }
-                if (p.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-                pk[e] = *reinterpret_cast<uint32_t*>(&h2);
-              }
-              *reinterpret_cast<uint4*>(drow + c * 32 + j8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            for (int e = 0; e < 4; ++e) {
+              float lo = fmaf(v[j8 * 8 + 2 * e], scv[2 * e], shv[2 * e]);
+              float hi = fmaf(v[j8 * 8 + 2 * e + 1], scv[2 * e + 1], shv[2 * e + 1]);
+              if (p.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
             }
+            const int slab = col >> 6, chunk = (col & 63) >> 3;
+            const uint32_t dst = out_base + (uint32_t)(slab * (TC_BM * 128) + r * 128 + ((chunk ^ (r & 7)) << 4));
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
           }
         }
       }
@@ -311,9 +332,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tempty[acc])) : "memory");
+      // make the generic-proxy smem writes visible to the async proxy, then one thread issues the bulk tensor stores
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        for (int sl = 0; sl < nslab; ++sl) {
+          if (n0 + sl * 64 < p.N)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(&mapD), "r"(out_base + (uint32_t)(sl * (TC_BM * 128))), "r"(n0 + sl * 64), "r"((int)m0) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
       if (stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");    // the 4 epilogue warps only
-        const int t = threadIdx.x - 64;
+        const int t = et;
         for (int j = t; j < p.bn; j += 128) {
           if (n0 + j < p.N) {
             atomicAdd(p.col_sum + n0 + j, s_sum[j]);
@@ -321,9 +352,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
           }
           s_sum[j] = 0.f; s_sq[j] = 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all stores complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -384,23 +415,28 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, 
 
 static int tc_launch(const CUtensorMap& a1, const CUtensorMap& b1, const CUtensorMap& a2, const CUtensorMap& b2,
                      TcParams p, int m_tiles, cudaStream_t st, const char* what, double alg_bytes) {
+  // output tile staged in smem for the TMA store: one 128-row x 128-byte slab per 64 output columns
+  CUtensorMap dmap;
+  int rcd = make_map_2d(&dmap, p.D, p.M, p.N, p.ldd, p.rows_per_tile);
+  if (rcd) return rcd;
+  const int out_bytes = ((p.bn + 63) / 64) * TC_BM * 128;
   const int a_bytes = TC_BM * TC_BK * 2, b_bytes = p.bn * TC_BK * 2;
   const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
   p.m_tiles = m_tiles;
   p.stages = TC_STAGES;
-  while (p.stages > 2 && p.stages * stage_bytes > 96 * 1024) --p.stages;     // two CTAs per SM
-  const int smem = p.stages * stage_bytes + 1024;
+  while (p.stages > 2 && p.stages * stage_bytes + out_bytes > 104 * 1024) --p.stages;     // two CTAs per SM when possible
+  const int smem = p.stages * stage_bytes + out_bytes + 1024;
   static int configured = 0;
   if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    configured = 200 * 1024;
+    configured = 220 * 1024;
   }
   const int total = m_tiles * ((p.N + p.bn - 1) / p.bn);
   int grid = 2 * num_sms();
   if (grid > total) grid = total;
   COTB200_PROF_B(what, alg_bytes);
-  tc_gemm_kernel<<<grid, TC_THREADS, smem, st>>>(a1, b1, a2, b2, p);
+  tc_gemm_kernel<<<grid, TC_THREADS, smem, st>>>(a1, b1, a2, b2, dmap, p);
   return check_launch(what);
 }
 
