@@ -58,6 +58,8 @@ SYMBOLS = {
     "cotb200_gn9_apply": (ctypes.c_int, [ctypes.c_int] * 5 + [_VP] * 7),
     "cotb200_gn9_bwd_sums": (ctypes.c_int, [ctypes.c_int] * 5 + [_VP] * 10),
     "cotb200_gn9_bwd_apply": (ctypes.c_int, [ctypes.c_int] * 5 + [_VP] * 9),
+    "cotb200_pool3s2_fwd": (ctypes.c_int, [ctypes.c_int] * 6 + [_VP] * 4),
+    "cotb200_pool3s2_bwd": (ctypes.c_int, [ctypes.c_int] * 6 + [_VP] * 4),
     "cotb200_gemm_bf16": (ctypes.c_int, [ctypes.c_int] * 3 + [_VP, ctypes.c_longlong, _VP, ctypes.c_longlong]
                           + [ctypes.c_int, _VP, ctypes.c_longlong, _VP, ctypes.c_longlong]
                           + [_VP, ctypes.c_longlong, _VP, _VP, ctypes.c_int, _VP, _VP, _VP]),

@@ -61,7 +61,7 @@ class Bottleneck(nn.Module):
         residual = x
         y = fused.bn_act(self.conv1(x).contiguous(memory_format=cl), self.bn1, relu=True)
         if self.avd is not None:
-            y = self.avd(y)
+            y = fused.avg_pool3x3s2(y)              # nn.AvgPool2d(3, 2, padding=1) on the fused NHWC kernel
         y = self.conv2(y.contiguous(memory_format=cl))
         if self.downsample is not None:
             residual = fused.bn_act(self.downsample[0](x).contiguous(memory_format=cl), self.downsample[1], relu=False)
@@ -108,7 +108,7 @@ class CoTResNet(nn.Module):
 
     def forward_features(self, x):
         if fused.supported(x):
-            x = self.maxpool(fused.bn_act(self.conv1(x).contiguous(memory_format=torch.channels_last), self.bn1, relu=True))
+            x = fused.max_pool3x3s2(fused.bn_act(self.conv1(x).contiguous(memory_format=torch.channels_last), self.bn1, relu=True))
         else:
             x = self.maxpool(self.act1(self.bn1(self.conv1(x))))
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))

@@ -441,10 +441,12 @@ static int tc_launch(const CUtensorMap& a1, const CUtensorMap& b1, const CUtenso
 }
 
 static int pick_bn(int N) {
-  // whole N when it fits one UMMA (<= 256), else the smallest equal split; always a multiple of 16
-  int parts = (N + 255) / 256;
-  int bn = (N + parts - 1) / parts;
-  return (bn + 15) & ~15;
+  // One N tile when N fits a single UMMA (<= 256): bn = N rounded up to 16, columns beyond N are clipped by the TMA store.
+  // Several N tiles: bn must be a multiple of 64 so that every 64-column store slab lies inside its own tile.
+  if (N <= 256) return (N + 15) & ~15;
+  const int parts = (N + 255) / 256;
+  const int bn = (((N + parts - 1) / parts) + 63) & ~63;
+  return bn > 256 ? 256 : bn;
 }
 
 }  // namespace cotb200

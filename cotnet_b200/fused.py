@@ -276,6 +276,42 @@ class AggTapFn(Function):
         return dv, dw, None, None
 
 
+class Pool3x3S2Fn(Function):
+    """nn.AvgPool2d(3, 2, padding=1) (mode 0, count_include_pad) / nn.MaxPool2d(3, 2, 1) (mode 1) on channels_last."""
+
+    @staticmethod
+    def forward(ctx, x, mode):
+        assert _is_cl(x)
+        B, C, H, W = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        x = x.detach()
+        y = torch.empty((B, C, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        idx = torch.empty((B, Ho, Wo, C), dtype=torch.uint8, device=x.device) if mode == 1 else None
+        _lib.check(_lib.load().cotb200_pool3s2_fwd(_lib.dtype_code(x), mode, B, H, W, C, x.data_ptr(), y.data_ptr(), _lib.ptr(idx),
+                                                   _lib.stream_ptr(x)), "pool3s2_fwd")
+        ctx.save_for_backward(idx)
+        ctx.cfg = (mode, B, C, H, W, x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        mode, B, C, H, W, dtype = ctx.cfg
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((B, C, H, W), dtype=dtype, device=dy.device, memory_format=torch.channels_last)
+        _lib.check(_lib.load().cotb200_pool3s2_bwd(_lib.dtype_code(dy), mode, B, H, W, C, dy.data_ptr(), _lib.ptr(idx), dx.data_ptr(),
+                                                   _lib.stream_ptr(dy)), "pool3s2_bwd")
+        return dx, None
+
+
+def avg_pool3x3s2(x):
+    return Pool3x3S2Fn.apply(x, 0)
+
+
+def max_pool3x3s2(x):
+    return Pool3x3S2Fn.apply(x, 1)
+
+
 def tap_chunk(wc, fold=1):
     """Chunk width of the tap-major weight order the fast kernels use, 0 when wc does not allow it."""
     return 8 if (wc // fold) % 8 == 0 else 0

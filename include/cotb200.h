@@ -157,6 +157,14 @@ int cotb200_gn9_bwd_sums(int dtype, int B, int HW, int wc, int gc, const void* d
 int cotb200_gn9_bwd_apply(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* mean,
                           const float* rstd, const float* gamma, const float* s1, const float* s2, void* dl, void* stream);
 
+/* 3x3 / stride 2 / pad 1 pooling on NHWC tensors x [N,H,W,C] -> y [N,Ho,Wo,C], Ho = (H-1)/2+1.
+ * mode 0: average with count_include_pad (nn.AvgPool2d(3, 2, padding=1), the `avd` of models/cotnet.py:199-202,237-238);
+ * mode 1: max (nn.MaxPool2d(3, 2, 1) of the trunk, models/resnet.py:555); idx [N,Ho,Wo,C] uint8 = winning tap, consumed
+ * by the backward (first maximum in scan order, like ATen).  Backward is a gather: no atomics. */
+int cotb200_pool3s2_fwd(int dtype, int mode, int N, int H, int W, int C, const void* x, void* y, void* idx, void* stream);
+int cotb200_pool3s2_bwd(int dtype, int mode, int N, int H, int W, int C, const void* dy, const void* idx, void* dx,
+                        void* stream);
+
 /* ---- dense contractions of the block on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operands) ----
  * bf16 operands, fp32 accumulation, bf16 output.  Row-major everywhere; "ld*" are row pitches in elements.
  *

@@ -173,3 +173,25 @@ def test_bn_act(dtype, tol, C, H, relu, res, training):
     if training:
         assert torch.allclose(bn.running_mean.double(), bn_r.running_mean, atol=2e-2 if dtype != torch.float32 else 1e-5)
         assert torch.allclose(bn.running_var.double(), bn_r.running_var, atol=2e-2 if dtype != torch.float32 else 1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,H,W", [(64, 56, 56), (128, 28, 28), (64, 112, 112), (24, 9, 7), (256, 14, 14)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_pool3x3s2(dtype, C, H, W, mode):
+    """Fused NHWC pooling vs nn.AvgPool2d(3,2,1) / nn.MaxPool2d(3,2,1): forward and backward (ties included: ReLU'd input)."""
+    from cotnet_b200 import fused
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    B = 3
+    x = _cl(torch.relu(torch.randn(B, C, H, W, generator=g, device="cuda")).to(dtype)).requires_grad_(True)
+    y = fused.avg_pool3x3s2(x) if mode == 0 else fused.max_pool3x3s2(x)
+    ref_mod = nn.AvgPool2d(3, 2, padding=1) if mode == 0 else nn.MaxPool2d(3, 2, 1)
+    xr = x.detach().float().requires_grad_(True)
+    yr = ref_mod(xr)
+    cot = _cl(torch.randn(yr.shape, generator=g, device="cuda").to(dtype))
+    (gx,) = torch.autograd.grad(y, x, cot)
+    (gxr,) = torch.autograd.grad(yr, xr, cot.float())
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert y.shape == yr.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert (y.float() - yr).abs().max().item() <= tol * max(1.0, yr.abs().max().item())
+    assert (gx.float() - gxr).abs().max().item() <= tol * max(1.0, gxr.abs().max().item())
