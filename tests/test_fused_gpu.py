@@ -186,11 +186,14 @@ def test_pool3x3s2(dtype, C, H, W, mode):
     x = _cl(torch.relu(torch.randn(B, C, H, W, generator=g, device="cuda")).to(dtype)).requires_grad_(True)
     y = fused.avg_pool3x3s2(x) if mode == 0 else fused.max_pool3x3s2(x)
     ref_mod = nn.AvgPool2d(3, 2, padding=1) if mode == 0 else nn.MaxPool2d(3, 2, 1)
-    xr = x.detach().float().requires_grad_(True)
+    # NCHW-contiguous reference on purpose: ATen's channels_last avg_pool2d BACKWARD kernel of this torch build
+    # (avg_pool2d_backward_out_cuda_frame_nhwc) disagrees with its own NCHW and CPU implementations by O(1)
+    # (tools/debug_pool.py, profiles/r01_notes.md); the NCHW path is the semantic definition.
+    xr = x.detach().float().contiguous().requires_grad_(True)
     yr = ref_mod(xr)
     cot = _cl(torch.randn(yr.shape, generator=g, device="cuda").to(dtype))
     (gx,) = torch.autograd.grad(y, x, cot)
-    (gxr,) = torch.autograd.grad(yr, xr, cot.float())
+    (gxr,) = torch.autograd.grad(yr, xr, cot.float().contiguous())
     tol = 1e-5 if dtype == torch.float32 else 2e-2
     assert y.shape == yr.shape and y.is_contiguous(memory_format=torch.channels_last)
     assert (y.float() - yr).abs().max().item() <= tol * max(1.0, yr.abs().max().item())
