@@ -47,8 +47,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fwd-only", action="store_true", help="diagnostic: time the forward pass only (not the headline)")
+    ap.add_argument("--dp", default="flat", choices=["flat", "ddp"],
+                    help="N>1: 'flat' = replicas + one flat-bucket NCCL all-reduce per step (graph-replayable); "
+                         "'ddp' = torch DistributedDataParallel (eager)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the whole fwd+bwd+SGD step from one CUDA graph (auto: on for a single GPU)")
+                    help="replay the whole fwd+bwd+SGD step from CUDA graphs (auto: on unless --dp ddp)")
     return ap.parse_args()
 
 
@@ -127,12 +130,53 @@ def ncu_traffic(kernel):
 
 
 # ----------------------------------------------------------------------------------------------- CPU baseline / reference arm
+def usable_cores():
+    """Host cores this process may actually run on: cpu_count capped by the affinity mask and the cgroup CPU quota
+    (a container that sees 128 CPUs but is throttled to a fraction of them collapses with 128 OpenMP threads)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def pick_cpu_threads(model, res):
+    """Thread count for the CPU arm: the fastest of {all usable cores, 1/2, 1/4, 16} on one bs2 forward of the model
+    (torchrun exports OMP_NUM_THREADS=1 and oversubscribed boxes get SLOWER with more threads, so neither the
+    environment nor cpu_count can be trusted).  Returns (threads, {threads: seconds})."""
+    top = usable_cores()
+    cands = sorted({c for c in (top, top // 2, top // 4, 16) if 1 <= c <= top}, reverse=True)
+    x = torch.randn(2, 3, res, res)
+    timing = {}
+    with torch.no_grad():
+        for c in cands:
+            torch.set_num_threads(c)
+            model(x)                                   # thread-pool spin-up
+            t0 = time.perf_counter()
+            model(x)
+            timing[c] = round(time.perf_counter() - t0, 3)
+    best = min(timing, key=timing.get)
+    torch.set_num_threads(best)
+    return best, timing
+
+
+CPU_THREADS = {"n": None, "timing": None}
+
+
 def cpu_step_fn(model_name, res, sample_batch, seed=0):
-    """One fwd+bwd+SGD step of the oracle's CPU restatement of the reference model (fp32, all host threads)."""
+    """One fwd+bwd+SGD step of the oracle's CPU restatement of the reference model (fp32, host threads chosen by
+    pick_cpu_threads)."""
     from oracle import cot_model_ref
     torch.manual_seed(seed)
-    torch.set_num_threads(os.cpu_count() or 1)
     m = cot_model_ref.build(model_name).train()
+    CPU_THREADS["n"], CPU_THREADS["timing"] = pick_cpu_threads(m, res)
     opt = torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9, nesterov=True, weight_decay=1e-4)
     x = torch.randn(sample_batch, 3, res, res)
     y = torch.randint(0, 1000, (sample_batch,))
@@ -142,7 +186,7 @@ def cpu_step_fn(model_name, res, sample_batch, seed=0):
         loss = torch.nn.functional.cross_entropy(m(x), y)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 
@@ -156,16 +200,18 @@ def run_cpu_baseline(model_name, res, sample_batch=8):
     for _ in range(n):
         step()
     dt = (time.perf_counter() - t0) / n
-    return {"value": sample_batch / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": sample_batch / dt, "unit": "images/s", "cores": CPU_THREADS["n"], "kind": "port",
             "sample": "oracle CPU restatement of %s (fp32, Unfold LocalConv), fwd+bwd+SGD on %d images %dx%d, "
-                      "1 warm-up + mean of %d" % (model_name, sample_batch, res, res, n)}
+                      "1 warm-up + mean of %d; %d threads (host reports %d CPUs, %d usable; bs2-forward seconds per "
+                      "thread count: %s)" % (model_name, sample_batch, res, res, n, CPU_THREADS["n"], os.cpu_count() or 1,
+                                             usable_cores(), CPU_THREADS["timing"])}
 
 
 def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample = 2
+    sample = 8
     step = cpu_step_fn(a.model, a.res, sample)
     for _ in range(a.warmup):
         step()
@@ -174,9 +220,11 @@ def main_reference(a):
         step()
     dt = time.perf_counter() - t0
     v = sample * a.steps / dt
-    cb = {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-          "sample": "oracle CPU restatement of the reference %s (fp32), fwd+bwd+SGD, %d images %dx%d per step"
-                    % (a.model, sample, a.res, a.res)}
+    cb = {"value": v, "unit": "images/s", "cores": CPU_THREADS["n"], "kind": "port",
+          "sample": "oracle CPU restatement of the reference %s (fp32), fwd+bwd+SGD, %d images %dx%d per step; %d threads "
+                    "(host reports %d CPUs, %d usable; bs2-forward seconds per thread count: %s)"
+                    % (a.model, sample, a.res, a.res, CPU_THREADS["n"], os.cpu_count() or 1, usable_cores(),
+                       CPU_THREADS["timing"])}
     print(json.dumps({
         "impl": "reference", "metric": "CoTNet-50 images/sec (fwd+bwd, 224^2)", "value": v, "unit": "images/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
@@ -212,7 +260,13 @@ def main_ours(a):
     except Exception:
         opt = torch.optim.SGD(params, lr=0.05, momentum=0.9, nesterov=True, weight_decay=1e-4, foreach=True)
     net = model
-    if world > 1:
+    flat = None
+    if world > 1 and a.dp == "flat":
+        # replicas + ONE flat gradient bucket all-reduced (mean) over NCCL/NVLink per step; no autograd hooks, so the
+        # step still replays from CUDA graphs (cotnet_b200/dist.py FlatGrads)
+        cdist.broadcast_module_(model, 0)
+        flat = cdist.FlatGrads(params)
+    elif world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
                                                         gradient_as_bucket_view=True)
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -227,13 +281,23 @@ def main_ours(a):
         x = ((u8.float() - mean) / std).contiguous(memory_format=torch.channels_last)
         return x, lab
 
-    def train_step(x, lab):
-        opt.zero_grad(set_to_none=True)
+    def fwd_bwd(x, lab):
+        if flat is not None:
+            flat.zero_()
+        else:
+            opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = net(x)
             loss = torch.nn.functional.cross_entropy(out.float(), lab)
         if not a.fwd_only:
             loss.backward()
+        return loss
+
+    def train_step(x, lab):
+        loss = fwd_bwd(x, lab)
+        if not a.fwd_only:
+            if flat is not None:
+                flat.all_reduce_mean_()
             opt.step()
         return loss
 
@@ -243,7 +307,7 @@ def main_ours(a):
     # ---- whole-step CUDA graph: the step is ~4000 small launches, replaying them from one graph removes the host
     #      launch overhead (Blackwell guide: "capture launch-bound inner loops in CUDA graphs").  Same kernels, same math.
     graph_info = {"cuda_graph": False}
-    use_graph = (a.graph == "on") or (a.graph == "auto" and world == 1 and not a.fwd_only)
+    use_graph = (a.graph == "on") or (a.graph == "auto" and (world == 1 or flat is not None) and not a.fwd_only)
     graphed = None
     if use_graph:
         try:
@@ -256,16 +320,26 @@ def main_ours(a):
             torch.cuda.synchronize()
             g_x, g_lab = x_res.clone(), lab_res.clone()
             cg = torch.cuda.CUDAGraph()
-            opt.zero_grad(set_to_none=True)
+            cg_opt = None
+            if flat is None:
+                opt.zero_grad(set_to_none=True)
             lc0 = _lib.launch_count()
             with torch.cuda.graph(cg):
-                with torch.autocast("cuda", dtype=torch.bfloat16):
-                    g_out = net(g_x)
-                    g_loss = torch.nn.functional.cross_entropy(g_out.float(), g_lab)
-                g_loss.backward()
-                opt.step()
-            graphed = (cg, g_x, g_lab, g_loss)
-            graph_info = {"cuda_graph": True, "libcotb200_kernels_per_replay": _lib.launch_count() - lc0}
+                g_loss = fwd_bwd(g_x, g_lab)
+                if flat is None:
+                    opt.step()
+            captured = _lib.launch_count() - lc0
+            if flat is not None:             # the all-reduce runs eagerly between the two graphs
+                if not flat.attached():
+                    raise RuntimeError("gradient views were detached from the flat bucket")
+                cg_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(cg_opt):
+                    opt.step()
+            graphed = (cg, g_x, g_lab, g_loss, cg_opt)
+            graph_info = {"cuda_graph": True, "libcotb200_kernels_per_replay": captured}
+            if flat is not None:
+                graph_info["data_parallel"] = "fwd+bwd graph -> NCCL all-reduce(mean) of one %.0f MB flat bucket -> optimizer graph" % (
+                    flat.flat.numel() * 4 / 1e6)
         except Exception as e:      # noqa: BLE001 -- never lose the bench line to a capture problem
             graph_info = {"cuda_graph": False, "cuda_graph_error": repr(e)[:300]}
             graphed = None
@@ -275,11 +349,14 @@ def main_ours(a):
         """one training step on device-resident (x, lab); returns the loss tensor"""
         if graphed is None:
             return train_step(x, lab)
-        cg, g_x, g_lab, g_loss = graphed
+        cg, g_x, g_lab, g_loss, cg_opt = graphed
         if x is not g_x:
             g_x.copy_(x, non_blocking=True)
             g_lab.copy_(lab, non_blocking=True)
         cg.replay()
+        if cg_opt is not None:
+            flat.all_reduce_mean_()
+            cg_opt.replay()
         return g_loss
 
     def timed(fn, steps):

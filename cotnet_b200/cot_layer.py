@@ -75,17 +75,22 @@ class CotLayer(nn.Module):
         B, C, H, W = x.shape
         ks2 = self.kernel_size * self.kernel_size
         cl = torch.channels_last
-        k = fused.bn_act(self.key_embed[0](x).contiguous(memory_format=cl), self.key_embed[1], relu=True)
-        e = fused.bn_act(self.embed[0](torch.cat([x, k], dim=1)).contiguous(memory_format=cl), self.embed[1], relu=True)
-        l = self.embed[3](e)
-        v = fused.bn_act(self.conv1x1[0](x).contiguous(memory_format=cl), self.conv1x1[1], relu=False)
+        # x has three consumers and k two: their gradients (two of them channel slices of the concat's) are summed by
+        # one kernel each (fused.fan_out) instead of autograd's pairwise strided adds
+        xk, xc, xv = fused.fan_out(x, 3)
+        k = fused.bn_act(self.key_embed[0](xk).contiguous(memory_format=cl), self.key_embed[1], relu=True)
+        kc, kt = fused.fan_out(k, 2)
+        e = fused.bn_act(self.embed[0](torch.cat([xc, kc], dim=1)).contiguous(memory_format=cl), self.embed[1], relu=True)
+        # embed.3 runs bias-free; its bias is added (and differentiated) inside the GroupNorm kernels
+        l = F.conv2d(e, self.embed[3].weight, None)
+        v = fused.bn_act(self.conv1x1[0](xv).contiguous(memory_format=cl), self.conv1x1[1], relu=False)
         if l.dtype != v.dtype:
             l = l.to(v.dtype)
         l = l.contiguous(memory_format=torch.channels_last)
         gc = fused.tap_chunk(C // 8)                                       # tap-major weight order for the fast kernels
-        w = fused.group_norm9(l, self.embed[4], gc)                        # fp32 statistics, storage dtype out
+        w = fused.group_norm9(l, self.embed[4], gc, self.embed[3].bias)    # fp32 statistics, storage dtype out
         u = fused.AggTapFn.apply(v.contiguous(memory_format=torch.channels_last), w, 1, gc)
-        return fused.cot_tail(u, k.contiguous(memory_format=torch.channels_last), self.bn, self.se)
+        return fused.cot_tail(u, kt.contiguous(memory_format=torch.channels_last), self.bn, self.se)
 
     # ---- inference path: every convolution of the block on the tcgen05 kernels, BatchNorms folded into epilogues ----
     def _tc_eval_ok(self, x):
@@ -209,17 +214,19 @@ class CoXtLayer(nn.Module):
         B, C, H, W = x.shape
         ks = self.kernel_size
         cl = torch.channels_last
-        k = fused.bn_act(self.key_embed[0](x).contiguous(memory_format=cl), self.key_embed[1], relu=True)
-        qk = torch.stack([x, k], dim=2).reshape(B, 2 * C, H, W).contiguous(memory_format=cl)
+        xk, xc, xv = fused.fan_out(x, 3)
+        k = fused.bn_act(self.key_embed[0](xk).contiguous(memory_format=cl), self.key_embed[1], relu=True)
+        kc, kt = fused.fan_out(k, 2)
+        qk = torch.stack([xc, kc], dim=2).reshape(B, 2 * C, H, W).contiguous(memory_format=cl)
         e = fused.bn_act(self.embed[0](qk).contiguous(memory_format=cl), self.embed[1], relu=True)
-        l = self.embed[3](e)
-        v = fused.bn_act(self.conv1x1[0](x).contiguous(memory_format=cl), self.conv1x1[1], relu=False)
+        l = F.conv2d(e, self.embed[3].weight, None, groups=self.embed[3].groups)
+        v = fused.bn_act(self.conv1x1[0](xv).contiguous(memory_format=cl), self.conv1x1[1], relu=False)
         if l.dtype != v.dtype:
             l = l.to(v.dtype)
         gc = fused.tap_chunk(C // 8, self.dw_group)
-        w = fused.group_norm9(l.contiguous(memory_format=torch.channels_last), self.embed[4], gc)
+        w = fused.group_norm9(l.contiguous(memory_format=torch.channels_last), self.embed[4], gc, self.embed[3].bias)
         u = fused.AggTapFn.apply(v.contiguous(memory_format=torch.channels_last), w, self.dw_group, gc)
-        return fused.cot_tail(u, k.contiguous(memory_format=torch.channels_last), self.bn, self.se)
+        return fused.cot_tail(u, kt.contiguous(memory_format=torch.channels_last), self.bn, self.se)
 
     def forward(self, x):
         B, C, H, W = x.shape

@@ -400,21 +400,22 @@ __device__ __forceinline__ int gn_j_of_pos(int pos, int gc) {
 // gsum[b,g] += sum over (9 taps x rows) of l ; gsq likewise
 template <typename T, int VEC>
 __global__ void __launch_bounds__(NT_THREADS)
-gn_stats_kernel(const T* __restrict__ l, float* __restrict__ gsum, float* __restrict__ gsq, RowsGeo g, int wc) {
+gn_stats_kernel(const T* __restrict__ l, const float* __restrict__ lbias, float* __restrict__ gsum, float* __restrict__ gsq,
+                RowsGeo g, int wc) {
   extern __shared__ float sm[];
   const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
   const bool active = tx < g.cq && ty < g.ry;
   const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
-  float acc[2][VEC];
+  float acc[2][VEC], lb[VEC];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) { acc[0][i] = acc[1][i] = 0.f; }
+  for (int i = 0; i < VEC; ++i) { acc[0][i] = acc[1][i] = 0.f; lb[i] = (active && lbias) ? lbias[tx * VEC + i] : 0.f; }
   if (active) {
     const T* lp = l + ((long long)b * g.HW) * g.C + tx * VEC;
 #pragma unroll 4
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> v = ld_pack<T, VEC>(lp + (long long)r * g.C);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { const float f = to_acc(v.v[i]); acc[0][i] += f; acc[1][i] = fmaf(f, f, acc[1][i]); }
+      for (int i = 0; i < VEC; ++i) { const float f = to_acc(v.v[i]) + lb[i]; acc[0][i] += f; acc[1][i] = fmaf(f, f, acc[1][i]); }
     }
   }
   cta_col_reduce<2, VEC>(acc, sm, g, tx, ty, active);
@@ -430,7 +431,7 @@ gn_stats_kernel(const T* __restrict__ l, float* __restrict__ gsum, float* __rest
 // store); the VEC inputs are gathered (stride 9 inside the pixel's 18*wc-byte row, L1 hits).
 template <typename T, int VEC>
 __global__ void __launch_bounds__(NT_THREADS)
-gn_apply_kernel(const T* __restrict__ l, const float* __restrict__ mean, const float* __restrict__ rstd,
+gn_apply_kernel(const T* __restrict__ l, const float* __restrict__ lbias, const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ out, RowsGeo g, int wc, int gc) {
   const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
   if (!(tx < g.cq && ty < g.ry)) return;
@@ -443,7 +444,7 @@ gn_apply_kernel(const T* __restrict__ l, const float* __restrict__ mean, const f
     jin[i] = j;
     const float rs = rstd[(long long)b * wc + gi], mn = mean[(long long)b * wc + gi];
     A[i] = rs * gamma[j];
-    Bc[i] = beta[j] - mn * A[i];
+    Bc[i] = beta[j] - (mn - (lbias ? lbias[j] : 0.f)) * A[i];
   }
   const long long base = ((long long)b * g.HW) * g.C;
   for (int r = r0 + ty; r < r1; r += g.ry) {
@@ -465,7 +466,7 @@ gn_apply_kernel(const T* __restrict__ l, const float* __restrict__ mean, const f
 // Thread = one packet of l in the reference order; dg gathered from its storage order.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(NT_THREADS)
-gn_bwd_sums_kernel(const T* __restrict__ dg, const T* __restrict__ l, const float* __restrict__ mean,
+gn_bwd_sums_kernel(const T* __restrict__ dg, const T* __restrict__ l, const float* __restrict__ lbias, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ s1,
                    float* __restrict__ s2, float* __restrict__ dgamma, float* __restrict__ dbeta, RowsGeo g, int wc, int gc) {
   extern __shared__ float sm[];
@@ -479,7 +480,8 @@ gn_bwd_sums_kernel(const T* __restrict__ dg, const T* __restrict__ l, const floa
     acc[0][i] = acc[1][i] = 0.f;
     const int j = tx * VEC + i, gi = active ? j / 9 : 0;
     pos[i] = active ? gn_pos(j, gc) : 0;
-    mn[i] = active ? mean[(long long)b * wc + gi] : 0.f; rs[i] = active ? rstd[(long long)b * wc + gi] : 0.f;
+    mn[i] = active ? mean[(long long)b * wc + gi] - (lbias ? lbias[j] : 0.f) : 0.f;     // (l + bias - mean) = l - mn
+    rs[i] = active ? rstd[(long long)b * wc + gi] : 0.f;
   }
   if (active) {
     const long long base = ((long long)b * g.HW) * g.C;
@@ -513,39 +515,52 @@ gn_bwd_sums_kernel(const T* __restrict__ dg, const T* __restrict__ l, const floa
   }
 }
 
-// dl = rstd * ( dg*gamma - s1/n - lhat * s2/n ),  n = 9*HW
-template <typename T, int VEC>
+// dl = rstd * ( dg*gamma - s1/n - lhat * s2/n ),  n = 9*HW ;  DB: dlbias[j] += sum_rows dl (the bias gradient of the
+// embed.3 convolution, models/cotnet.py:55, when the bias add is folded into these kernels)
+template <typename T, int VEC, bool DB>
 __global__ void __launch_bounds__(NT_THREADS)
-gn_bwd_apply_kernel(const T* __restrict__ dg, const T* __restrict__ l, const float* __restrict__ mean,
-                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ s1,
-                    const float* __restrict__ s2, T* __restrict__ dl, RowsGeo g, int wc, int gc) {
+gn_bwd_apply_kernel(const T* __restrict__ dg, const T* __restrict__ l, const float* __restrict__ lbias,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                    const float* __restrict__ s1, const float* __restrict__ s2, T* __restrict__ dl,
+                    float* __restrict__ dlbias, RowsGeo g, int wc, int gc) {
+  extern __shared__ float sm[];
   const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
-  if (!(tx < g.cq && ty < g.ry)) return;
+  const bool active = tx < g.cq && ty < g.ry;
+  if (!DB && !active) return;
   const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
   const float inv_n = 1.f / (9.f * (float)g.HW);
-  float mn[VEC], rs[VEC], ga[VEC], k1[VEC], k2[VEC];
+  float mn[VEC], rs[VEC], ga[VEC], k1[VEC], k2[VEC], acc[1][VEC];
   int pos[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    const int j = tx * VEC + i, gi = j / 9;
+    const int j = active ? tx * VEC + i : 0, gi = j / 9;
     pos[i] = gn_pos(j, gc);
-    mn[i] = mean[(long long)b * wc + gi]; rs[i] = rstd[(long long)b * wc + gi]; ga[i] = gamma[j];
+    mn[i] = mean[(long long)b * wc + gi] - (lbias ? lbias[j] : 0.f); rs[i] = rstd[(long long)b * wc + gi]; ga[i] = gamma[j];
     k1[i] = s1[(long long)b * wc + gi] * inv_n; k2[i] = s2[(long long)b * wc + gi] * inv_n;
+    acc[0][i] = 0.f;
   }
-  const long long base = ((long long)b * g.HW) * g.C;
-  for (int r = r0 + ty; r < r1; r += g.ry) {
-    const T* dr = dg + base + (long long)r * g.C;
-    const Pack<T, VEC> lv = ld_pack<T, VEC>(l + base + (long long)r * g.C + tx * VEC);
-    Pack<T, VEC> dv;
-    if (gc <= 0) dv = ld_pack<T, VEC>(dr + tx * VEC);
-    Pack<T, VEC> o;
+  if (active) {
+    const long long base = ((long long)b * g.HW) * g.C;
+    for (int r = r0 + ty; r < r1; r += g.ry) {
+      const T* dr = dg + base + (long long)r * g.C;
+      const Pack<T, VEC> lv = ld_pack<T, VEC>(l + base + (long long)r * g.C + tx * VEC);
+      Pack<T, VEC> dv;
+      if (gc <= 0) dv = ld_pack<T, VEC>(dr + tx * VEC);
+      Pack<T, VEC> o;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const float d = gc <= 0 ? to_acc(dv.v[i]) : (float)Elem<T>::ld(dr + pos[i]);
-      const float lh = (to_acc(lv.v[i]) - mn[i]) * rs[i];
-      o.v[i] = Elem<T>::from(rs[i] * (d * ga[i] - k1[i] - lh * k2[i]));
+      for (int i = 0; i < VEC; ++i) {
+        const float d = gc <= 0 ? to_acc(dv.v[i]) : (float)Elem<T>::ld(dr + pos[i]);
+        const float lh = (to_acc(lv.v[i]) - mn[i]) * rs[i];
+        const float v = rs[i] * (d * ga[i] - k1[i] - lh * k2[i]);
+        if (DB) acc[0][i] += v;
+        o.v[i] = Elem<T>::from(v);
+      }
+      st_pack<T, VEC>(dl + base + (long long)r * g.C + tx * VEC, o);
     }
-    st_pack<T, VEC>(dl + base + (long long)r * g.C + tx * VEC, o);
+  }
+  if (DB) {
+    cta_col_reduce<1, VEC>(acc, sm, g, tx, ty, active);
+    for (int j = threadIdx.x; j < g.C; j += NT_THREADS) atomicAdd(dlbias + j, sm[j]);
   }
 }
 
@@ -745,7 +760,8 @@ extern "C" int cotb200_tail_bwd_apply(int dtype, int B, int HW, int C, const voi
   return 0;
 }
 
-extern "C" int cotb200_gn9_stats(int dtype, int B, int HW, int wc, int gc, const void* l, float* gsum, float* gsq, void* stream) {
+extern "C" int cotb200_gn9_stats(int dtype, int B, int HW, int wc, int gc, const void* l, const float* lbias, float* gsum,
+                                 float* gsq, void* stream) {
   if (!l || !gsum || !gsq) { set_error("gn9_stats: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("gn9_stats: fp64 not supported"); return COTB200_EDTYPE; }
   if (gc > 0 && wc % gc) { set_error("gn9: gc %d does not divide wc %d", gc, wc); return COTB200_EINVAL; }
@@ -759,15 +775,15 @@ extern "C" int cotb200_gn9_stats(int dtype, int B, int HW, int wc, int gc, const
       if (rc) return rc;
       COTB200_PROF_B("gn9_stats", (double)B * HW * J * sizeof(T));
       NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(gn_stats_kernel<T, V>, smem))) return rc;
-                             gn_stats_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)l, gsum, gsq, g, wc); });
+                             gn_stats_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)l, lbias, gsum, gsq, g, wc); });
       return check_launch("gn9_stats");
     }
   });
   return 0;
 }
 
-extern "C" int cotb200_gn9_apply(int dtype, int B, int HW, int wc, int gc, const void* l, const float* mean, const float* rstd,
-                                 const float* gamma, const float* beta, void* out, void* stream) {
+extern "C" int cotb200_gn9_apply(int dtype, int B, int HW, int wc, int gc, const void* l, const float* lbias, const float* mean,
+                                 const float* rstd, const float* gamma, const float* beta, void* out, void* stream) {
   if (!l || !mean || !rstd || !gamma || !beta || !out) { set_error("gn9_apply: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("gn9_apply: fp64 not supported"); return COTB200_EDTYPE; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -779,16 +795,16 @@ extern "C" int cotb200_gn9_apply(int dtype, int B, int HW, int wc, int gc, const
       int rc = make_geo(g, B, HW, J, vec, 1, &smem);
       if (rc) return rc;
       COTB200_PROF_B("gn9_apply", (double)B * HW * J * 2 * sizeof(T));
-      NT_DISPATCH_VEC(vec, { gn_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)l, mean, rstd, gamma, beta, (T*)out, g, wc, gc); });
+      NT_DISPATCH_VEC(vec, { gn_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)l, lbias, mean, rstd, gamma, beta, (T*)out, g, wc, gc); });
       return check_launch("gn9_apply");
     }
   });
   return 0;
 }
 
-extern "C" int cotb200_gn9_bwd_sums(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* mean,
-                                    const float* rstd, const float* gamma, float* s1, float* s2, float* dgamma, float* dbeta,
-                                    void* stream) {
+extern "C" int cotb200_gn9_bwd_sums(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* lbias,
+                                    const float* mean, const float* rstd, const float* gamma, float* s1, float* s2,
+                                    float* dgamma, float* dbeta, void* stream) {
   if (!dg || !l || !mean || !rstd || !gamma || !s1 || !s2 || !dgamma || !dbeta) { set_error("gn9_bwd_sums: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("gn9_bwd_sums: fp64 not supported"); return COTB200_EDTYPE; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -801,16 +817,16 @@ extern "C" int cotb200_gn9_bwd_sums(int dtype, int B, int HW, int wc, int gc, co
       if (rc) return rc;
       COTB200_PROF_B("gn9_bwd_sums", (double)B * HW * J * 2 * sizeof(T));
       NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(gn_bwd_sums_kernel<T, V>, smem))) return rc;
-                             gn_bwd_sums_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dg, (const T*)l, mean, rstd, gamma, s1, s2, dgamma, dbeta, g, wc, gc); });
+                             gn_bwd_sums_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dg, (const T*)l, lbias, mean, rstd, gamma, s1, s2, dgamma, dbeta, g, wc, gc); });
       return check_launch("gn9_bwd_sums");
     }
   });
   return 0;
 }
 
-extern "C" int cotb200_gn9_bwd_apply(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* mean,
-                                     const float* rstd, const float* gamma, const float* s1, const float* s2, void* dl,
-                                     void* stream) {
+extern "C" int cotb200_gn9_bwd_apply(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* lbias,
+                                     const float* mean, const float* rstd, const float* gamma, const float* s1,
+                                     const float* s2, void* dl, float* dlbias, void* stream) {
   if (!dg || !l || !mean || !rstd || !gamma || !s1 || !s2 || !dl) { set_error("gn9_bwd_apply: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("gn9_bwd_apply: fp64 not supported"); return COTB200_EDTYPE; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -822,7 +838,10 @@ extern "C" int cotb200_gn9_bwd_apply(int dtype, int B, int HW, int wc, int gc, c
       int rc = make_geo(g, B, HW, J, vec, 1, &smem);
       if (rc) return rc;
       COTB200_PROF_B("gn9_bwd_apply", (double)B * HW * J * 3 * sizeof(T));
-      NT_DISPATCH_VEC(vec, { gn_bwd_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dg, (const T*)l, mean, rstd, gamma, s1, s2, (T*)dl, g, wc, gc); });
+      NT_DISPATCH_VEC(vec, {
+        if (dlbias) { if ((rc = ensure_smem(gn_bwd_apply_kernel<T, V, true>, smem))) return rc;
+                      gn_bwd_apply_kernel<T, V, true><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dg, (const T*)l, lbias, mean, rstd, gamma, s1, s2, (T*)dl, dlbias, g, wc, gc); }
+        else gn_bwd_apply_kernel<T, V, false><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dg, (const T*)l, lbias, mean, rstd, gamma, s1, s2, (T*)dl, nullptr, g, wc, gc); });
       return check_launch("gn9_bwd_apply");
     }
   });

@@ -120,17 +120,20 @@ def bn_act(x, bn: torch.nn.BatchNorm2d, relu=False, res=None):
 
 class GroupNorm9Fn(Function):
     """l [B, 9*wc, H, W] channels_last -> GroupNorm with wc groups of 9 consecutive channels (gc=0) or tap-major
-    chunks (gc>0); gamma/beta [9*wc]."""
+    chunks (gc>0); gamma/beta [9*wc].  `lbias` (None or [9*wc]): bias of the producing embed.3 convolution, added to l
+    inside the kernels (the convolution then runs bias-free and its bias gradient comes out of gn9_bwd_apply)."""
 
     @staticmethod
-    def forward(ctx, l, gamma, beta, eps, gc=0):
+    def forward(ctx, l, gamma, beta, eps, gc=0, lbias=None):
         assert _is_cl(l)
         B, J, H, W = l.shape
         wc, HW = J // 9, H * W
         lib, st, dt = _lib.load(), _lib.stream_ptr(l), _lib.dtype_code(l)
         l = l.detach()
+        lb32 = None if lbias is None else _f32(lbias)
         stats = torch.zeros(2, B, wc, dtype=torch.float32, device=l.device)
-        _lib.check(lib.cotb200_gn9_stats(dt, B, HW, wc, gc, l.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), st), "gn9_stats")
+        _lib.check(lib.cotb200_gn9_stats(dt, B, HW, wc, gc, l.data_ptr(), _lib.ptr(lb32), stats[0].data_ptr(),
+                                         stats[1].data_ptr(), st), "gn9_stats")
         fin = torch.empty(4, B * wc, dtype=torch.float32, device=l.device)      # (rstd, -mean*rstd, mean, rstd)
         _lib.check(lib.cotb200_bn_finalize(B * wc, stats[0].data_ptr(), stats[1].data_ptr(), None, None, None, None, 9.0 * HW,
                                            float(eps), 0.0, 1, 0, fin[0].data_ptr(), fin[1].data_ptr(), fin[2].data_ptr(),
@@ -138,32 +141,93 @@ class GroupNorm9Fn(Function):
         mean, rstd = fin[2], fin[3]
         g32, b32 = _f32(gamma), _f32(beta)
         out = torch.empty_like(l, memory_format=torch.channels_last)
-        _lib.check(lib.cotb200_gn9_apply(dt, B, HW, wc, gc, l.data_ptr(), mean.data_ptr(), rstd.data_ptr(), g32.data_ptr(),
-                                         b32.data_ptr(), out.data_ptr(), st), "gn9_apply")
-        ctx.save_for_backward(l, mean, rstd, g32)
+        _lib.check(lib.cotb200_gn9_apply(dt, B, HW, wc, gc, l.data_ptr(), _lib.ptr(lb32), mean.data_ptr(), rstd.data_ptr(),
+                                         g32.data_ptr(), b32.data_ptr(), out.data_ptr(), st), "gn9_apply")
+        ctx.save_for_backward(l, mean, rstd, g32, lb32)
         ctx.gc = gc
-        ctx.param_dtype = (gamma.dtype, beta.dtype)
+        ctx.param_dtype = (gamma.dtype, beta.dtype, None if lbias is None else lbias.dtype)
         return out
 
     @staticmethod
     def backward(ctx, dg):
-        l, mean, rstd, g32 = ctx.saved_tensors
+        l, mean, rstd, g32, lb32 = ctx.saved_tensors
         B, J, H, W = l.shape
         wc, HW = J // 9, H * W
         dg = dg.contiguous(memory_format=torch.channels_last)
         lib, st, dt = _lib.load(), _lib.stream_ptr(l), _lib.dtype_code(l)
         sums = torch.zeros(2, B, wc, dtype=torch.float32, device=l.device)
-        dgb = torch.zeros(2, J, dtype=torch.float32, device=l.device)
-        _lib.check(lib.cotb200_gn9_bwd_sums(dt, B, HW, wc, ctx.gc, dg.data_ptr(), l.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                            g32.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), dgb[0].data_ptr(),
-                                            dgb[1].data_ptr(), st), "gn9_bwd_sums")
+        dgb = torch.zeros(3, J, dtype=torch.float32, device=l.device)          # dgamma, dbeta, dlbias
+        _lib.check(lib.cotb200_gn9_bwd_sums(dt, B, HW, wc, ctx.gc, dg.data_ptr(), l.data_ptr(), _lib.ptr(lb32), mean.data_ptr(),
+                                            rstd.data_ptr(), g32.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(),
+                                            dgb[0].data_ptr(), dgb[1].data_ptr(), st), "gn9_bwd_sums")
+        want_db = lb32 is not None and ctx.needs_input_grad[5]
         dl = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] or want_db:
             dl = torch.empty_like(l, memory_format=torch.channels_last)
-            _lib.check(lib.cotb200_gn9_bwd_apply(dt, B, HW, wc, ctx.gc, dg.data_ptr(), l.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                                 g32.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), dl.data_ptr(), st),
+            _lib.check(lib.cotb200_gn9_bwd_apply(dt, B, HW, wc, ctx.gc, dg.data_ptr(), l.data_ptr(), _lib.ptr(lb32),
+                                                 mean.data_ptr(), rstd.data_ptr(), g32.data_ptr(), sums[0].data_ptr(),
+                                                 sums[1].data_ptr(), dl.data_ptr(), dgb[2].data_ptr() if want_db else None, st),
                        "gn9_bwd_apply")
-        return dl, dgb[0].to(ctx.param_dtype[0]), dgb[1].to(ctx.param_dtype[1]), None, None
+        return (dl if ctx.needs_input_grad[0] else None, dgb[0].to(ctx.param_dtype[0]), dgb[1].to(ctx.param_dtype[1]), None, None,
+                dgb[2].to(ctx.param_dtype[2]) if want_db else None)
+
+
+def _row_view(t):
+    """(pitch in elements) of a [B, C, H, W] tensor whose memory is NHWC rows with a constant pixel pitch >= C (a
+    channels_last tensor or a channel slice of one), else None."""
+    if t.dim() != 4:
+        return None
+    B, C, H, W = t.shape
+    sb, sc, sh, sw = t.stride()
+    if C > 1 and sc != 1:
+        return None
+    ld = sw if W > 1 else (sh if H > 1 else (sb if B > 1 else C))
+    if ld < C or (W > 1 and H > 1 and sh != W * ld) or (B > 1 and H * W > 1 and sb != H * W * ld):
+        return None
+    return ld
+
+
+class FanOutFn(Function):
+    """x -> n aliases of x whose gradients are accumulated by ONE kernel (cotb200_sum_rows) instead of autograd's chain
+    of pairwise adds; the concat's channel-sliced gradients (pitch 2C) are read in place."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.n = n
+        return tuple(x.view_as(x) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        gs = [g for g in grads if g is not None]
+        if not gs:
+            return None, None
+        if len(gs) == 1:
+            return gs[0], None
+        srcs = []
+        for g in gs:
+            ld = _row_view(g) if g.is_cuda else None
+            if ld is None:
+                g = g.contiguous(memory_format=torch.channels_last)
+                ld = g.shape[1]
+            srcs.append((g, ld))
+        B, C, H, W = gs[0].shape
+        lib, st, dt = _lib.load(), _lib.stream_ptr(gs[0]), _lib.dtype_code(gs[0])
+        out = torch.empty((B, C, H, W), dtype=gs[0].dtype, device=gs[0].device, memory_format=torch.channels_last)
+        while len(srcs) > 1:
+            grp, srcs = srcs[:4], srcs[4:]
+            args = []
+            for i in range(4):
+                args += [grp[i][0].data_ptr(), grp[i][1]] if i < len(grp) else [None, 0]
+            _lib.check(lib.cotb200_sum_rows(dt, B * H * W, C, *args, out.data_ptr(), C, st), "sum_rows")
+            srcs = [(out, C)] + srcs
+        return out, None
+
+
+def fan_out(x, n):
+    """n aliases of x for n consumers; see FanOutFn.  Falls through (returns x n times) when no gradient is needed."""
+    if not (torch.is_grad_enabled() and x.requires_grad):
+        return (x,) * n
+    return FanOutFn.apply(x, n)
 
 
 class CotTailFn(Function):
@@ -342,8 +406,8 @@ def _se_fp32(se, p):
     return torch.nn.functional.linear(z, c3.weight.float().flatten(1), None if c3.bias is None else c3.bias.float())
 
 
-def group_norm9(l, gn: torch.nn.GroupNorm, gc=0):
-    return GroupNorm9Fn.apply(l, gn.weight, gn.bias, gn.eps, gc)
+def group_norm9(l, gn: torch.nn.GroupNorm, gc=0, lbias=None):
+    return GroupNorm9Fn.apply(l, gn.weight, gn.bias, gn.eps, gc, lbias)
 
 
 def cot_tail(u, k, bn: torch.nn.BatchNorm2d, se: torch.nn.Module):

@@ -147,15 +147,28 @@ int cotb200_bn_finalize(int C, const float* sum, const float* sq, const float* w
 /* GroupNorm(num_groups = wc, channels = 9*wc) of the attention logits (models/cotnet.py:56): group g = the 9 taps of
  * weight channel g.  The logits l / dl are always in the reference channel order j = g*9 + t; `gc` is the storage order
  * of the normalised weights (and of their gradient dg): 0 = same order, > 0 = tap-major chunks (COTB200_NHWC_TAP), so
- * the permutation the LocalConv kernels want costs nothing extra.  (cotb200_gn9_stats ignores gc.) */
-int cotb200_gn9_stats(int dtype, int B, int HW, int wc, int gc, const void* l, float* gsum, float* gsq, void* stream);
-int cotb200_gn9_apply(int dtype, int B, int HW, int wc, int gc, const void* l, const float* mean, const float* rstd,
-                      const float* gamma, const float* beta, void* out, void* stream);
-int cotb200_gn9_bwd_sums(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* mean,
-                         const float* rstd, const float* gamma, float* s1, float* s2, float* dgamma, float* dbeta,
-                         void* stream);
-int cotb200_gn9_bwd_apply(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* mean,
-                          const float* rstd, const float* gamma, const float* s1, const float* s2, void* dl, void* stream);
+ * the permutation the LocalConv kernels want costs nothing extra.  (cotb200_gn9_stats ignores gc.)
+ * lbias (NULL or [9*wc] fp32, reference order): the bias of the embed.3 convolution (models/cotnet.py:55) added to l on
+ * load, so the convolution can run bias-free; cotb200_gn9_bwd_apply then also returns its gradient
+ * dlbias[j] += sum_{b,px} dl (NULL = not wanted) instead of a separate column reduction over dl. */
+int cotb200_gn9_stats(int dtype, int B, int HW, int wc, int gc, const void* l, const float* lbias, float* gsum, float* gsq,
+                      void* stream);
+int cotb200_gn9_apply(int dtype, int B, int HW, int wc, int gc, const void* l, const float* lbias, const float* mean,
+                      const float* rstd, const float* gamma, const float* beta, void* out, void* stream);
+int cotb200_gn9_bwd_sums(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* lbias,
+                         const float* mean, const float* rstd, const float* gamma, float* s1, float* s2, float* dgamma,
+                         float* dbeta, void* stream);
+int cotb200_gn9_bwd_apply(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* lbias,
+                          const float* mean, const float* rstd, const float* gamma, const float* s1, const float* s2,
+                          void* dl, float* dlbias, void* stream);
+
+/* out[r, 0:C] = sum_i src_i[r, 0:C] over up to four row-pitched sources (ld_i elements; src2/src3 may be NULL).
+ * Gradient accumulation of a tensor with several consumers inside the block -- x feeds key_embed, the concat and
+ * conv1x1 (models/cotnet.py:80-84), k feeds the concat and the recombination (:81,:97) -- in ONE pass, including the
+ * channel-sliced (pitch 2C) gradients of the concat, instead of autograd's chain of pairwise strided adds. */
+int cotb200_sum_rows(int dtype, long long rows, int C, const void* src0, long long ld0, const void* src1, long long ld1,
+                     const void* src2, long long ld2, const void* src3, long long ld3, void* out, long long ldo,
+                     void* stream);
 
 /* 3x3 / stride 2 / pad 1 pooling on NHWC tensors x [N,H,W,C] -> y [N,Ho,Wo,C], Ho = (H-1)/2+1.
  * mode 0: average with count_include_pad (nn.AvgPool2d(3, 2, padding=1), the `avd` of models/cotnet.py:199-202,237-238);

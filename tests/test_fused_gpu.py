@@ -67,7 +67,8 @@ def test_agg_tap(dtype, C, wc, H, fold, gc):
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
 @pytest.mark.parametrize("gc", [0, 8])
 @pytest.mark.parametrize("wc,H", [(8, 14), (16, 9), (12, 7), (64, 7)])
-def test_groupnorm9(dtype, tol, wc, H, gc):
+@pytest.mark.parametrize("with_lbias", [False, True])
+def test_groupnorm9(dtype, tol, wc, H, gc, with_lbias):
     if gc and wc % gc:
         pytest.skip("chunk does not divide wc")
     from cotnet_b200 import fused
@@ -79,19 +80,54 @@ def test_groupnorm9(dtype, tol, wc, H, gc):
         gn.bias.normal_(0, 0.3, generator=g)
     l = _cl((torch.randn(B, J, H, H, generator=g, device="cuda") * 2 + 0.5).to(dtype)).requires_grad_(True)
     cot = _cl(torch.randn(B, J, H, H, generator=g, device="cuda").to(dtype))
-    out_t = fused.group_norm9(l, gn, gc)
-    gl, gw, gb = torch.autograd.grad(out_t, (l, gn.weight, gn.bias), _cl(_to_tap(cot, gc)))
+    # lbias = the embed.3 convolution bias folded into the kernels: GroupNorm(l + bias), gradient from gn9_bwd_apply
+    lbias = (torch.randn(J, generator=g, device="cuda") * 0.7).requires_grad_(True) if with_lbias else None
+    out_t = fused.group_norm9(l, gn, gc, lbias)
+    wanted = (l, gn.weight, gn.bias) + ((lbias,) if with_lbias else ())
+    got = torch.autograd.grad(out_t, wanted, _cl(_to_tap(cot, gc)))
     out = _from_tap(out_t, gc)
     lr = l.detach().double().requires_grad_(True)
+    br = lbias.detach().double().requires_grad_(True) if with_lbias else None
     gnr = nn.GroupNorm(wc, J).cuda().double()
     gnr.load_state_dict(gn.state_dict())
-    ref = gnr(lr)
-    rl, rw, rb = torch.autograd.grad(ref, (lr, gnr.weight, gnr.bias), cot.double())
-    for a, b, name in ((out, ref, "out"), (gl, rl, "dl"), (gw, rw, "dgamma"), (gb, rb, "dbeta")):
+    ref = gnr(lr + br.view(1, J, 1, 1)) if with_lbias else gnr(lr)
+    refs = torch.autograd.grad(ref, (lr, gnr.weight, gnr.bias) + ((br,) if with_lbias else ()), cot.double())
+    for a, b, name in zip((out,) + tuple(got), (ref,) + tuple(refs), ("out", "dl", "dgamma", "dbeta", "dlbias")):
         err = (a.double() - b).abs().max().item()
         scale = max(1.0, b.abs().max().item())
         assert err <= tol * scale, "%s err %.3e scale %.3e" % (name, err, scale)
     assert out_t.is_contiguous(memory_format=torch.channels_last) and out_t.dtype == dtype
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,H", [(64, 14), (24, 9), (3, 5)])
+def test_fan_out_sums_gradients(dtype, C, H):
+    """fused.fan_out: one cotb200_sum_rows launch accumulates the gradients of all consumers, reading the channel
+    slices of a concat gradient (pitch 2C) in place; must equal autograd's own accumulation."""
+    from cotnet_b200 import fused
+    g = torch.Generator(device="cuda").manual_seed(C * H)
+    B = 3
+    x = _cl(torch.randn(B, C, H, H, generator=g, device="cuda").to(dtype)).requires_grad_(True)
+    wgt = [torch.randn(B, C, H, H, generator=g, device="cuda").to(dtype) for _ in range(2)]
+    wcat = _cl(torch.randn(B, 2 * C, H, H, generator=g, device="cuda").to(dtype))
+
+    def graph(a, b, c):
+        # consumer 1: elementwise; consumer 2: first half of a concat (sliced, pitch-2C gradient); consumer 3: NCHW product
+        cat = torch.cat([b, torch.zeros_like(b)], dim=1) * wcat
+        return (a * _cl(wgt[0])).sum() + cat.sum() + (c * wgt[1]).sum()
+
+    a, b, c = fused.fan_out(x, 3)
+    (gx,) = torch.autograd.grad(graph(a, b, c), x)
+    xr = x.detach().double().requires_grad_(True)
+    ref = (xr * wgt[0].double()).sum() + (xr * wcat[:, :C].double()).sum() + (xr * wgt[1].double()).sum()
+    (gr,) = torch.autograd.grad(ref, xr)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    err = (gx.double() - gr).abs()
+    assert bool((err <= tol + tol * gr.abs()).all()), "max err %.3e" % err.max().item()
+    assert gx.is_contiguous(memory_format=torch.channels_last) or C == 1
+    # no-grad: pass-through
+    with torch.no_grad():
+        assert all(t is x for t in fused.fan_out(x, 2))
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-4), (torch.bfloat16, 4e-2)])
