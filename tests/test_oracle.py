@@ -99,3 +99,22 @@ def test_restatement_vs_live_reference_module():
         want = m(x)
     got = cot_ref.cot_layer(x, {k: v.clone() for k, v in sd.items()}, training=False)
     assert (got - want).abs().max() < 1e-11
+
+
+def test_reference_kernel_cubins_are_consistent():
+    """oracle/_ref (built from /root/reference by oracle/build_ref_kernels.py): every manifest entry has its cubin and the
+    launch geometry the reference uses (block 1024, grid ceil(n / 1024), aggregation_zeropad.py:8,17-18,140-141)."""
+    import json
+    import os
+    from oracle import ref_kernels
+    if not ref_kernels.available():
+        pytest.skip("oracle/_ref not built")
+    man = json.load(open(os.path.join(ref_kernels.HERE, "manifest.json")))
+    assert man["block"] == 1024 and len(man["kernels"]) >= 30
+    for e in man["kernels"]:
+        blob = open(os.path.join(ref_kernels.HERE, e["file"]), "rb").read()
+        assert blob[:4] == b"\x7fELF" and e["kernel"].encode() in blob
+        if "mix_weight_backward" in e["kernel"]:
+            assert e["grid"] == (e["nthreads"] // 2 + 1023) // 1024
+        else:
+            assert e["grid"] == (e["nthreads"] + 1023) // 1024

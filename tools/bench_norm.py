@@ -47,14 +47,16 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--shapes", default=None, help="comma list of HWxC, e.g. 56x256,7x2048 (default: all)")
     a = ap.parse_args()
+    shapes = SHAPES if not a.shapes else [tuple(int(v) for v in s.split("x")) for s in a.shapes.split(",")]
     lib = _lib.load()
     dev = torch.device("cuda")
     pk = peak()
     st = torch.cuda.current_stream().cuda_stream
     B = a.batch
     out = []
-    for HW, C in SHAPES:
+    for HW, C in shapes:
         rows = B * HW * HW
         es = 2
         nbytes = rows * C * es
