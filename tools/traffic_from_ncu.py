@@ -20,7 +20,7 @@ def main():
     lines = [l for l in open(src) if not l.startswith("==")]
     per = collections.defaultdict(lambda: collections.defaultdict(dict))
     for row in csv.DictReader(lines):
-        m = re.search(r"cotb200::(\w+)", row["Kernel Name"])
+        m = re.search(r"(\w+_kernel)\b", row["Kernel Name"])
         if not m or m.group(1) not in NAMES:
             continue
         val = float(row["Metric Value"].replace(",", "")) * UNIT.get(row["Metric Unit"], 1.0)
