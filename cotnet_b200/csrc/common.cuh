@@ -120,6 +120,25 @@ template <> __device__ __forceinline__ double to_acc<double>(double v) { return 
 template <> __device__ __forceinline__ float to_acc<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <> __device__ __forceinline__ float to_acc<__half>(__half v) { return __half2float(v); }
 
+// d = a*b + c with 16-bit a, b consumed directly (sm_100 mixed-precision FMA, SASS FHFMA with .H0/.H1 operand selectors):
+// no unpack instructions in reductions over bf16/fp16 tensors.  Exact products, fp32 accumulation.
+template <typename T> __device__ __forceinline__ float mfma(T a, T b, float c);
+template <> __device__ __forceinline__ float mfma<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> __device__ __forceinline__ float mfma<__nv_bfloat16>(__nv_bfloat16 a, __nv_bfloat16 b, float c) {
+  float d;
+  asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(__bfloat16_as_ushort(a)), "h"(__bfloat16_as_ushort(b)), "f"(c));
+  return d;
+}
+template <> __device__ __forceinline__ float mfma<__half>(__half a, __half b, float c) {
+  float d;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(__half_as_ushort(a)), "h"(__half_as_ushort(b)), "f"(c));
+  return d;
+}
+template <typename T> __device__ __forceinline__ T one_of();
+template <> __device__ __forceinline__ float one_of<float>() { return 1.f; }
+template <> __device__ __forceinline__ __nv_bfloat16 one_of<__nv_bfloat16>() { return __ushort_as_bfloat16((unsigned short)0x3F80); }
+template <> __device__ __forceinline__ __half one_of<__half>() { return __ushort_as_half((unsigned short)0x3C00); }
+
 // dtype dispatch on the host
 #define COTB200_DISPATCH_DTYPE(dtype, ...)                                   \
   switch (dtype) {                                                           \

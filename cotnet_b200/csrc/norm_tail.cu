@@ -27,6 +27,18 @@ struct RowsGeo {
 
 // fast sigmoid: ex2 + approximate reciprocal (2 ulp) instead of an IEEE division (~10 instructions) per element
 __device__ __forceinline__ float sigmoidf_(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+// 16-bit tensors: sigmoid(z) = 0.5 + 0.5*tanh(z/2) with the hardware tanh (ONE MUFU op instead of ex2 + rcp; abs error
+// ~2.5e-4, an order below the bf16 output ulp).  The SiLU kernels are MUFU-bound otherwise (2 x 10.7 elements/clk/SM at
+// the HBM rate against 16 MUFU/clk/SM).  fp32 tensors keep the exact-ish form above.
+template <typename T> __device__ __forceinline__ float sigmoid_t(float z) {
+  if constexpr (sizeof(T) == 2) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+    return fmaf(0.5f, t, 0.5f);
+  } else {
+    return sigmoidf_(z);
+  }
+}
 
 // Reduce acc[NS][VEC] over the ty lanes of the CTA; result for column c lands in smem_out[s*C + c].
 template <int NS, int VEC>
@@ -66,7 +78,7 @@ col_stats_kernel(const T* __restrict__ x, float* __restrict__ sum, float* __rest
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> v = ld_pack<T, VEC>(xp + (long long)r * g.ld);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { const float f = to_acc(v.v[i]); acc[0][i] += f; acc[1][i] = fmaf(f, f, acc[1][i]); }
+      for (int i = 0; i < VEC; ++i) { acc[0][i] = mfma<T>(v.v[i], one_of<T>(), acc[0][i]); acc[1][i] = mfma<T>(v.v[i], v.v[i], acc[1][i]); }
     }
   }
   cta_col_reduce<2, VEC>(acc, sm, g, tx, ty, active);
@@ -97,7 +109,7 @@ tail_pool_kernel(const T* __restrict__ u, const T* __restrict__ k, const float* 
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const float z = fmaf(to_acc(uv.v[i]), sc[i], sh[i]);
-        acc[0][i] += z * sigmoidf_(z) + to_acc(kv.v[i]);
+        acc[0][i] += z * sigmoid_t<T>(z) + to_acc(kv.v[i]);
       }
     }
   }
@@ -128,7 +140,7 @@ tail_combine_kernel(const T* __restrict__ u, const T* __restrict__ k, const floa
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const float z = fmaf(to_acc(uv.v[i]), sc[i], sh[i]);
-      o.v[i] = Elem<T>::from(fmaf(a0[i], z * sigmoidf_(z), a1[i] * to_acc(kv.v[i])));
+      o.v[i] = Elem<T>::from(fmaf(a0[i], z * sigmoid_t<T>(z), a1[i] * to_acc(kv.v[i])));
     }
     st_pack<T, VEC>(out + base + (long long)r * g.C, o);
   }
@@ -157,7 +169,7 @@ tail_bwd_sums_kernel(const T* __restrict__ dout, const T* __restrict__ u, const 
       for (int i = 0; i < VEC; ++i) {
         const float z = fmaf(to_acc(uv.v[i]), sc[i], sh[i]);
         const float d = to_acc(dv.v[i]);
-        acc[0][i] = fmaf(d, z * sigmoidf_(z), acc[0][i]);
+        acc[0][i] = fmaf(d, z * sigmoid_t<T>(z), acc[0][i]);
         acc[1][i] = fmaf(d, to_acc(kv.v[i]), acc[1][i]);
       }
     }
@@ -198,7 +210,7 @@ tail_bwd_dz_sums_kernel(const T* __restrict__ dout, const T* __restrict__ u, con
       for (int i = 0; i < VEC; ++i) {
         const float uf = to_acc(uv.v[i]);
         const float z = fmaf(uf, sc[i], sh[i]);
-        const float s = sigmoidf_(z);
+        const float s = sigmoid_t<T>(z);
         const float dz = fmaf(a0[i], to_acc(dv.v[i]), dp[i]) * (s * (1.f + z * (1.f - s)));
         acc[0][i] += dz;
         acc[1][i] = fmaf(dz, (uf - m[i]) * rs[i], acc[1][i]);
@@ -240,7 +252,7 @@ tail_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ u, const
     for (int i = 0; i < VEC; ++i) {
       const float uf = to_acc(uv.v[i]), d = to_acc(dv.v[i]);
       const float z = fmaf(uf, sc[i], sh[i]);
-      const float s = sigmoidf_(z);
+      const float s = sigmoid_t<T>(z);
       const float dz = fmaf(a0[i], d, dp[i]) * (s * (1.f + z * (1.f - s)));
       o1.v[i] = Elem<T>::from(sc[i] * (dz - k1[i] - (uf - m[i]) * rs[i] * k2[i]));
       o2.v[i] = Elem<T>::from(fmaf(a1[i], d, dp[i]));
@@ -462,22 +474,22 @@ gn_apply_kernel(const T* __restrict__ l, const float* __restrict__ lbias, const 
   }
 }
 
-// backward sums: s1[b,g] += sum dg*gamma ; s2[b,g] += sum dg*gamma*lhat ; dgamma[j] += sum dg*lhat ; dbeta[j] += sum dg
-// Thread = one packet of l in the reference order; dg gathered from its storage order.
+// backward sums, per (sample, column j) partials:  P[b][0][j] += sum dg ; P[b][1][j] += sum dg*lhat ; P[b][2][j] += sum lhat
+// (lhat = (l + lbias - mean)*rstd).  gn_bwd_finish_kernel (gn72.cu) turns them into s1, s2, dgamma, dbeta and the bias
+// gradient.  Thread = one packet of l in the reference order; dg gathered from its storage order.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(NT_THREADS)
 gn_bwd_sums_kernel(const T* __restrict__ dg, const T* __restrict__ l, const float* __restrict__ lbias, const float* __restrict__ mean,
-                   const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ s1,
-                   float* __restrict__ s2, float* __restrict__ dgamma, float* __restrict__ dbeta, RowsGeo g, int wc, int gc) {
+                   const float* __restrict__ rstd, float* __restrict__ P, RowsGeo g, int wc, int gc) {
   extern __shared__ float sm[];
   const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
   const bool active = tx < g.cq && ty < g.ry;
   const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
-  float acc[2][VEC], mn[VEC], rs[VEC];    // acc[0] = sum dg ; acc[1] = sum dg*lhat   (per column j)
+  float acc[3][VEC], mn[VEC], rs[VEC];    // acc[0] = sum dg ; acc[1] = sum dg*lhat ; acc[2] = sum lhat   (per column j)
   int pos[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    acc[0][i] = acc[1][i] = 0.f;
+    acc[0][i] = acc[1][i] = acc[2][i] = 0.f;
     const int j = tx * VEC + i, gi = active ? j / 9 : 0;
     pos[i] = active ? gn_pos(j, gc) : 0;
     mn[i] = active ? mean[(long long)b * wc + gi] - (lbias ? lbias[j] : 0.f) : 0.f;     // (l + bias - mean) = l - mn
@@ -493,74 +505,55 @@ gn_bwd_sums_kernel(const T* __restrict__ dg, const T* __restrict__ l, const floa
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const float d = gc <= 0 ? to_acc(dv.v[i]) : (float)Elem<T>::ld(dr + pos[i]);
+        const float lh = (to_acc(lv.v[i]) - mn[i]) * rs[i];
         acc[0][i] += d;
-        acc[1][i] = fmaf(d, (to_acc(lv.v[i]) - mn[i]) * rs[i], acc[1][i]);
+        acc[1][i] = fmaf(d, lh, acc[1][i]);
+        acc[2][i] += lh;
       }
     }
   }
-  cta_col_reduce<2, VEC>(acc, sm, g, tx, ty, active);
+  cta_col_reduce<3, VEC>(acc, sm, g, tx, ty, active);
+  float* Pb = P + (long long)b * 3 * g.C;
   for (int j = threadIdx.x; j < g.C; j += NT_THREADS) {
-    atomicAdd(dbeta + j, sm[j]);
-    atomicAdd(dgamma + j, sm[g.ry * g.C + j]);
-  }
-  for (int gi = threadIdx.x; gi < wc; gi += NT_THREADS) {
-    float a = 0.f, q = 0.f;
-    for (int t = 0; t < 9; ++t) {
-      const int j = gi * 9 + t;
-      a = fmaf(sm[j], gamma[j], a);
-      q = fmaf(sm[g.ry * g.C + j], gamma[j], q);
-    }
-    atomicAdd(s1 + (long long)b * wc + gi, a);
-    atomicAdd(s2 + (long long)b * wc + gi, q);
+    atomicAdd(Pb + j, sm[j]);
+    atomicAdd(Pb + g.C + j, sm[g.ry * g.C + j]);
+    atomicAdd(Pb + 2 * g.C + j, sm[2 * g.ry * g.C + j]);
   }
 }
 
-// dl = rstd * ( dg*gamma - s1/n - lhat * s2/n ),  n = 9*HW ;  DB: dlbias[j] += sum_rows dl (the bias gradient of the
-// embed.3 convolution, models/cotnet.py:55, when the bias add is folded into these kernels)
-template <typename T, int VEC, bool DB>
+// dl = rstd * ( dg*gamma - s1/n - lhat * s2/n ),  n = 9*HW
+template <typename T, int VEC>
 __global__ void __launch_bounds__(NT_THREADS)
 gn_bwd_apply_kernel(const T* __restrict__ dg, const T* __restrict__ l, const float* __restrict__ lbias,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                    const float* __restrict__ s1, const float* __restrict__ s2, T* __restrict__ dl,
-                    float* __restrict__ dlbias, RowsGeo g, int wc, int gc) {
-  extern __shared__ float sm[];
+                    const float* __restrict__ s1, const float* __restrict__ s2, T* __restrict__ dl, RowsGeo g, int wc, int gc) {
   const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
-  const bool active = tx < g.cq && ty < g.ry;
-  if (!DB && !active) return;
+  if (!(tx < g.cq && ty < g.ry)) return;
   const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
   const float inv_n = 1.f / (9.f * (float)g.HW);
-  float mn[VEC], rs[VEC], ga[VEC], k1[VEC], k2[VEC], acc[1][VEC];
+  float mn[VEC], rs[VEC], ga[VEC], k1[VEC], k2[VEC];
   int pos[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    const int j = active ? tx * VEC + i : 0, gi = j / 9;
+    const int j = tx * VEC + i, gi = j / 9;
     pos[i] = gn_pos(j, gc);
     mn[i] = mean[(long long)b * wc + gi] - (lbias ? lbias[j] : 0.f); rs[i] = rstd[(long long)b * wc + gi]; ga[i] = gamma[j];
     k1[i] = s1[(long long)b * wc + gi] * inv_n; k2[i] = s2[(long long)b * wc + gi] * inv_n;
-    acc[0][i] = 0.f;
   }
-  if (active) {
-    const long long base = ((long long)b * g.HW) * g.C;
-    for (int r = r0 + ty; r < r1; r += g.ry) {
-      const T* dr = dg + base + (long long)r * g.C;
-      const Pack<T, VEC> lv = ld_pack<T, VEC>(l + base + (long long)r * g.C + tx * VEC);
-      Pack<T, VEC> dv;
-      if (gc <= 0) dv = ld_pack<T, VEC>(dr + tx * VEC);
-      Pack<T, VEC> o;
+  const long long base = ((long long)b * g.HW) * g.C;
+  for (int r = r0 + ty; r < r1; r += g.ry) {
+    const T* dr = dg + base + (long long)r * g.C;
+    const Pack<T, VEC> lv = ld_pack<T, VEC>(l + base + (long long)r * g.C + tx * VEC);
+    Pack<T, VEC> dv;
+    if (gc <= 0) dv = ld_pack<T, VEC>(dr + tx * VEC);
+    Pack<T, VEC> o;
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const float d = gc <= 0 ? to_acc(dv.v[i]) : (float)Elem<T>::ld(dr + pos[i]);
-        const float lh = (to_acc(lv.v[i]) - mn[i]) * rs[i];
-        const float v = rs[i] * (d * ga[i] - k1[i] - lh * k2[i]);
-        if (DB) acc[0][i] += v;
-        o.v[i] = Elem<T>::from(v);
-      }
-      st_pack<T, VEC>(dl + base + (long long)r * g.C + tx * VEC, o);
+    for (int i = 0; i < VEC; ++i) {
+      const float d = gc <= 0 ? to_acc(dv.v[i]) : (float)Elem<T>::ld(dr + pos[i]);
+      const float lh = (to_acc(lv.v[i]) - mn[i]) * rs[i];
+      o.v[i] = Elem<T>::from(rs[i] * (d * ga[i] - k1[i] - lh * k2[i]));
     }
-  }
-  if (DB) {
-    cta_col_reduce<1, VEC>(acc, sm, g, tx, ty, active);
-    for (int j = threadIdx.x; j < g.C; j += NT_THREADS) atomicAdd(dlbias + j, sm[j]);
+    st_pack<T, VEC>(dl + base + (long long)r * g.C + tx * VEC, o);
   }
 }
 
@@ -625,6 +618,18 @@ static int ensure_smem(KFn fn, size_t smem) {
   }
   return 0;
 }
+
+// block-of-72 kernels (gn72.cu)
+bool gn72_ok(int dtype, int wc, int gc, bool permuting, const void* p0, const void* p1, const void* p2);
+template <typename T> int gn72_stats_launch(int B, int HW, int wc, const void* l, const float* lbias, float* gsum, float* gsq, cudaStream_t st);
+template <typename T> int gn72_apply_launch(int B, int HW, int wc, const void* l, const float* lbias, const float* mean, const float* rstd,
+                                            const float* gamma, const float* beta, void* out, cudaStream_t st);
+template <typename T> int gn72_bwd_sums_launch(int B, int HW, int wc, const void* dg, const void* l, float* P, cudaStream_t st);
+template <typename T> int gn72_bwd_apply_launch(int B, int HW, int wc, const void* dg, const void* l, const float* lbias, const float* mean,
+                                                const float* rstd, const float* gamma, const float* s1, const float* s2, void* dl,
+                                                cudaStream_t st);
+int gn_bwd_finish_launch(int B, int HW, int wc, const float* P, int raw, const float* lbias, const float* mean, const float* rstd,
+                         const float* gamma, float* s1, float* s2, float* dgamma, float* dbeta, float* dlbias, cudaStream_t st);
 
 }  // namespace cotb200
 
@@ -767,13 +772,15 @@ extern "C" int cotb200_gn9_stats(int dtype, int B, int HW, int wc, int gc, const
   if (gc > 0 && wc % gc) { set_error("gn9: gc %d does not divide wc %d", gc, wc); return COTB200_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
   const int J = 9 * wc;
+  const bool fast = gn72_ok(dtype, wc, gc, false, l, nullptr, nullptr);
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
+      COTB200_PROF_B("gn9_stats", (double)B * HW * J * sizeof(T));
+      if (fast) return gn72_stats_launch<T>(B, HW, wc, l, lbias, gsum, gsq, st);
       const int vec = pick_vec<T>(J, l);
       RowsGeo g; size_t smem;
       int rc = make_geo(g, B, HW, J, vec, 2, &smem);
       if (rc) return rc;
-      COTB200_PROF_B("gn9_stats", (double)B * HW * J * sizeof(T));
       NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(gn_stats_kernel<T, V>, smem))) return rc;
                              gn_stats_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)l, lbias, gsum, gsq, g, wc); });
       return check_launch("gn9_stats");
@@ -786,15 +793,18 @@ extern "C" int cotb200_gn9_apply(int dtype, int B, int HW, int wc, int gc, const
                                  const float* rstd, const float* gamma, const float* beta, void* out, void* stream) {
   if (!l || !mean || !rstd || !gamma || !beta || !out) { set_error("gn9_apply: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("gn9_apply: fp64 not supported"); return COTB200_EDTYPE; }
+  if (gc > 0 && wc % gc) { set_error("gn9: gc %d does not divide wc %d", gc, wc); return COTB200_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
   const int J = 9 * wc;
+  const bool fast = gn72_ok(dtype, wc, gc, true, l, out, nullptr);
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
+      COTB200_PROF_B("gn9_apply", (double)B * HW * J * 2 * sizeof(T));
+      if (fast) return gn72_apply_launch<T>(B, HW, wc, l, lbias, mean, rstd, gamma, beta, out, st);
       const int vec = pick_vec<T>(J, l, out);
       RowsGeo g; size_t smem;
       int rc = make_geo(g, B, HW, J, vec, 1, &smem);
       if (rc) return rc;
-      COTB200_PROF_B("gn9_apply", (double)B * HW * J * 2 * sizeof(T));
       NT_DISPATCH_VEC(vec, { gn_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)l, lbias, mean, rstd, gamma, beta, (T*)out, g, wc, gc); });
       return check_launch("gn9_apply");
     }
@@ -803,22 +813,32 @@ extern "C" int cotb200_gn9_apply(int dtype, int B, int HW, int wc, int gc, const
 }
 
 extern "C" int cotb200_gn9_bwd_sums(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* lbias,
-                                    const float* mean, const float* rstd, const float* gamma, float* s1, float* s2,
-                                    float* dgamma, float* dbeta, void* stream) {
-  if (!dg || !l || !mean || !rstd || !gamma || !s1 || !s2 || !dgamma || !dbeta) { set_error("gn9_bwd_sums: NULL pointer"); return COTB200_ENULL; }
+                                    const float* mean, const float* rstd, const float* gamma, float* work, float* s1,
+                                    float* s2, float* dgamma, float* dbeta, float* dlbias, void* stream) {
+  if (!dg || !l || !mean || !rstd || !gamma || !work || !s1 || !s2 || !dgamma || !dbeta) { set_error("gn9_bwd_sums: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("gn9_bwd_sums: fp64 not supported"); return COTB200_EDTYPE; }
+  if (gc > 0 && wc % gc) { set_error("gn9: gc %d does not divide wc %d", gc, wc); return COTB200_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
   const int J = 9 * wc;
+  const bool fast = gn72_ok(dtype, wc, gc, true, dg, l, nullptr);
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
-      const int vec = pick_vec<T>(J, dg, l);
-      RowsGeo g; size_t smem;
-      int rc = make_geo(g, B, HW, J, vec, 2, &smem);
-      if (rc) return rc;
-      COTB200_PROF_B("gn9_bwd_sums", (double)B * HW * J * 2 * sizeof(T));
-      NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(gn_bwd_sums_kernel<T, V>, smem))) return rc;
-                             gn_bwd_sums_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dg, (const T*)l, lbias, mean, rstd, gamma, s1, s2, dgamma, dbeta, g, wc, gc); });
-      return check_launch("gn9_bwd_sums");
+      int rc;
+      {
+        COTB200_PROF_B("gn9_bwd_sums", (double)B * HW * J * 2 * sizeof(T));
+        if (fast) {
+          if ((rc = gn72_bwd_sums_launch<T>(B, HW, wc, dg, l, work, st))) return rc;
+        } else {
+          const int vec = pick_vec<T>(J, dg, l);
+          RowsGeo g; size_t smem;
+          if ((rc = make_geo(g, B, HW, J, vec, 3, &smem))) return rc;
+          NT_DISPATCH_VEC(vec, { if ((rc = ensure_smem(gn_bwd_sums_kernel<T, V>, smem))) return rc;
+                                 gn_bwd_sums_kernel<T, V><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dg, (const T*)l, lbias, mean, rstd, work, g, wc, gc); });
+          if ((rc = check_launch("gn9_bwd_sums"))) return rc;
+        }
+      }
+      COTB200_PROF_B("gn9_bwd_finish", 0.0);
+      return gn_bwd_finish_launch(B, HW, wc, work, fast ? 1 : 0, lbias, mean, rstd, gamma, s1, s2, dgamma, dbeta, dlbias, st);
     }
   });
   return 0;
@@ -826,22 +846,22 @@ extern "C" int cotb200_gn9_bwd_sums(int dtype, int B, int HW, int wc, int gc, co
 
 extern "C" int cotb200_gn9_bwd_apply(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* lbias,
                                      const float* mean, const float* rstd, const float* gamma, const float* s1,
-                                     const float* s2, void* dl, float* dlbias, void* stream) {
+                                     const float* s2, void* dl, void* stream) {
   if (!dg || !l || !mean || !rstd || !gamma || !s1 || !s2 || !dl) { set_error("gn9_bwd_apply: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("gn9_bwd_apply: fp64 not supported"); return COTB200_EDTYPE; }
+  if (gc > 0 && wc % gc) { set_error("gn9: gc %d does not divide wc %d", gc, wc); return COTB200_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
   const int J = 9 * wc;
+  const bool fast = gn72_ok(dtype, wc, gc, true, dg, l, dl);
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
+      COTB200_PROF_B("gn9_bwd_apply", (double)B * HW * J * 3 * sizeof(T));
+      if (fast) return gn72_bwd_apply_launch<T>(B, HW, wc, dg, l, lbias, mean, rstd, gamma, s1, s2, dl, st);
       const int vec = pick_vec<T>(J, dg, l, dl);
       RowsGeo g; size_t smem;
       int rc = make_geo(g, B, HW, J, vec, 1, &smem);
       if (rc) return rc;
-      COTB200_PROF_B("gn9_bwd_apply", (double)B * HW * J * 3 * sizeof(T));
-      NT_DISPATCH_VEC(vec, {
-        if (dlbias) { if ((rc = ensure_smem(gn_bwd_apply_kernel<T, V, true>, smem))) return rc;
-                      gn_bwd_apply_kernel<T, V, true><<<NT_GRID, NT_THREADS, smem, st>>>((const T*)dg, (const T*)l, lbias, mean, rstd, gamma, s1, s2, (T*)dl, dlbias, g, wc, gc); }
-        else gn_bwd_apply_kernel<T, V, false><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dg, (const T*)l, lbias, mean, rstd, gamma, s1, s2, (T*)dl, nullptr, g, wc, gc); });
+      NT_DISPATCH_VEC(vec, { gn_bwd_apply_kernel<T, V><<<NT_GRID, NT_THREADS, 0, st>>>((const T*)dg, (const T*)l, lbias, mean, rstd, gamma, s1, s2, (T*)dl, g, wc, gc); });
       return check_launch("gn9_bwd_apply");
     }
   });

@@ -155,20 +155,21 @@ class GroupNorm9Fn(Function):
         wc, HW = J // 9, H * W
         dg = dg.contiguous(memory_format=torch.channels_last)
         lib, st, dt = _lib.load(), _lib.stream_ptr(l), _lib.dtype_code(l)
-        sums = torch.zeros(2, B, wc, dtype=torch.float32, device=l.device)
-        dgb = torch.zeros(3, J, dtype=torch.float32, device=l.device)          # dgamma, dbeta, dlbias
-        _lib.check(lib.cotb200_gn9_bwd_sums(dt, B, HW, wc, ctx.gc, dg.data_ptr(), l.data_ptr(), _lib.ptr(lb32), mean.data_ptr(),
-                                            rstd.data_ptr(), g32.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(),
-                                            dgb[0].data_ptr(), dgb[1].data_ptr(), st), "gn9_bwd_sums")
+        sums = torch.empty(2, B, wc, dtype=torch.float32, device=l.device)      # s1, s2 (written)
+        acc = torch.zeros(3 * J + 3 * B * J, dtype=torch.float32, device=l.device)   # dgamma, dbeta, dlbias | work [B,3,J]
+        dgb, work = acc[:3 * J].view(3, J), acc[3 * J:]
         want_db = lb32 is not None and ctx.needs_input_grad[5]
+        _lib.check(lib.cotb200_gn9_bwd_sums(dt, B, HW, wc, ctx.gc, dg.data_ptr(), l.data_ptr(), _lib.ptr(lb32), mean.data_ptr(),
+                                            rstd.data_ptr(), g32.data_ptr(), work.data_ptr(), sums[0].data_ptr(),
+                                            sums[1].data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(),
+                                            dgb[2].data_ptr() if want_db else None, st), "gn9_bwd_sums")
         dl = None
-        if ctx.needs_input_grad[0] or want_db:
+        if ctx.needs_input_grad[0]:
             dl = torch.empty_like(l, memory_format=torch.channels_last)
             _lib.check(lib.cotb200_gn9_bwd_apply(dt, B, HW, wc, ctx.gc, dg.data_ptr(), l.data_ptr(), _lib.ptr(lb32),
                                                  mean.data_ptr(), rstd.data_ptr(), g32.data_ptr(), sums[0].data_ptr(),
-                                                 sums[1].data_ptr(), dl.data_ptr(), dgb[2].data_ptr() if want_db else None, st),
-                       "gn9_bwd_apply")
-        return (dl if ctx.needs_input_grad[0] else None, dgb[0].to(ctx.param_dtype[0]), dgb[1].to(ctx.param_dtype[1]), None, None,
+                                                 sums[1].data_ptr(), dl.data_ptr(), st), "gn9_bwd_apply")
+        return (dl, dgb[0].to(ctx.param_dtype[0]), dgb[1].to(ctx.param_dtype[1]), None, None,
                 dgb[2].to(ctx.param_dtype[2]) if want_db else None)
 
 

@@ -149,18 +149,22 @@ int cotb200_bn_finalize(int C, const float* sum, const float* sq, const float* w
  * of the normalised weights (and of their gradient dg): 0 = same order, > 0 = tap-major chunks (COTB200_NHWC_TAP), so
  * the permutation the LocalConv kernels want costs nothing extra.  (cotb200_gn9_stats ignores gc.)
  * lbias (NULL or [9*wc] fp32, reference order): the bias of the embed.3 convolution (models/cotnet.py:55) added to l on
- * load, so the convolution can run bias-free; cotb200_gn9_bwd_apply then also returns its gradient
- * dlbias[j] += sum_{b,px} dl (NULL = not wanted) instead of a separate column reduction over dl. */
+ * load, so the convolution can run bias-free; cotb200_gn9_bwd_sums then also returns its gradient
+ * dlbias[j] += sum_{b,px} dl (NULL = not wanted), derived analytically from the column sums -- no extra pass over dl.
+ * cotb200_gn9_bwd_sums: work = [B, 3, 9*wc] fp32 zeros (per-sample column partials); s1, s2 [B, wc] are written;
+ * dgamma, dbeta (and dlbias) [9*wc] are accumulated into (zero them first).
+ * Fast path ("blocks of 72", csrc/gn72.cu): wc in {8,16,32,64}, gc == 8, 16-byte aligned tensors -- tiles moved by
+ * cp.async.bulk, the tap permutation done in registers.  Everything else runs the generic kernels. */
 int cotb200_gn9_stats(int dtype, int B, int HW, int wc, int gc, const void* l, const float* lbias, float* gsum, float* gsq,
                       void* stream);
 int cotb200_gn9_apply(int dtype, int B, int HW, int wc, int gc, const void* l, const float* lbias, const float* mean,
                       const float* rstd, const float* gamma, const float* beta, void* out, void* stream);
 int cotb200_gn9_bwd_sums(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* lbias,
-                         const float* mean, const float* rstd, const float* gamma, float* s1, float* s2, float* dgamma,
-                         float* dbeta, void* stream);
+                         const float* mean, const float* rstd, const float* gamma, float* work, float* s1, float* s2,
+                         float* dgamma, float* dbeta, float* dlbias, void* stream);
 int cotb200_gn9_bwd_apply(int dtype, int B, int HW, int wc, int gc, const void* dg, const void* l, const float* lbias,
                           const float* mean, const float* rstd, const float* gamma, const float* s1, const float* s2,
-                          void* dl, float* dlbias, void* stream);
+                          void* dl, void* stream);
 
 /* out[r, 0:C] = sum_i src_i[r, 0:C] over up to four row-pitched sources (ld_i elements; src2/src3 may be NULL).
  * Gradient accumulation of a tensor with several consumers inside the block -- x feeds key_embed, the concat and

@@ -66,7 +66,7 @@ def test_agg_tap(dtype, C, wc, H, fold, gc):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
 @pytest.mark.parametrize("gc", [0, 8])
-@pytest.mark.parametrize("wc,H", [(8, 14), (16, 9), (12, 7), (64, 7)])
+@pytest.mark.parametrize("wc,H", [(8, 14), (16, 9), (12, 7), (64, 7), (8, 56), (32, 14), (24, 5)])
 @pytest.mark.parametrize("with_lbias", [False, True])
 def test_groupnorm9(dtype, tol, wc, H, gc, with_lbias):
     if gc and wc % gc:
