@@ -11,6 +11,7 @@ max-pool, [3,4,6,3]/[3,4,23,3] stages, 1x1 conv down-sample, 3x3/2 avg-pool in f
 of stride-2 blocks (``avd``, :199-202,:237-238), global average pool + fc.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -120,7 +121,7 @@ class CoTResNet(nn.Module):
         wp = F.pad(c1.weight, (0, 0, 0, 0, 0, pad)).contiguous(memory_format=torch.channels_last)
         return F.conv2d(xp, wp, c1.bias, c1.stride, c1.padding, c1.dilation, 1)
 
-    stem_pad = 8
+    stem_pad = int(os.environ.get("COTB200_STEM_PAD", "8"))
 
     def forward_features(self, x):
         if fused.supported(x):

@@ -83,43 +83,75 @@ __device__ __forceinline__ void g7_st_block(uint32_t sa, const T (&v)[72]) {
 }
 
 // ------------------------------------------------------------------------------------------------ statistics
-// gsum[b,g] += sum_{t,px} (l + lbias) ; gsq likewise.   grid (ceil(bps / TB), B), TB threads.
+// gsum[b,g] += sum_{t,px} (l + lbias) ; gsq likewise.   grid (X, B): CTA (x, b) walks the tiles x, x+X, .. of sample b with a
+// two-stage bulk-copy ring.  Thread = one block per tile; it keeps 72 per-COLUMN sums of the raw l and 8 per-group sums of
+// l^2, both by mixed-precision FMAs on the 16-bit operands (144 FHFMA + 9 LDS.128 per 144 bytes, no unpack, no per-element
+// bias loads); the bias enters analytically at the end:  sum (l+b) = S_j + n*b_j,  sum (l+b)^2 = Q_g + 2*sum_t b_j*S_j + n*b_j^2.
 template <typename T>
 __global__ void __launch_bounds__(G7<T>::TB)
 gn72_stats_kernel(const T* __restrict__ l, const float* __restrict__ lbias, float* __restrict__ gsum, float* __restrict__ gsq, GN72 g) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar[2];
   __shared__ float s_acc[2 * 64];                 // [2][wc <= 64]
-  __shared__ float s_lb[576];
   constexpr int TB = G7<T>::TB;
+  constexpr uint32_t TILE = TB * 72 * sizeof(T);
   const int tid = threadIdx.x, b = blockIdx.y;
-  const int blk0 = blockIdx.x * TB, nblk = min(TB, g.bps - blk0);
-  const uint32_t bytes = (uint32_t)nblk * 72u * sizeof(T);
+  const int ntiles = (g.bps + TB - 1) / TB;
+  const T* lb = l + (long long)b * g.bps * 72;
+  auto issue = [&](int tile, int stage) {
+    const int nblk = min(TB, g.bps - tile * TB);
+    const uint32_t bytes = (uint32_t)nblk * 72u * sizeof(T);
+    g7_expect_tx(g7_smem(&bar[stage]), bytes);
+    g7_bulk_load(g7_smem(smem) + stage * TILE, lb + (long long)tile * TB * 72, bytes, g7_smem(&bar[stage]));
+  };
   if (tid == 0) {
-    g7_mbar_init(g7_smem(&bar), 1);
-    g7_expect_tx(g7_smem(&bar), bytes);
-    g7_bulk_load(g7_smem(smem), l + ((long long)b * g.bps + blk0) * 72, bytes, g7_smem(&bar));
+    g7_mbar_init(g7_smem(&bar[0]), 1);
+    g7_mbar_init(g7_smem(&bar[1]), 1);
+    if ((int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
   }
   for (int i = tid; i < 2 * g.wc; i += TB) s_acc[i] = 0.f;
-  for (int j = tid; j < g.J; j += TB) s_lb[j] = lbias ? lbias[j] : 0.f;
   __syncthreads();
-  g7_wait(g7_smem(&bar), 0);
   const int chunk = tid % g.nchunk;               // TB % nchunk == 0 -> blk % nchunk == tid % nchunk
+  float S[72], Q[8];
+#pragma unroll
+  for (int j = 0; j < 72; ++j) S[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Q[i] = 0.f;
+  int npx = 0;                                    // blocks this thread accumulated
+  const T one = one_of<T>();
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int stage = it & 1;
+    if (tid == 0 && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, stage ^ 1);   // stage^1 was drained before the last sync
+    g7_wait(g7_smem(&bar[stage]), (it >> 1) & 1);
+    const int nblk = min(TB, g.bps - tile * TB);
+    if (tid < nblk) {
+      T v[72];
+      g7_ld_block<T>(g7_smem(smem) + stage * TILE + tid * 72 * (int)sizeof(T), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          S[i * 9 + t] = mfma<T>(v[i * 9 + t], one, S[i * 9 + t]);
+          Q[i] = mfma<T>(v[i * 9 + t], v[i * 9 + t], Q[i]);
+        }
+      ++npx;
+    }
+    __syncthreads();                              // everyone is done with `stage` before it is refilled two tiles later
+  }
+  // fold the bias in, then per-group sums
   float s[8], q[8];
+  const float n = (float)npx;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  if (tid < nblk) {
-    T v[72];
-    g7_ld_block<T>(g7_smem(smem) + tid * 72 * (int)sizeof(T), v);
-    const float* lb = s_lb + chunk * 72;
+  for (int i = 0; i < 8; ++i) {
+    float ss = 0.f, qq = Q[i];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const float f = to_acc(v[i * 9 + t]) + lb[i * 9 + t];
-        s[i] += f;
-        q[i] = fmaf(f, f, q[i]);
-      }
+    for (int t = 0; t < 9; ++t) {
+      const float bj = lbias ? lbias[chunk * 72 + i * 9 + t] : 0.f;
+      ss += S[i * 9 + t] + n * bj;
+      qq += bj * (2.f * S[i * 9 + t] + n * bj);
+    }
+    s[i] = ss; q[i] = qq;
   }
   // lanes with equal lane % nchunk hold the same chunk: butterfly over the remaining lane bits
   for (int off = 16; off >= g.nchunk; off >>= 1) {
@@ -241,38 +273,63 @@ gn72_bwd_sums_kernel(const T* __restrict__ dg, const T* __restrict__ l, float* _
   for (int i = tid; i < 3 * g.J; i += G7_SUM_THREADS) atomicAdd(Pb + i, s_p[i]);
 }
 
-// thread = (b, group): s1, s2 of the group, and its 9 columns' contributions to dgamma / dbeta / dlbias.
+// CTA = one group g, thread = sample b (strided): s1, s2 of (b, g) are written; the group's 9 columns of dgamma / dbeta /
+// dlbias are reduced over the batch inside the CTA (no same-address atomics: one CTA owns its 27 outputs).
 //   lhat_j = (l_j + lb_j - mean) * rstd:  sum dg*lhat = rstd*(P1 - m_j*P0),  sum lhat = rstd*(P2 - HW*m_j),  m_j = mean - lb_j
-__global__ void gn_bwd_finish_kernel(const float* __restrict__ P, int raw, const float* __restrict__ lbias, const float* __restrict__ mean,
-                                     const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ s1,
-                                     float* __restrict__ s2, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                     float* __restrict__ dlbias, int B, int HW, int wc) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * wc) return;
-  const int b = idx / wc, gi = idx - b * wc, J = 9 * wc;
-  const float mn = mean[idx], rs = rstd[idx];
-  const float* Pb = P + (long long)b * 3 * J;
-  float D[9], DL[9], LH[9], a = 0.f, q = 0.f;
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int j = gi * 9 + t;
-    const float m = mn - (lbias ? lbias[j] : 0.f);
-    D[t] = Pb[j];
-    DL[t] = raw ? rs * (Pb[J + j] - m * D[t]) : Pb[J + j];           // raw: sums over l, else already over lhat
-    LH[t] = raw ? rs * (Pb[2 * J + j] - (float)HW * m) : Pb[2 * J + j];
-    a = fmaf(D[t], gamma[j], a);
-    q = fmaf(DL[t], gamma[j], q);
-  }
-  s1[idx] = a;
-  s2[idx] = q;
+static constexpr int G7_FIN_THREADS = 256;
+__global__ void __launch_bounds__(G7_FIN_THREADS)
+gn_bwd_finish_kernel(const float* __restrict__ P, int raw, const float* __restrict__ lbias, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ s1,
+                     float* __restrict__ s2, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     float* __restrict__ dlbias, int B, int HW, int wc) {
+  __shared__ float s_red[G7_FIN_THREADS / 32][27];
+  const int gi = blockIdx.x, J = 9 * wc, tid = threadIdx.x;
   const float inv_n = 1.f / (9.f * (float)HW);
-  const float k1 = a * inv_n, k2 = q * inv_n;
+  float ga[9], lb[9], acc[27];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int j = gi * 9 + t;
-    atomicAdd(dbeta + j, D[t]);
-    atomicAdd(dgamma + j, DL[t]);
-    if (dlbias) atomicAdd(dlbias + j, rs * (gamma[j] * D[t] - (float)HW * k1 - k2 * LH[t]));
+  for (int t = 0; t < 9; ++t) { ga[t] = gamma[gi * 9 + t]; lb[t] = lbias ? lbias[gi * 9 + t] : 0.f; }
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  for (int b = tid; b < B; b += G7_FIN_THREADS) {
+    const int idx = b * wc + gi;
+    const float mn = mean[idx], rs = rstd[idx];
+    const float* Pb = P + (long long)b * 3 * J + gi * 9;
+    float D[9], DL[9], LH[9], a = 0.f, q = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float m = mn - lb[t];
+      D[t] = Pb[t];
+      DL[t] = raw ? rs * (Pb[J + t] - m * D[t]) : Pb[J + t];           // raw: sums over l, else already over lhat
+      LH[t] = raw ? rs * (Pb[2 * J + t] - (float)HW * m) : Pb[2 * J + t];
+      a = fmaf(D[t], ga[t], a);
+      q = fmaf(DL[t], ga[t], q);
+    }
+    s1[idx] = a;
+    s2[idx] = q;
+    const float k1 = a * inv_n, k2 = q * inv_n;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      acc[t] += D[t];
+      acc[9 + t] += DL[t];
+      acc[18 + t] += rs * (ga[t] * D[t] - (float)HW * k1 - k2 * LH[t]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 27; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((tid & 31) == 0) s_red[tid >> 5][i] = v;
+  }
+  __syncthreads();
+  if (tid < 27) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < G7_FIN_THREADS / 32; ++w) v += s_red[w][tid];
+    const int t = tid % 9, j = gi * 9 + t;
+    if (tid < 9) dbeta[j] += v;
+    else if (tid < 18) dgamma[j] += v;
+    else if (dlbias) dlbias[j] += v;
   }
 }
 
@@ -367,10 +424,15 @@ template <typename T>
 int gn72_stats_launch(int B, int HW, int wc, const void* l, const float* lbias, float* gsum, float* gsq, cudaStream_t st) {
   constexpr int TB = G7<T>::TB;
   const GN72 g = make_gn72(B, HW, wc, TB);
-  const size_t smem = (size_t)TB * 72 * sizeof(T);
+  const size_t smem = (size_t)2 * TB * 72 * sizeof(T);
   int rc = g7_smem_attr(gn72_stats_kernel<T>, smem);
   if (rc) return rc;
-  gn72_stats_kernel<T><<<dim3((g.bps + TB - 1) / TB, B), TB, smem, st>>>((const T*)l, lbias, gsum, gsq, g);
+  // walkers per sample: enough CTAs for ~4 per SM, never more than the sample has tiles
+  const int ntiles = (g.bps + TB - 1) / TB;
+  int X = (4 * num_sms() + B - 1) / B;
+  if (X > ntiles) X = ntiles;
+  if (X < 1) X = 1;
+  gn72_stats_kernel<T><<<dim3(X, B), TB, smem, st>>>((const T*)l, lbias, gsum, gsq, g);
   return check_launch("gn9_stats(gn72)");
 }
 
@@ -400,7 +462,7 @@ int gn72_bwd_sums_launch(int B, int HW, int wc, const void* dg, const void* l, f
 
 int gn_bwd_finish_launch(int B, int HW, int wc, const float* P, int raw, const float* lbias, const float* mean, const float* rstd,
                          const float* gamma, float* s1, float* s2, float* dgamma, float* dbeta, float* dlbias, cudaStream_t st) {
-  gn_bwd_finish_kernel<<<(B * wc + 127) / 128, 128, 0, st>>>(P, raw, lbias, mean, rstd, gamma, s1, s2, dgamma, dbeta, dlbias, B, HW, wc);
+  gn_bwd_finish_kernel<<<wc, G7_FIN_THREADS, 0, st>>>(P, raw, lbias, mean, rstd, gamma, s1, s2, dgamma, dbeta, dlbias, B, HW, wc);
   return check_launch("gn9_bwd_finish");
 }
 

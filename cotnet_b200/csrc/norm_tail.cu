@@ -103,6 +103,7 @@ tail_pool_kernel(const T* __restrict__ u, const T* __restrict__ k, const float* 
   for (int i = 0; i < VEC; ++i) { acc[0][i] = 0.f; sc[i] = active ? scale[tx * VEC + i] : 0.f; sh[i] = active ? shift[tx * VEC + i] : 0.f; }
   if (active) {
     const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+    #pragma unroll 2
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
       const Pack<T, VEC> kv = ld_pack<T, VEC>(k + base + (long long)r * g.C);
@@ -133,6 +134,7 @@ tail_combine_kernel(const T* __restrict__ u, const T* __restrict__ k, const floa
     a0[i] = a[((long long)b * g.C + c) * 2]; a1[i] = a[((long long)b * g.C + c) * 2 + 1];
   }
   const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+  #pragma unroll 2
   for (int r = r0 + ty; r < r1; r += g.ry) {
     const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
     const Pack<T, VEC> kv = ld_pack<T, VEC>(k + base + (long long)r * g.C);
@@ -161,6 +163,7 @@ tail_bwd_sums_kernel(const T* __restrict__ dout, const T* __restrict__ u, const 
   for (int i = 0; i < VEC; ++i) { acc[0][i] = acc[1][i] = 0.f; sc[i] = active ? scale[tx * VEC + i] : 0.f; sh[i] = active ? shift[tx * VEC + i] : 0.f; }
   if (active) {
     const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+    #pragma unroll 2
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> dv = ld_pack<T, VEC>(dout + base + (long long)r * g.C);
       const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
@@ -203,6 +206,7 @@ tail_bwd_dz_sums_kernel(const T* __restrict__ dout, const T* __restrict__ u, con
   }
   if (active) {
     const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+    #pragma unroll 2
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> dv = ld_pack<T, VEC>(dout + base + (long long)r * g.C);
       const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
@@ -244,6 +248,7 @@ tail_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ u, const
     k1[i] = c1 ? c1[c] * inv_n : 0.f; k2[i] = c2 ? c2[c] * inv_n : 0.f;
   }
   const long long base = ((long long)b * g.HW) * g.C + tx * VEC;
+  #pragma unroll 2
   for (int r = r0 + ty; r < r1; r += g.ry) {
     const Pack<T, VEC> dv = ld_pack<T, VEC>(dout + base + (long long)r * g.C);
     const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
