@@ -239,7 +239,7 @@ def main_reference(a):
 
 # ----------------------------------------------------------------------------------------------- our arm
 def main_ours(a):
-    from cotnet_b200 import _lib, backbone
+    from cotnet_b200 import _lib, backbone, fused
     from cotnet_b200 import dist as cdist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -282,6 +282,7 @@ def main_ours(a):
         return x, lab
 
     def fwd_bwd(x, lab):
+        fused.step_begin(dev)             # accumulator scratch of the fused kernels: one memset per step
         if flat is not None:
             flat.zero_()
         else:

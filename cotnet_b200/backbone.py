@@ -110,8 +110,9 @@ class CoTResNet(nn.Module):
 
     def _stem_conv(self, x):
         """conv1 (models/resnet.py:552: 7x7/s2, 3 -> 64) with the input and the weight zero-padded to `stem_pad` channels:
-        identical arithmetic, but a 3-channel NHWC tensor is 6-byte aligned and cuDNN falls back to legacy kernels for it
-        (1.5 ms fprop + 1.5 ms wgrad at bs256, 6 % of the step); 8 channels = 16-byte rows = the align8 tensor-core kernels."""
+        identical arithmetic.  MEASURED AND REJECTED (tools/bench_stem.py, profiles/r01_notes.md): cuDNN's 3-channel kernels take
+        2.67 ms fwd+wgrad at bs256, the padded variants 2.87 ms (4 ch) / 3.44 ms (8 ch) -- the pad/cast traffic costs more
+        than the aligned kernels gain.  Kept behind COTB200_STEM_PAD (default 0 = off) for other cuDNN versions."""
         C = x.shape[1]
         pad = self.stem_pad - C if (self.stem_pad and C < self.stem_pad and self.conv1.groups == 1) else 0
         if pad <= 0:
@@ -121,7 +122,7 @@ class CoTResNet(nn.Module):
         wp = F.pad(c1.weight, (0, 0, 0, 0, 0, pad)).contiguous(memory_format=torch.channels_last)
         return F.conv2d(xp, wp, c1.bias, c1.stride, c1.padding, c1.dilation, 1)
 
-    stem_pad = int(os.environ.get("COTB200_STEM_PAD", "8"))
+    stem_pad = int(os.environ.get("COTB200_STEM_PAD", "0"))
 
     def forward_features(self, x):
         if fused.supported(x):

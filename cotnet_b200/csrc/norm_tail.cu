@@ -271,16 +271,44 @@ tail_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ u, const
 // Training / eval BatchNorm2d on NHWC tensors as 2 + 2 HBM passes (col_stats + apply; bwd sums + bwd apply), replacing
 // ATen's channels_last batch-norm kernels (ncu: 4 kernels, ~0.65 TB/s on the stage-1 tensors).
 //   ACT: 0 none, 1 ReLU.   y = act(x*scale + shift (+ res))                  (models/cotnet.py:45-46,53-54,61-62,:248-262)
-template <typename T, int VEC, int ACT, bool RES>
+// FIN: the BatchNorm bookkeeping of bn_finalize_kernel is done in the prologue instead of a separate launch -- every thread
+// derives scale/shift of its own columns from the batch sums (4 loads + one rsqrt per column, nothing next to >= 64 rows of
+// streaming), CTA (0,0) also publishes scale/shift/mean/rstd for the backward and updates the running statistics.
+struct BnFin {
+  const float* sum; const float* sq; const float* weight; const float* bias;
+  float* running_mean; float* running_var;
+  float n, eps, momentum; int update_running;
+  float* scale; float* shift; float* mean; float* rstd;
+};
+
+template <typename T, int VEC, int ACT, bool RES, bool FIN>
 __global__ void __launch_bounds__(NT_THREADS)
 bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ scale,
-                const float* __restrict__ shift, T* __restrict__ y, RowsGeo g) {
+                const float* __restrict__ shift, T* __restrict__ y, RowsGeo g, BnFin f) {
   const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
   if (!(tx < g.cq && ty < g.ry)) return;
   const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
   float sc[VEC], sh[VEC];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) { sc[i] = scale[tx * VEC + i]; sh[i] = shift[tx * VEC + i]; }
+  for (int i = 0; i < VEC; ++i) {
+    const int c = tx * VEC + i;
+    if (FIN) {
+      const float mean = f.sum[c] / f.n;
+      const float var = fmaxf(f.sq[c] / f.n - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + f.eps);
+      sc[i] = (f.weight ? f.weight[c] : 1.f) * rstd;
+      sh[i] = (f.bias ? f.bias[c] : 0.f) - mean * sc[i];
+      if (blockIdx.x == 0 && blockIdx.y == 0 && ty == 0) {
+        f.scale[c] = sc[i]; f.shift[c] = sh[i]; f.mean[c] = mean; f.rstd[c] = rstd;
+        if (f.update_running) {
+          f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
+          f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * var * (f.n / fmaxf(f.n - 1.f, 1.f));
+        }
+      }
+    } else {
+      sc[i] = scale[c]; sh[i] = shift[c];
+    }
+  }
   const long long base = ((long long)b * g.HW) * g.ld + tx * VEC;
   for (int r = r0 + ty; r < r1; r += g.ry) {
     const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.ld);
@@ -873,37 +901,64 @@ extern "C" int cotb200_gn9_bwd_apply(int dtype, int B, int HW, int wc, int gc, c
   return 0;
 }
 
-extern "C" int cotb200_bn_apply(int dtype, int B, int HW, int C, const void* x, const void* res, const float* scale,
-                                const float* shift, int relu, void* y, void* stream) {
-  if (!x || !scale || !shift || !y) { set_error("bn_apply: NULL pointer"); return COTB200_ENULL; }
-  if (dtype == COTB200_F64) { set_error("bn_apply: fp64 not supported"); return COTB200_EDTYPE; }
-  { const long long rows = (long long)B * HW; if (rows > 2147483647LL) { set_error("cotb200_bn_apply: too many rows"); return COTB200_ETOOBIG; }
-    HW = (int)rows; B = 1; }      // per-channel statistics: flatten [B, HW] -> rows
+#define BN_APPLY_LAUNCH(ACT, RES, FIN) bn_apply_kernel<T, V, ACT, RES, FIN><<<NT_GRID, NT_THREADS, 0, st>>>(xp, rp, scp, shp, yp, g, f)
+static int bn_apply_impl(const char* what, int dtype, int B, int HW, int C, const void* x, const void* res, const float* scale,
+                         const float* shift, int relu, void* y, const BnFin* fin, void* stream) {
+  if (dtype == COTB200_F64) { set_error("%s: fp64 not supported", what); return COTB200_EDTYPE; }
+  { const long long rows = (long long)B * HW; if (rows > 2147483647LL) { set_error("%s: too many rows", what); return COTB200_ETOOBIG; }
+    HW = (int)rows; B = 1; }      // per-channel affine: flatten [B, HW] -> rows
   cudaStream_t st = (cudaStream_t)stream;
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
       const int vec = pick_vec<T>(C, x, res, y);
       const int cw = col_chunk(C, vec);
-      if (!cw) { set_error("bn_apply: cannot tile %d channels", C); return COTB200_EINVAL; }
+      if (!cw) { set_error("%s: cannot tile %d channels", what, C); return COTB200_EINVAL; }
       for (int c0 = 0; c0 < C; c0 += cw) {
         RowsGeo g; size_t smem;
         int rc = make_geo(g, B, HW, cw, vec, 1, &smem);
         if (rc) return rc;
         g.ld = C;
         const T* xp = (const T*)x + c0; const T* rp = res ? (const T*)res + c0 : nullptr; T* yp = (T*)y + c0;
-        COTB200_PROF_B("bn_apply", (double)B * HW * cw * (2 + (res ? 1 : 0)) * sizeof(T));
+        BnFin f{};
+        if (fin) {
+          f = *fin;
+          f.sum += c0; f.sq += c0; if (f.weight) f.weight += c0; if (f.bias) f.bias += c0;
+          if (f.running_mean) f.running_mean += c0; if (f.running_var) f.running_var += c0;
+          f.scale += c0; f.shift += c0; f.mean += c0; f.rstd += c0;
+        }
+        const float* scp = scale ? scale + c0 : nullptr; const float* shp = shift ? shift + c0 : nullptr;
+        COTB200_PROF_B(fin ? "bn_apply_batch" : "bn_apply", (double)B * HW * cw * (2 + (res ? 1 : 0)) * sizeof(T));
         NT_DISPATCH_VEC(vec, {
-          if (relu) { if (res) bn_apply_kernel<T, V, 1, true><<<NT_GRID, NT_THREADS, 0, st>>>(xp, rp, scale + c0, shift + c0, yp, g);
-                      else bn_apply_kernel<T, V, 1, false><<<NT_GRID, NT_THREADS, 0, st>>>(xp, nullptr, scale + c0, shift + c0, yp, g); }
-          else { if (res) bn_apply_kernel<T, V, 0, true><<<NT_GRID, NT_THREADS, 0, st>>>(xp, rp, scale + c0, shift + c0, yp, g);
-                 else bn_apply_kernel<T, V, 0, false><<<NT_GRID, NT_THREADS, 0, st>>>(xp, nullptr, scale + c0, shift + c0, yp, g); }
+          if (fin) {
+            if (relu) { if (res) BN_APPLY_LAUNCH(1, true, true); else BN_APPLY_LAUNCH(1, false, true); }
+            else { if (res) BN_APPLY_LAUNCH(0, true, true); else BN_APPLY_LAUNCH(0, false, true); }
+          } else {
+            if (relu) { if (res) BN_APPLY_LAUNCH(1, true, false); else BN_APPLY_LAUNCH(1, false, false); }
+            else { if (res) BN_APPLY_LAUNCH(0, true, false); else BN_APPLY_LAUNCH(0, false, false); }
+          }
         });
-        if ((rc = check_launch("bn_apply"))) return rc;
+        if ((rc = check_launch(what))) return rc;
       }
       return 0;
     }
   });
   return 0;
+}
+
+extern "C" int cotb200_bn_apply(int dtype, int B, int HW, int C, const void* x, const void* res, const float* scale,
+                                const float* shift, int relu, void* y, void* stream) {
+  if (!x || !scale || !shift || !y) { set_error("bn_apply: NULL pointer"); return COTB200_ENULL; }
+  return bn_apply_impl("bn_apply", dtype, B, HW, C, x, res, scale, shift, relu, y, nullptr, stream);
+}
+
+extern "C" int cotb200_bn_apply_batch(int dtype, int B, int HW, int C, const void* x, const void* res, const float* sum,
+                                      const float* sq, const float* weight, const float* bias, float* running_mean,
+                                      float* running_var, float n, float eps, float momentum, int update_running, int relu,
+                                      void* y, float* scale, float* shift, float* mean, float* rstd, void* stream) {
+  if (!x || !y || !sum || !sq || !scale || !shift || !mean || !rstd) { set_error("bn_apply_batch: NULL pointer"); return COTB200_ENULL; }
+  if (update_running && (!running_mean || !running_var)) { set_error("bn_apply_batch: running buffers missing"); return COTB200_ENULL; }
+  BnFin f{sum, sq, weight, bias, running_mean, running_var, n, eps, momentum, update_running, scale, shift, mean, rstd};
+  return bn_apply_impl("bn_apply_batch", dtype, B, HW, C, x, res, nullptr, nullptr, relu, y, &f, stream);
 }
 
 extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y, const float* mu,

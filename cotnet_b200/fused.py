@@ -16,6 +16,63 @@ from torch.autograd import Function
 from . import _lib
 
 
+class _ZeroArena:
+    """Pre-zeroed fp32 scratch for the kernels' accumulators (column sums, pooled sums, ...).  Every fused function needs a
+    few KB of zeros per call; as torch.zeros that is ~370 fill launches per CoTNet-50 step.  A trainer that calls
+    `fused.step_begin()` once per step gets them as slices of one buffer that is cleared by ONE memset of the part the
+    previous step used.  Without step_begin() (or when the arena is exhausted) this is plain torch.zeros."""
+    SIZE = 8 << 20                     # floats (32 MB)
+
+    def __init__(self):
+        self.buf = {}                  # device -> [buffer, used]
+        self.active = False
+
+    def begin(self, device):
+        ent = self.buf.get(device)
+        if ent is None:
+            ent = [torch.zeros(self.SIZE, dtype=torch.float32, device=device), 0]
+            self.buf[device] = ent
+        elif ent[1]:
+            ent[0][:ent[1]].zero_()
+        ent[1] = 0
+        self.active = True
+
+    def take(self, n, device):
+        ent = self.buf.get(device) if self.active else None
+        if ent is None:
+            return None
+        n4 = (n + 3) & ~3              # keep 16-byte alignment of every slice
+        if ent[1] + n4 > self.SIZE:
+            return None
+        out = ent[0][ent[1]:ent[1] + n]
+        ent[1] += n4
+        return out
+
+
+_ARENA = _ZeroArena()
+
+
+def step_begin(device=None):
+    """Call once at the start of every training step (before the forward): recycles the accumulator scratch."""
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    _ARENA.begin(torch.device(device))
+
+
+def step_arena_off():
+    _ARENA.active = False
+
+
+def _zeros(shape, device):
+    n = 1
+    for d in shape:
+        n *= int(d)
+    t = _ARENA.take(n, torch.device(device)) if n else None
+    if t is None:
+        return torch.zeros(*shape, dtype=torch.float32, device=device)
+    return t.view(*shape)
+
+
 def _is_cl(t):
     return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
 
@@ -28,13 +85,8 @@ def _f32(t):
     return t.detach().float().contiguous()
 
 
-def _bn_prepare(bn, weight, bias, C, n, sums, device, st):
-    """[4, C] fp32 = (scale, shift, mean, rstd) in ONE launch (cotb200_bn_finalize).  `sums` = [2, C] column sums of the
-    batch (training mode) or None (eval: running statistics).  Training updates the module's running buffers exactly like
-    nn.BatchNorm2d (momentum, unbiased variance, num_batches_tracked)."""
-    lib = _lib.load()
-    out = torch.empty(4, C, dtype=torch.float32, device=device)
-    use_batch = sums is not None
+def _bn_running(bn, use_batch):
+    """Bookkeeping shared by the two finalize routes: bumps num_batches_tracked, returns (update, momentum, rm, rv, copy_back)."""
     update = bool(use_batch and bn.running_mean is not None and bn.track_running_stats)
     mom = 0.0
     rm = rv = None
@@ -46,16 +98,31 @@ def _bn_prepare(bn, weight, bias, C, n, sums, device, st):
         rm, rv = bn.running_mean, bn.running_var
         if rm.dtype != torch.float32:
             rm, rv = rm.float(), rv.float()
+    return update, mom, rm, rv
+
+
+def _bn_running_writeback(bn, update, rm, rv):
+    if update and rm is not bn.running_mean:
+        with torch.no_grad():
+            bn.running_mean.copy_(rm)
+            bn.running_var.copy_(rv)
+
+
+def _bn_prepare(bn, weight, bias, C, n, sums, device, st):
+    """[4, C] fp32 = (scale, shift, mean, rstd) in ONE launch (cotb200_bn_finalize).  `sums` = [2, C] column sums of the
+    batch (training mode) or None (eval: running statistics).  Training updates the module's running buffers exactly like
+    nn.BatchNorm2d (momentum, unbiased variance, num_batches_tracked)."""
+    lib = _lib.load()
+    out = torch.empty(4, C, dtype=torch.float32, device=device)
+    use_batch = sums is not None
+    update, mom, rm, rv = _bn_running(bn, use_batch)
     w32 = None if weight is None else weight.detach().float().contiguous()
     b32 = None if bias is None else bias.detach().float().contiguous()
     _lib.check(lib.cotb200_bn_finalize(C, _lib.ptr(sums[0]) if use_batch else None, _lib.ptr(sums[1]) if use_batch else None,
                                        _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(rm), _lib.ptr(rv), float(n), float(bn.eps),
                                        float(mom), 1 if use_batch else 0, 1 if update else 0, out[0].data_ptr(),
                                        out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), st), "bn_finalize")
-    if update and rm is not bn.running_mean:
-        with torch.no_grad():
-            bn.running_mean.copy_(rm)
-            bn.running_var.copy_(rv)
+    _bn_running_writeback(bn, update, rm, rv)
     return out
 
 
@@ -63,7 +130,7 @@ def _bn_batch_stats(x, bn, weight, bias, lib, st, dt):
     """Statistics pass (training) + finalize -> ([4,C] scale/shift/mean/rstd, used_batch_stats)."""
     B, C, H, W = x.shape
     if bn.training or bn.running_mean is None:
-        sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)
+        sums = _zeros((2, C,), x.device)
         _lib.check(lib.cotb200_col_stats(dt, B, H * W, C, x.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), st), "col_stats")
         return _bn_prepare(bn, weight, bias, C, float(B * H * W), sums, x.device, st), True
     return _bn_prepare(bn, weight, bias, C, float(B * H * W), None, x.device, st), False
@@ -81,10 +148,25 @@ class BNActFn(Function):
         B, C, H, W = x.shape
         lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.dtype_code(x)
         x = x.detach()
-        ss, batch = _bn_batch_stats(x, bn, weight, bias, lib, st, dt)      # [4,C]: scale, shift, mean, rstd
         y = torch.empty_like(x, memory_format=torch.channels_last)
-        _lib.check(lib.cotb200_bn_apply(dt, B, H * W, C, x.data_ptr(), _lib.ptr(res), ss[0].data_ptr(), ss[1].data_ptr(),
-                                        1 if relu else 0, y.data_ptr(), st), "bn_apply")
+        batch = bool(bn.training or bn.running_mean is None)
+        if batch:       # training: column sums, then ONE kernel that finalises the statistics in its prologue and applies them
+            sums = _zeros((2, C,), x.device)
+            _lib.check(lib.cotb200_col_stats(dt, B, H * W, C, x.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), st), "col_stats")
+            ss = torch.empty(4, C, dtype=torch.float32, device=x.device)      # [4,C]: scale, shift, mean, rstd
+            update, mom, rm, rv = _bn_running(bn, True)
+            w32 = None if weight is None else weight.detach().float().contiguous()
+            b32 = None if bias is None else bias.detach().float().contiguous()
+            _lib.check(lib.cotb200_bn_apply_batch(dt, B, H * W, C, x.data_ptr(), _lib.ptr(res), sums[0].data_ptr(), sums[1].data_ptr(),
+                                                  _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(rm), _lib.ptr(rv), float(B * H * W),
+                                                  float(bn.eps), float(mom), 1 if update else 0, 1 if relu else 0, y.data_ptr(),
+                                                  ss[0].data_ptr(), ss[1].data_ptr(), ss[2].data_ptr(), ss[3].data_ptr(), st),
+                       "bn_apply_batch")
+            _bn_running_writeback(bn, update, rm, rv)
+        else:
+            ss = _bn_prepare(bn, weight, bias, C, float(B * H * W), None, x.device, st)
+            _lib.check(lib.cotb200_bn_apply(dt, B, H * W, C, x.data_ptr(), _lib.ptr(res), ss[0].data_ptr(), ss[1].data_ptr(),
+                                            1 if relu else 0, y.data_ptr(), st), "bn_apply")
         ctx.save_for_backward(x, y if relu else None, ss)
         ctx.cfg = (relu, batch, res is not None, weight.dtype, bias.dtype)
         return y
@@ -98,7 +180,7 @@ class BNActFn(Function):
         dy = dy.contiguous(memory_format=torch.channels_last)
         sums = None
         if batch or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)
+            sums = _zeros((2, C,), x.device)
             _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), x.data_ptr(), _lib.ptr(y), ss[2].data_ptr(),
                                                ss[3].data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
                        "bn_bwd_sums")
@@ -131,7 +213,7 @@ class GroupNorm9Fn(Function):
         lib, st, dt = _lib.load(), _lib.stream_ptr(l), _lib.dtype_code(l)
         l = l.detach()
         lb32 = None if lbias is None else _f32(lbias)
-        stats = torch.zeros(2, B, wc, dtype=torch.float32, device=l.device)
+        stats = _zeros((2, B, wc,), l.device)
         _lib.check(lib.cotb200_gn9_stats(dt, B, HW, wc, gc, l.data_ptr(), _lib.ptr(lb32), stats[0].data_ptr(),
                                          stats[1].data_ptr(), st), "gn9_stats")
         fin = torch.empty(4, B * wc, dtype=torch.float32, device=l.device)      # (rstd, -mean*rstd, mean, rstd)
@@ -156,7 +238,7 @@ class GroupNorm9Fn(Function):
         dg = dg.contiguous(memory_format=torch.channels_last)
         lib, st, dt = _lib.load(), _lib.stream_ptr(l), _lib.dtype_code(l)
         sums = torch.empty(2, B, wc, dtype=torch.float32, device=l.device)      # s1, s2 (written)
-        acc = torch.zeros(3 * J + 3 * B * J, dtype=torch.float32, device=l.device)   # dgamma, dbeta, dlbias | work [B,3,J]
+        acc = _zeros((3 * J + 3 * B * J,), l.device)   # dgamma, dbeta, dlbias | work [B,3,J]
         dgb, work = acc[:3 * J].view(3, J), acc[3 * J:]
         want_db = lb32 is not None and ctx.needs_input_grad[5]
         _lib.check(lib.cotb200_gn9_bwd_sums(dt, B, HW, wc, ctx.gc, dg.data_ptr(), l.data_ptr(), _lib.ptr(lb32), mean.data_ptr(),
@@ -244,7 +326,7 @@ class CotTailFn(Function):
         u, k = u.detach(), k.detach()
         ss, training = _bn_batch_stats(u, bn, bn_weight, bn_bias, lib, st, dt)     # [4,C]: scale, shift, mean, rstd
         scale, shift, mean, rstd = ss[0], ss[1], ss[2], ss[3]
-        psum = torch.zeros(B, C, dtype=torch.float32, device=u.device)
+        psum = _zeros((B, C,), u.device)
         _lib.check(lib.cotb200_tail_pool(dt, B, HW, C, u.data_ptr(), k.data_ptr(), scale.data_ptr(), shift.data_ptr(),
                                          psum.data_ptr(), st), "tail_pool")
         # the SE MLP on [B, C] (3 tiny GEMV-sized ops) stays PyTorch; its graph is kept for backward
@@ -271,13 +353,13 @@ class CotTailFn(Function):
         HW, n = H * W, float(B * H * W)
         lib, st, dt = _lib.load(), _lib.stream_ptr(u), _lib.dtype_code(u)
         dout = dout.contiguous(memory_format=torch.channels_last)
-        S = torch.zeros(B, C, 2, dtype=torch.float32, device=u.device)
+        S = _zeros((B, C, 2,), u.device)
         _lib.check(lib.cotb200_tail_bwd_sums(dt, B, HW, C, dout.data_ptr(), u.data_ptr(), k.data_ptr(), scale.data_ptr(),
                                              shift.data_ptr(), S.data_ptr(), st), "tail_bwd_sums")
         grads = torch.autograd.grad(a, [p_leaf] + se_params, grad_outputs=S, allow_unused=True)
         dpn = grads[0].contiguous()                      # d/d(pooled mean); the kernels apply the 1/HW (pscale)
         se_grads = [None if g is None else g for g in grads[1:]]
-        sums = torch.zeros(2, C, dtype=torch.float32, device=u.device)
+        sums = _zeros((2, C,), u.device)
         need_param = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         if ctx.training or need_param:
             _lib.check(lib.cotb200_tail_bwd_dz_sums(dt, B, HW, C, dout.data_ptr(), u.data_ptr(), scale.data_ptr(), shift.data_ptr(),
@@ -384,27 +466,31 @@ def tap_chunk(wc, fold=1):
 
 def _se_fp32(se, p):
     """models/cotnet.py:69-77 on p [B, C] in fp32: conv1x1 -> BatchNorm2d -> ReLU -> conv1x1, using (and updating) the
-    module's parameters / buffers; differentiable w.r.t. p and the parameters."""
+    module's parameters / buffers; differentiable w.r.t. p and the parameters.  The BatchNorm is ONE fused ATen kernel each
+    way (F.batch_norm on private copies of the running buffers -- autograd saves those copies, so updating the module's
+    own buffers afterwards cannot invalidate the graph); the whole MLP is ~10 launches forward, ~10 backward."""
+    F = torch.nn.functional
     c0, b1, c3 = se[0], se[1], se[3]
-    z = torch.nn.functional.linear(p, c0.weight.float().flatten(1), None if c0.bias is None else c0.bias.float())
+    z = F.linear(p, c0.weight.float().flatten(1), None if c0.bias is None else c0.bias.float())
     w1, bb1 = b1.weight.float(), b1.bias.float()
     if b1.training or b1.running_mean is None:
-        # batch statistics written out with differentiable torch ops (no in-place update of tensors autograd saved)
-        n = z.shape[0]
-        mean = z.mean(0)
-        var = z.var(0, unbiased=False)
-        zn = (z - mean) * torch.rsqrt(var + b1.eps) * w1 + bb1
-        if b1.running_mean is not None and b1.track_running_stats:
+        track = b1.running_mean is not None and b1.track_running_stats
+        rm = rv = None
+        mom = 0.0
+        if track:
             with torch.no_grad():
                 b1.num_batches_tracked += 1
                 mom = b1.momentum if b1.momentum is not None else 1.0 / float(b1.num_batches_tracked)
-                b1.running_mean.mul_(1 - mom).add_(mean.detach().to(b1.running_mean.dtype), alpha=mom)
-                b1.running_var.mul_(1 - mom).add_((var.detach() * (n / max(n - 1.0, 1.0))).to(b1.running_var.dtype), alpha=mom)
-        z = zn
+                rm, rv = b1.running_mean.float().clone(), b1.running_var.float().clone()
+        z = F.batch_norm(z, rm, rv, w1, bb1, True, mom, b1.eps)
+        if track:
+            with torch.no_grad():
+                b1.running_mean.copy_(rm)
+                b1.running_var.copy_(rv)
     else:
-        z = (z - b1.running_mean.float()) * torch.rsqrt(b1.running_var.float() + b1.eps) * w1 + bb1
+        z = F.batch_norm(z, b1.running_mean.float(), b1.running_var.float(), w1, bb1, False, 0.0, b1.eps)
     z = torch.relu(z)
-    return torch.nn.functional.linear(z, c3.weight.float().flatten(1), None if c3.bias is None else c3.bias.float())
+    return F.linear(z, c3.weight.float().flatten(1), None if c3.bias is None else c3.bias.float())
 
 
 def group_norm9(l, gn: torch.nn.GroupNorm, gc=0, lbias=None):
@@ -468,7 +554,7 @@ class TcConv1x1Fn(Function):
             _tc.gemm_bf16(a1, b1, a2, b2, shift=None if cbias is None else cbias.detach().float().contiguous(), relu=relu, out=out2d)
         elif bn.training or bn.running_mean is None:
             batch = True
-            sums = torch.zeros(2, N, dtype=torch.float32, device=a1.device)
+            sums = _zeros((2, N,), a1.device)
             pre = torch.empty_like(out, memory_format=torch.channels_last)
             _tc.gemm_bf16(a1, b1, a2, b2, stats=(sums[0], sums[1]), out=_rows2d(pre))
             scale, shift, mean, rstd = _bn_from_sums(sums, float(M), bn, bn_w, bn_b)
@@ -496,7 +582,7 @@ class TcConv1x1Fn(Function):
         dy = dy.contiguous(memory_format=torch.channels_last)
         dgamma = dbeta = dcb = None
         if has_bn:
-            sums = torch.zeros(2, N, dtype=torch.float32, device=dy.device)
+            sums = _zeros((2, N,), dy.device)
             _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), mean.data_ptr(),
                                                rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
                        "bn_bwd_sums")
@@ -543,7 +629,7 @@ class TcConv3x3Fn(Function):
         pre = None
         batch = bn.training or bn.running_mean is None
         if batch:
-            sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)
+            sums = _zeros((2, C,), x.device)
             pre = torch.empty_like(x, memory_format=torch.channels_last)
             _tc.conv3x3_bf16(x, wp, bnt, stats=(sums[0], sums[1]), out=pre)
             scale, shift, mean, rstd = _bn_from_sums(sums, float(M), bn, bn_w, bn_b)
@@ -566,7 +652,7 @@ class TcConv3x3Fn(Function):
         M = B * H * W
         lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.BF16
         dy = dy.contiguous(memory_format=torch.channels_last)
-        sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)
+        sums = _zeros((2, C,), x.device)
         _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), mean.data_ptr(),
                                            rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
                    "bn_bwd_sums")

@@ -129,6 +129,13 @@ int cotb200_tail_bwd_apply(int dtype, int B, int HW, int C, const void* dout, co
  * bottleneck (models/cotnet.py:231-235,:249-262) in 2 forward + 2 backward HBM passes.  relu: 0/1; res may be NULL. */
 int cotb200_bn_apply(int dtype, int B, int HW, int C, const void* x, const void* res, const float* scale,
                      const float* shift, int relu, void* y, void* stream);
+/* Training-mode variant: the bookkeeping of cotb200_bn_finalize folded into the apply kernel's prologue (one launch less per
+ * BatchNorm): scale/shift are derived from the batch sums of cotb200_col_stats (n rows), scale/shift/mean/rstd [C] are
+ * written for the backward, the running statistics updated when update_running (momentum, unbiased variance). */
+int cotb200_bn_apply_batch(int dtype, int B, int HW, int C, const void* x, const void* res, const float* sum, const float* sq,
+                           const float* weight, const float* bias, float* running_mean, float* running_var, float n,
+                           float eps, float momentum, int update_running, int relu, void* y, float* scale, float* shift,
+                           float* mean, float* rstd, void* stream);
 /* dz = dy*[y>0] (relu) ; sum_dz[c] += sum dz ; sum_dzx[c] += sum dz*xhat      (y may be NULL when relu == 0) */
 int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y, const float* mu,
                         const float* rstd, int relu, float* sum_dz, float* sum_dzx, void* stream);
