@@ -180,7 +180,7 @@ class BNActFn(Function):
         dy = dy.contiguous(memory_format=torch.channels_last)
         sums = None
         if batch or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            sums = _zeros((2, C,), x.device)
+            sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)       # escapes as dgamma/dbeta: not from the arena
             _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), x.data_ptr(), _lib.ptr(y), ss[2].data_ptr(),
                                                ss[3].data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
                        "bn_bwd_sums")
@@ -238,8 +238,8 @@ class GroupNorm9Fn(Function):
         dg = dg.contiguous(memory_format=torch.channels_last)
         lib, st, dt = _lib.load(), _lib.stream_ptr(l), _lib.dtype_code(l)
         sums = torch.empty(2, B, wc, dtype=torch.float32, device=l.device)      # s1, s2 (written)
-        acc = _zeros((3 * J + 3 * B * J,), l.device)   # dgamma, dbeta, dlbias | work [B,3,J]
-        dgb, work = acc[:3 * J].view(3, J), acc[3 * J:]
+        dgb = torch.zeros(3, J, dtype=torch.float32, device=l.device)            # dgamma, dbeta, dlbias (escape)
+        work = _zeros((3 * B * J,), l.device)                                     # per-sample column partials
         want_db = lb32 is not None and ctx.needs_input_grad[5]
         _lib.check(lib.cotb200_gn9_bwd_sums(dt, B, HW, wc, ctx.gc, dg.data_ptr(), l.data_ptr(), _lib.ptr(lb32), mean.data_ptr(),
                                             rstd.data_ptr(), g32.data_ptr(), work.data_ptr(), sums[0].data_ptr(),
@@ -359,7 +359,7 @@ class CotTailFn(Function):
         grads = torch.autograd.grad(a, [p_leaf] + se_params, grad_outputs=S, allow_unused=True)
         dpn = grads[0].contiguous()                      # d/d(pooled mean); the kernels apply the 1/HW (pscale)
         se_grads = [None if g is None else g for g in grads[1:]]
-        sums = _zeros((2, C,), u.device)
+        sums = torch.zeros(2, C, dtype=torch.float32, device=u.device)          # escapes as dgamma/dbeta
         need_param = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         if ctx.training or need_param:
             _lib.check(lib.cotb200_tail_bwd_dz_sums(dt, B, HW, C, dout.data_ptr(), u.data_ptr(), scale.data_ptr(), shift.data_ptr(),
@@ -582,7 +582,7 @@ class TcConv1x1Fn(Function):
         dy = dy.contiguous(memory_format=torch.channels_last)
         dgamma = dbeta = dcb = None
         if has_bn:
-            sums = _zeros((2, N,), dy.device)
+            sums = torch.zeros(2, N, dtype=torch.float32, device=dy.device)      # escapes as dgamma/dbeta
             _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), mean.data_ptr(),
                                                rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
                        "bn_bwd_sums")
@@ -652,7 +652,7 @@ class TcConv3x3Fn(Function):
         M = B * H * W
         lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.BF16
         dy = dy.contiguous(memory_format=torch.channels_last)
-        sums = _zeros((2, C,), x.device)
+        sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)          # escapes as dgamma/dbeta
         _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), mean.data_ptr(),
                                            rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
                    "bn_bwd_sums")
