@@ -243,6 +243,7 @@ def main_ours(a):
     from cotnet_b200 import dist as cdist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout = the one JSON line even if NCCL_DEBUG is set
     rank, local_rank, world = cdist.init_from_env()
     if world != a.gpus and world > 1:
         a.gpus = world
@@ -445,7 +446,7 @@ def main_ours(a):
                                    "enclosing bottleneck; convolutions: cuDNN (training) / tcgen05 (inference path)"},
             "e2e": e2e, "gpu_launches": int(launches), "launch_mode": graph_info, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0

@@ -128,6 +128,66 @@ def test_backbone_matches_oracle_model_fp32():
     assert torch.allclose(got_cl.cpu(), want, atol=1e-3, rtol=1e-3)
 
 
+def test_cotnext_backbone_matches_oracle_model_fp32():
+    """BASELINE.json configs[2]: CoTNeXt-50 (CoXtLayer: grouped convs + the folded LocalConv), eval logits vs the CPU oracle."""
+    from cotnet_b200 import backbone
+    from oracle import cot_model_ref
+    torch.manual_seed(1)
+    m = backbone.MODELS["cotnext50_2x48d"]()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            torch.nn.init.uniform_(mod.weight, 0.3, 0.7)
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.8, 1.2)
+    o = cot_model_ref.build("cotnext50_2x48d")
+    o.load_reference_state(m.state_dict())
+    x = torch.randn(2, 3, 96, 96)
+    o.eval()
+    with torch.no_grad():
+        want = o(x)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        got = m(x.cuda())
+        got_cl = m.to(memory_format=torch.channels_last)(x.cuda().contiguous(memory_format=torch.channels_last))
+    assert torch.allclose(got.cpu(), want, atol=1e-3, rtol=1e-3)
+    assert torch.allclose(got_cl.cpu(), want, atol=1e-3, rtol=1e-3)
+
+
+def test_backbone_training_step_matches_oracle_fp32():
+    """The whole fused training path (fused BatchNorm(+ReLU,+residual), pooling kernels, CoT layers with bias-folded
+    GroupNorm and one-pass gradient fan-in) end to end: loss and parameter gradients of one CoTNet-50 step, fp32
+    channels_last, against the CPU oracle model on the same weights and batch."""
+    from cotnet_b200 import backbone
+    from oracle import cot_model_ref
+    torch.manual_seed(2)
+    m = backbone.cotnet50()
+    o = cot_model_ref.build("cotnet50")
+    o.load_reference_state(m.state_dict())
+    x = torch.randn(8, 3, 96, 96)
+    y = torch.randint(0, 1000, (8,))
+    o.train()
+    lo = torch.nn.functional.cross_entropy(o(x), y)
+    lo.backward()
+    want = {k.replace("__", "."): p.grad for k, p in o.named_parameters() if p.grad is not None}   # oracle flattens CoT params
+    m = m.cuda().to(memory_format=torch.channels_last).train()
+    lg = torch.nn.functional.cross_entropy(m(x.cuda().contiguous(memory_format=torch.channels_last)), y.cuda())
+    lg.backward()
+    assert abs(lg.item() - lo.item()) <= 1e-3 * max(1.0, abs(lo.item())), (lg.item(), lo.item())
+    got = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    assert set(got) == set(want)
+    worst = ("", 0.0)
+    for k in want:
+        rel = ((got[k].detach().cpu().double() - want[k].double()).norm() / want[k].double().norm().clamp_min(1e-12)).item()
+        if rel > worst[1]:
+            worst = (k, rel)
+    assert worst[1] <= 2e-2, "largest relative L2 gradient error %.3e at %s" % (worst[1], worst[0])
+    # running statistics of a CoT-internal and a trunk BatchNorm moved like the oracle's
+    so, sm = {k.replace("__", "."): v for k, v in o.state_dict().items()}, m.state_dict()
+    for k in ("bn1.running_mean", "layer1.0.conv2.bn.running_var", "layer4.2.conv2.embed.1.running_mean"):
+        if k in so and k in sm:
+            assert torch.allclose(sm[k].cpu(), so[k].to(sm[k].dtype), atol=1e-4, rtol=1e-3), k
+
+
 @pytest.mark.parametrize("dim,H", [(64, 28), (128, 14), (256, 14), (512, 7)])
 def test_tc_training_backend_vs_oracle(dim, H):
     """train_conv_backend='tc': every convolution of the block on the tcgen05 kernels, forward + backward, vs the oracle."""
