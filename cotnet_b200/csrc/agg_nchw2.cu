@@ -8,6 +8,7 @@
 //   * interior fast path without any predication, edge path with zero fill;
 //   * bf16/fp16 use the mixed-precision FMA (fma.rn.f32.bf16 -> SASS FHFMA), no unpack instructions.
 // Requires W % PXV == 0 (56, 28 -> 4; 14 -> 2); other widths use the first-generation scalar kernels.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace cotb200 {
@@ -66,6 +67,7 @@ __device__ __forceinline__ void nchw2_fwd_body(const T* __restrict__ xp, const T
         if (!((unsigned)(h + dh) < (unsigned)H && (unsigned)(w0 + i + dw) < (unsigned)W)) wt[t].v[i] = Elem<T>::from(0.f);
     }
   }
+#pragma unroll 2
   for (int j = 0; j < rep; ++j) {
     float acc[PXV];
 #pragma unroll
@@ -179,8 +181,9 @@ __device__ __forceinline__ void nchw2_bwd_body(const T* __restrict__ dp, const T
   }
 }
 
+// 2 CTAs per SM: the fused dX+dW variant otherwise takes 130 (bf16) registers -> one 8-warp CTA per SM, latency-bound
 template <typename T, int PXV, bool DX, bool DW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 agg3_bwd_nchw2_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ dx,
                       T* __restrict__ dw, int C, int H, int W, int wc, int rep, long long dy_sn) {
   const int HW = H * W, WQ = W / PXV;
@@ -237,8 +240,15 @@ int nchw2_bwd(int N, int C, int H, int W, int wc, long long dy_sn, const T* dy, 
     dim3 grid((H * (W / pxv) + 255) / 256, N * wc);
     const int rep = C / wc;
     COTB200_PROF_B(dx && dw ? "agg3_bwd_nchw2_dxdw" : (dx ? "agg3_bwd_nchw2_dx" : "agg3_bwd_nchw2_dw"), ((double)N * H * W) * ((dx && dw ? 3.0 : 2.0) * C + (dx && dw ? 18.0 : 9.0) * wc) * sizeof(T));
+    // fp32: the fused kernel needs 170+ registers (1 CTA/SM, or spills when capped) -- two launches that re-read dY win
+    // (measured against the reference's kernels: profiles/r01_bench_ref_kernels_*.json); 16-bit types stay fused.
+    static int split_env = -1;
+    if (split_env < 0) { const char* e = getenv("COTB200_NCHW_SPLIT"); split_env = (e && e[0] == '0') ? 0 : 1; }
+    const bool split = split_env && sizeof(T) == 4 && dx && dw;
 #define NCHW2_LAUNCH(P)                                                                                              \
-  if (dx && dw) agg3_bwd_nchw2_kernel<T, P, true, true><<<grid, 256, 0, st>>>(dy, x, w, dx, dw, C, H, W, wc, rep, dy_sn); \
+  if (split) { agg3_bwd_nchw2_kernel<T, P, true, false><<<grid, 256, 0, st>>>(dy, x, w, dx, nullptr, C, H, W, wc, rep, dy_sn); \
+               agg3_bwd_nchw2_kernel<T, P, false, true><<<grid, 256, 0, st>>>(dy, x, w, nullptr, dw, C, H, W, wc, rep, dy_sn); } \
+  else if (dx && dw) agg3_bwd_nchw2_kernel<T, P, true, true><<<grid, 256, 0, st>>>(dy, x, w, dx, dw, C, H, W, wc, rep, dy_sn); \
   else if (dx) agg3_bwd_nchw2_kernel<T, P, true, false><<<grid, 256, 0, st>>>(dy, x, w, dx, dw, C, H, W, wc, rep, dy_sn); \
   else agg3_bwd_nchw2_kernel<T, P, false, true><<<grid, 256, 0, st>>>(dy, x, w, dx, dw, C, H, W, wc, rep, dy_sn);
     if (pxv == 4) { NCHW2_LAUNCH(4) } else { NCHW2_LAUNCH(2) }
