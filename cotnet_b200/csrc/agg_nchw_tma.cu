@@ -8,8 +8,9 @@
 //   tile      = (sample n, weight channel g, band of TH image rows);   channels of g: c = g + j*wc, j < rep (= C / wc)
 //   planes    = x / dY / dX seen as the 5-D tensor {W, H, wc, rep, N}: ONE box {BW, TH+2, 1, rep, 1} fetched at
 //               (-PXV, h0-1, g, 0, n) brings the band of all `rep` channels with its halo; out-of-bounds coordinates are
-//               zero-filled by the TMA unit == the operator's zero padding.  The left halo is PXV wide (not 1) so that the
-//               centre PXV-vector of every thread stays 16-byte aligned in shared memory.
+//               zero-filled by the TMA unit == the operator's zero padding.  The left halo is 16 bytes wide (4 fp32 / 8 bf16
+//               pixels, not 1): a TMA box must start 16-byte aligned in global memory (a -8-byte start faults as "illegal
+//               instruction"), and the centre vector of every thread then stays vector-aligned in shared memory.
 //   weights   = {W, H, 9, wc, N}: box {BW', TH(+2), 9, 1, 1}.
 //   compute   : thread = (row, PXV pixels, channel subset); 9 weight vectors in registers, per channel 3 x (1 vector +
 //               2 scalar) shared loads and 9*PXV FMAs; results stored straight to global memory (PXV-wide, coalesced).
@@ -29,7 +30,8 @@ static constexpr int NT_THREADS_TOTAL = NT_COMPUTE_THREADS + 32;
 struct NchwTmaP {
   int N, C, H, W, wc, rep;
   int TH, bands, total_tiles, stages;
-  int BWa;                // row pitch (elements) of haloed tiles: round_up(W + 2*PXV, 16/sizeof(T))
+  int halo;               // columns of left halo in the tiles: max(PXV, 16/sizeof(T)) -- the box must START 16-byte aligned in global memory
+  int BWa;                // row pitch (elements) of haloed tiles: round_up(W + 2*halo, 16/sizeof(T))
   int BWb;                // row pitch of plain tiles: round_up(W, 16/sizeof(T))
   int a_bytes, b_bytes;   // per-stage bytes of operand A / B (each rounded up to 128)
   int a_tx, b_tx;         // bytes the TMA reports per stage
@@ -103,9 +105,9 @@ agg3_nchw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const uint32_t full = nt_smem(&s_full[s]);
         const uint32_t base = nt_smem(smem + (size_t)s * p.stage_bytes);
         nt_expect_tx(full, (uint32_t)(p.a_tx + p.b_tx));
-        nt_tma_5d(base, &mapA, full, -PXV, h0 - 1, g, 0, n);                        // haloed planes of the rep channels
+        nt_tma_5d(base, &mapA, full, -p.halo, h0 - 1, g, 0, n);                        // haloed planes of the rep channels
         if (MODE == 0) nt_tma_5d(base + p.a_bytes, &mapB, full, 0, h0, 0, g, n);      // weights, plain band
-        else if (MODE == 1) nt_tma_5d(base + p.a_bytes, &mapB, full, -PXV, h0 - 1, 0, g, n);   // weights with halo
+        else if (MODE == 1) nt_tma_5d(base + p.a_bytes, &mapB, full, -p.halo, h0 - 1, 0, g, n);   // weights with halo
         else nt_tma_5d(base + p.a_bytes, &mapB, full, 0, h0, g, 0, n);               // dY planes, plain band
       }
     }
@@ -136,7 +138,7 @@ agg3_nchw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         for (int t = 0; t < 9; ++t) wt[t] = *reinterpret_cast<const Pack<T, PXV>*>(sB + (t * p.TH + r) * p.BWb + w0);
         T* yb = out + (long long)n * p.out_sn + (long long)g * HW + (long long)h * p.W + w0;
         for (int j = js; j < p.rep; j += p.nsplit) {
-          const T* xb = sA + (j * rowsA + r + 1) * p.BWa + w0 + PXV;               // centre row, centre vector
+          const T* xb = sA + (j * rowsA + r + 1) * p.BWa + w0 + p.halo;               // centre row, centre vector
           float acc[PXV];
 #pragma unroll
           for (int i = 0; i < PXV; ++i) acc[i] = 0.f;
@@ -163,13 +165,13 @@ agg3_nchw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           for (int dw = -1; dw <= 1; ++dw) {
             const int t = (dh + 1) * 3 + dw + 1;
             T v[PXV + 2];
-            nt_ld_seg<T, PXV>(sB + (t * rowsA + r + 1 - dh) * p.BWa + w0 + PXV, v);
+            nt_ld_seg<T, PXV>(sB + (t * rowsA + r + 1 - dh) * p.BWa + w0 + p.halo, v);
 #pragma unroll
             for (int i = 0; i < PXV; ++i) ws[t][i] = v[i + 1 - dw];
           }
         T* xb = out + (long long)n * p.out_sn + (long long)g * HW + (long long)h * p.W + w0;
         for (int j = js; j < p.rep; j += p.nsplit) {
-          const T* db = sA + (j * rowsA + r + 1) * p.BWa + w0 + PXV;
+          const T* db = sA + (j * rowsA + r + 1) * p.BWa + w0 + p.halo;
           float acc[PXV];
 #pragma unroll
           for (int i = 0; i < PXV; ++i) acc[i] = 0.f;
@@ -196,7 +198,7 @@ agg3_nchw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           for (int i = 0; i < PXV; ++i) gw[t][i] = 0.f;
         for (int j = 0; j < p.rep; ++j) {
           const Pack<T, PXV> d = *reinterpret_cast<const Pack<T, PXV>*>(sB + (j * p.TH + r) * p.BWb + w0);
-          const T* xb = sA + (j * rowsA + r + 1) * p.BWa + w0 + PXV;
+          const T* xb = sA + (j * rowsA + r + 1) * p.BWa + w0 + p.halo;
 #pragma unroll
           for (int dh = -1; dh <= 1; ++dh) {
             T v[PXV + 2];
@@ -278,10 +280,11 @@ int nchw_tma_launch(int mode, int N, int C, int H, int W, int wc, long long a_sn
     if (((long long)W * es) % 16 || ((long long)H * W * es) % 16) return 0;                 // TMA global strides: multiples of 16 B
     if ((a_sn * es) % 16 || (b_sn * es) % 16 || (out_sn * es) % (pxv * es)) return 0;
     if (!aligned16(A) || !aligned16(Bp) || !aligned16(out)) return 0;
-    if (W + 2 * pxv > 256 || H < 1 || N < 1) return 0;
+    if (W + 2 * (pxv > al ? pxv : al) > 256 || H < 1 || N < 1) return 0;
     NchwTmaP p;
     p.N = N; p.C = C; p.H = H; p.W = W; p.wc = wc; p.rep = rep; p.mode = mode; p.out_sn = out_sn;
-    p.BWa = nt_round_up(W + 2 * pxv, al);
+    p.halo = pxv > al ? pxv : al;
+    p.BWa = nt_round_up(W + 2 * p.halo, al);
     p.BWb = nt_round_up(W, al);
     p.nsplit = mode == 2 ? 1 : (rep % 2 == 0 ? 2 : 1);
     const int nq = W / pxv;
