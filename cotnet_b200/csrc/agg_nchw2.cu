@@ -181,9 +181,11 @@ __device__ __forceinline__ void nchw2_bwd_body(const T* __restrict__ dp, const T
   }
 }
 
-// 2 CTAs per SM: the fused dX+dW variant otherwise takes 130 (bf16) registers -> one 8-warp CTA per SM, latency-bound
+// 16-bit types: 2 CTAs per SM (the fused dX+dW variant otherwise takes 130 registers -> one 8-warp CTA per SM).  fp32 keeps
+// its 172 registers: capping it to 128 or splitting it into two launches measured SLOWER on the small planes this kernel
+// still serves (stage 3: 157 us uncapped vs 185-187 us; the large fp32 planes go through agg_nchw_tma.cu).
 template <typename T, int PXV, bool DX, bool DW>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (sizeof(T) == 2 ? 2 : 1))
 agg3_bwd_nchw2_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ dx,
                       T* __restrict__ dw, int C, int H, int W, int wc, int rep, long long dy_sn) {
   const int HW = H * W, WQ = W / PXV;
@@ -240,10 +242,10 @@ int nchw2_bwd(int N, int C, int H, int W, int wc, long long dy_sn, const T* dy, 
     dim3 grid((H * (W / pxv) + 255) / 256, N * wc);
     const int rep = C / wc;
     COTB200_PROF_B(dx && dw ? "agg3_bwd_nchw2_dxdw" : (dx ? "agg3_bwd_nchw2_dx" : "agg3_bwd_nchw2_dw"), ((double)N * H * W) * ((dx && dw ? 3.0 : 2.0) * C + (dx && dw ? 18.0 : 9.0) * wc) * sizeof(T));
-    // fp32: the fused kernel needs 170+ registers (1 CTA/SM, or spills when capped) -- two launches that re-read dY win
-    // (measured against the reference's kernels: profiles/r01_bench_ref_kernels_*.json); 16-bit types stay fused.
+    // COTB200_NCHW_SPLIT=1: fp32 dX and dW as two launches (measured: 488 vs 500 us at stage 1, 187 vs 157 us at stage 3 --
+    // not a win; kept as a switch).
     static int split_env = -1;
-    if (split_env < 0) { const char* e = getenv("COTB200_NCHW_SPLIT"); split_env = (e && e[0] == '0') ? 0 : 1; }
+    if (split_env < 0) { const char* e = getenv("COTB200_NCHW_SPLIT"); split_env = (e && e[0] == '1') ? 1 : 0; }
     const bool split = split_env && sizeof(T) == 4 && dx && dw;
 #define NCHW2_LAUNCH(P)                                                                                              \
   if (split) { agg3_bwd_nchw2_kernel<T, P, true, false><<<grid, 256, 0, st>>>(dy, x, w, dx, nullptr, C, H, W, wc, rep, dy_sn); \
