@@ -15,6 +15,8 @@ Forward maths is SURVEY.md Appendix A.  Differences from the reference's eager g
     ``.contiguous()`` gives; channels_last in -> channels_last out, no transposes), and the LocalConv runs on
     the B200 kernels (NHWC kernels for channels_last tensors).
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -80,10 +82,19 @@ class CotLayer(nn.Module):
         xk, xc, xv = fused.fan_out(x, 3)
         k = fused.bn_act(self.key_embed[0](xk).contiguous(memory_format=cl), self.key_embed[1], relu=True)
         kc, kt = fused.fan_out(k, 2)
-        e = fused.bn_act(self.embed[0](torch.cat([xc, kc], dim=1)).contiguous(memory_format=cl), self.embed[1], relu=True)
+        hybrid = self.train_conv_backend in ("tc_e0", "tc_1x1") and fused.tc_supported(x, self.dim) and k.dtype == x.dtype
+        if hybrid:      # embed.0 as ONE tcgen05 GEMM over the operand pairs (x, W_x), (k, W_k): no concat, statistics in the epilogue
+            em = self.embed
+            e = fused.TcConv1x1Fn.apply(xc, kc, em[0].weight, None, em[1].weight, em[1].bias, em[1], True)
+        else:
+            e = fused.bn_act(self.embed[0](torch.cat([xc, kc], dim=1)).contiguous(memory_format=cl), self.embed[1], relu=True)
         # embed.3 runs bias-free; its bias is added (and differentiated) inside the GroupNorm kernels
         l = F.conv2d(e, self.embed[3].weight, None)
-        v = fused.bn_act(self.conv1x1[0](xv).contiguous(memory_format=cl), self.conv1x1[1], relu=False)
+        if hybrid and self.train_conv_backend == "tc_1x1":
+            cv = self.conv1x1
+            v = fused.TcConv1x1Fn.apply(xv, None, cv[0].weight, None, cv[1].weight, cv[1].bias, cv[1], False)
+        else:
+            v = fused.bn_act(self.conv1x1[0](xv).contiguous(memory_format=cl), self.conv1x1[1], relu=False)
         if l.dtype != v.dtype:
             l = l.to(v.dtype)
         l = l.contiguous(memory_format=torch.channels_last)
@@ -156,7 +167,9 @@ class CotLayer(nn.Module):
 
     #: "tc" = tcgen05 kernels for the block's convolutions also when autograd is on; "cudnn" = cuDNN convolutions +
     #: fused normalisation kernels.  Inference (no_grad, eval) always takes the tcgen05 path when the shape allows.
-    train_conv_backend = "cudnn"
+    #: "tc_e0" / "tc_1x1": hybrids of the fused path -- only embed.0 (concat-free two-pair GEMM) / embed.0 and conv1x1 on
+    #: the tcgen05 kernels, the 3x3 key convolution and embed.3 stay on cuDNN.
+    train_conv_backend = os.environ.get("COTB200_TRAIN_CONV", "cudnn")
 
     def forward(self, x):
         B, C, H, W = x.shape

@@ -87,3 +87,33 @@ def test_tail_backward_formula():
     assert (du - gu).abs().max() < 1e-10
     assert (dk - gk).abs().max() < 1e-10
     assert (sum_dzx - ggw).abs().max() < 1e-10 and (sum_dz - ggb).abs().max() < 1e-10
+
+
+def test_zero_arena_hands_out_clean_disjoint_slices():
+    """fused._ZeroArena (accumulator scratch): slices are zero, 16-byte aligned, disjoint within a step, recycled (and
+    cleared) by step_begin(), and the allocator falls back to torch.zeros when the arena is off or exhausted."""
+    import torch
+    from cotnet_b200 import fused
+    dev = torch.device("cpu")
+    fused._ARENA.buf.pop(dev, None)
+    fused.step_arena_off()
+    a = fused._zeros((2, 5), dev)                      # arena off: plain zeros
+    assert a.shape == (2, 5) and float(a.abs().sum()) == 0.0
+    old = fused._ZeroArena.SIZE
+    fused._ZeroArena.SIZE = 64
+    try:
+        fused.step_begin(dev)
+        x = fused._zeros((3, 3), dev)
+        y = fused._zeros((7,), dev)
+        assert x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0
+        assert y.data_ptr() >= x.data_ptr() + 9 * 4                      # disjoint
+        x.add_(1.0); y.add_(2.0)
+        big = fused._zeros((100,), dev)                                  # does not fit: falls back, still zero
+        assert float(big.abs().sum()) == 0.0 and big.numel() == 100
+        fused.step_begin(dev)                                            # recycle: the used prefix is cleared
+        x2 = fused._zeros((3, 3), dev)
+        assert x2.data_ptr() == x.data_ptr() and float(x2.abs().sum()) == 0.0
+    finally:
+        fused._ZeroArena.SIZE = old
+        fused._ARENA.buf.pop(dev, None)
+        fused.step_arena_off()
