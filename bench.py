@@ -443,7 +443,8 @@ def main_ours(a):
                        "l2": "per-step working set (activations, several GB) >> 126 MB L2; no explicit flush needed",
                        "cot_path": "libcotb200: LocalConv fwd/dX/dW, GroupNorm(9 taps) fwd/bwd, bn+SiLU+pool+radix-2 "
                                    "recombination fwd/bwd, fused BatchNorm(+ReLU,+residual) of the block and of the "
-                                   "enclosing bottleneck; convolutions: cuDNN (training) / tcgen05 (inference path)"},
+                                   "enclosing bottleneck, NHWC pooling, gradient fan-in; embed.0 of every CoT layer = tcgen05 two-pair GEMM "
+                                   "(no concat, BN statistics in the epilogue), the other convolutions cuDNN"},
             "e2e": e2e, "gpu_launches": int(launches), "launch_mode": graph_info, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -169,7 +169,10 @@ class CotLayer(nn.Module):
     #: fused normalisation kernels.  Inference (no_grad, eval) always takes the tcgen05 path when the shape allows.
     #: "tc_e0" / "tc_1x1": hybrids of the fused path -- only embed.0 (concat-free two-pair GEMM) / embed.0 and conv1x1 on
     #: the tcgen05 kernels, the 3x3 key convolution and embed.3 stay on cuDNN.
-    train_conv_backend = os.environ.get("COTB200_TRAIN_CONV", "cudnn")
+    #: Measured inside the whole CoTNet-50 bs256 training step (CUDA graph, profiles/r01_bench_conv_backends_run18.json):
+    #: cudnn 42.80 ms, tc_e0 41.29 ms, tc_1x1 42.37 ms, tc 46.38 ms  ->  tc_e0 is the default (bf16 channels_last, dim % 64 == 0;
+    #: anything else silently uses cuDNN for embed.0 as well).
+    train_conv_backend = os.environ.get("COTB200_TRAIN_CONV", "tc_e0")
 
     def forward(self, x):
         B, C, H, W = x.shape

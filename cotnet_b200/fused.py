@@ -136,6 +136,24 @@ def _bn_batch_stats(x, bn, weight, bias, lib, st, dt):
     return _bn_prepare(bn, weight, bias, C, float(B * H * W), None, x.device, st), False
 
 
+def _bn_apply_batch(x, res, sums, bn, weight, bias, relu, y, lib, st, dt):
+    """Training-mode BatchNorm tail shared by BNActFn and the tcgen05 functions: ONE kernel finalises the batch statistics
+    (sums = [2, C] column sums over the B*H*W rows of x), updates the running buffers and applies scale/shift(+res)(+ReLU).
+    Returns ss = [4, C] (scale, shift, mean, rstd) for the backward."""
+    B, C, H, W = x.shape
+    ss = torch.empty(4, C, dtype=torch.float32, device=x.device)
+    update, mom, rm, rv = _bn_running(bn, True)
+    w32 = None if weight is None else weight.detach().float().contiguous()
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    _lib.check(lib.cotb200_bn_apply_batch(dt, B, H * W, C, x.data_ptr(), _lib.ptr(res), sums[0].data_ptr(), sums[1].data_ptr(),
+                                          _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(rm), _lib.ptr(rv), float(B * H * W),
+                                          float(bn.eps), float(mom), 1 if update else 0, 1 if relu else 0, y.data_ptr(),
+                                          ss[0].data_ptr(), ss[1].data_ptr(), ss[2].data_ptr(), ss[3].data_ptr(), st),
+               "bn_apply_batch")
+    _bn_running_writeback(bn, update, rm, rv)
+    return ss
+
+
 class BNActFn(Function):
     """y = act(BatchNorm2d(x) (+ res)) on channels_last tensors: col_stats + bn_finalize + bn_apply forward,
     bn_bwd_sums + bn_bwd_apply backward.  Replaces the nn.BatchNorm2d / nn.ReLU (/ residual add) modules of
@@ -153,16 +171,7 @@ class BNActFn(Function):
         if batch:       # training: column sums, then ONE kernel that finalises the statistics in its prologue and applies them
             sums = _zeros((2, C,), x.device)
             _lib.check(lib.cotb200_col_stats(dt, B, H * W, C, x.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), st), "col_stats")
-            ss = torch.empty(4, C, dtype=torch.float32, device=x.device)      # [4,C]: scale, shift, mean, rstd
-            update, mom, rm, rv = _bn_running(bn, True)
-            w32 = None if weight is None else weight.detach().float().contiguous()
-            b32 = None if bias is None else bias.detach().float().contiguous()
-            _lib.check(lib.cotb200_bn_apply_batch(dt, B, H * W, C, x.data_ptr(), _lib.ptr(res), sums[0].data_ptr(), sums[1].data_ptr(),
-                                                  _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(rm), _lib.ptr(rv), float(B * H * W),
-                                                  float(bn.eps), float(mom), 1 if update else 0, 1 if relu else 0, y.data_ptr(),
-                                                  ss[0].data_ptr(), ss[1].data_ptr(), ss[2].data_ptr(), ss[3].data_ptr(), st),
-                       "bn_apply_batch")
-            _bn_running_writeback(bn, update, rm, rv)
+            ss = _bn_apply_batch(x, res, sums, bn, weight, bias, relu, y, lib, st, dt)   # [4,C]: scale, shift, mean, rstd
         else:
             ss = _bn_prepare(bn, weight, bias, C, float(B * H * W), None, x.device, st)
             _lib.check(lib.cotb200_bn_apply(dt, B, H * W, C, x.data_ptr(), _lib.ptr(res), ss[0].data_ptr(), ss[1].data_ptr(),
@@ -557,9 +566,8 @@ class TcConv1x1Fn(Function):
             sums = _zeros((2, N,), a1.device)
             pre = torch.empty_like(out, memory_format=torch.channels_last)
             _tc.gemm_bf16(a1, b1, a2, b2, stats=(sums[0], sums[1]), out=_rows2d(pre))
-            scale, shift, mean, rstd = _bn_from_sums(sums, float(M), bn, bn_w, bn_b)
-            _lib.check(lib.cotb200_bn_apply(dt, B, H * W, N, pre.data_ptr(), None, scale.data_ptr(), shift.data_ptr(),
-                                            1 if relu else 0, out.data_ptr(), st), "bn_apply")
+            ss = _bn_apply_batch(pre, None, sums, bn, bn_w, bn_b, relu, out, lib, st, dt)
+            scale, shift, mean, rstd = ss[0], ss[1], ss[2], ss[3]
         else:
             scale, shift, mean, rstd = _bn_eval_fold(bn, bn_w, bn_b)
             _tc.gemm_bf16(a1, b1, a2, b2, scale=scale, shift=shift, relu=relu, out=out2d)
@@ -632,9 +640,8 @@ class TcConv3x3Fn(Function):
             sums = _zeros((2, C,), x.device)
             pre = torch.empty_like(x, memory_format=torch.channels_last)
             _tc.conv3x3_bf16(x, wp, bnt, stats=(sums[0], sums[1]), out=pre)
-            scale, shift, mean, rstd = _bn_from_sums(sums, float(M), bn, bn_w, bn_b)
-            _lib.check(lib.cotb200_bn_apply(dt, B, H * W, C, pre.data_ptr(), None, scale.data_ptr(), shift.data_ptr(),
-                                            1 if relu else 0, out.data_ptr(), st), "bn_apply")
+            ss = _bn_apply_batch(pre, None, sums, bn, bn_w, bn_b, relu, out, lib, st, dt)
+            scale, shift, mean, rstd = ss[0], ss[1], ss[2], ss[3]
         else:
             scale, shift, mean, rstd = _bn_eval_fold(bn, bn_w, bn_b)
             _tc.conv3x3_bf16(x, wp, bnt, scale=scale, shift=shift, relu=relu, out=out)

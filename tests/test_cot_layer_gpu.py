@@ -188,8 +188,9 @@ def test_backbone_training_step_matches_oracle_fp32():
             assert torch.allclose(sm[k].cpu(), so[k].to(sm[k].dtype), atol=1e-4, rtol=1e-3), k
 
 
+@pytest.mark.parametrize("backend", ["tc", "tc_e0", "tc_1x1"])
 @pytest.mark.parametrize("dim,H", [(64, 28), (128, 14), (256, 14), (512, 7)])
-def test_tc_training_backend_vs_oracle(dim, H):
+def test_tc_training_backend_vs_oracle(dim, H, backend):
     """train_conv_backend='tc': every convolution of the block on the tcgen05 kernels, forward + backward, vs the oracle."""
     gen = torch.Generator().manual_seed(dim)
     sd64 = cot_ref.init_state_dict("cot", dim, gen, dtype=torch.float64, perturb=True)
@@ -207,13 +208,13 @@ def test_tc_training_backend_vs_oracle(dim, H):
     (want * cot64).sum().backward()
     rel = {}
     import copy
-    for backend in ("cudnn", "tc"):
+    for be in ("cudnn", backend):
         mb = copy.deepcopy(m)
-        mb.train_conv_backend = backend
+        mb.train_conv_backend = be
         x = x64.to(dtype).cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
         out = mb(x)
         (out.float() * cot64.float().cuda()).sum().backward()
-        rel[backend] = (((out.double().cpu() - want.detach()).norm() / want.detach().norm()).item(),
+        rel["tc" if be != "cudnn" else "cudnn"] = (((out.double().cpu() - want.detach()).norm() / want.detach().norm()).item(),
                         ((x.grad.double().cpu() - xr.grad).norm() / xr.grad.norm()).item())
     # bf16 activations between the stages: ReLU masks come from rounded pre-activations and four batch-statistics
     # BatchNorms amplify that -- the Frobenius error of ANY bf16 pipeline sits at the percent level here.  The tcgen05
