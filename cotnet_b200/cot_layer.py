@@ -82,14 +82,18 @@ class CotLayer(nn.Module):
         xk, xc, xv = fused.fan_out(x, 3)
         k = fused.bn_act(self.key_embed[0](xk).contiguous(memory_format=cl), self.key_embed[1], relu=True)
         kc, kt = fused.fan_out(k, 2)
-        hybrid = self.train_conv_backend in ("tc_e0", "tc_1x1") and fused.tc_supported(x, self.dim) and k.dtype == x.dtype
+        hybrid = (self.train_conv_backend in ("tc_e0", "tc_1x1", "tc_e0e3") and fused.tc_supported(x, self.dim)
+                  and k.dtype == x.dtype)
         if hybrid:      # embed.0 as ONE tcgen05 GEMM over the operand pairs (x, W_x), (k, W_k): no concat, statistics in the epilogue
             em = self.embed
             e = fused.TcConv1x1Fn.apply(xc, kc, em[0].weight, None, em[1].weight, em[1].bias, em[1], True)
         else:
             e = fused.bn_act(self.embed[0](torch.cat([xc, kc], dim=1)).contiguous(memory_format=cl), self.embed[1], relu=True)
         # embed.3 runs bias-free; its bias is added (and differentiated) inside the GroupNorm kernels
-        l = F.conv2d(e, self.embed[3].weight, None)
+        if hybrid and self.train_conv_backend == "tc_e0e3":
+            l = fused.TcConv1x1Fn.apply(e, None, self.embed[3].weight, None, None, None, None, False)
+        else:
+            l = F.conv2d(e, self.embed[3].weight, None)
         if hybrid and self.train_conv_backend == "tc_1x1":
             cv = self.conv1x1
             v = fused.TcConv1x1Fn.apply(xv, None, cv[0].weight, None, cv[1].weight, cv[1].bias, cv[1], False)
