@@ -326,18 +326,23 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float*
   }
 }
 
-// dz = dy * [y > 0] (ACT==1) ; sum_dz[c] += dz ; sum_dzx[c] += dz * xhat
+// dz = dy * [y > 0] (ACT==1: mask read from y ; ACT==2: mask recomputed as x*scale+shift > 0, one HBM pass less) ;
+// sum_dz[c] += dz ; sum_dzx[c] += dz * xhat
 template <typename T, int VEC, int ACT>
 __global__ void __launch_bounds__(NT_THREADS)
-bn_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ mu,
-                   const float* __restrict__ rstd, float* __restrict__ sum_dz, float* __restrict__ sum_dzx, RowsGeo g) {
+bn_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ scale,
+                   const float* __restrict__ shift, const float* __restrict__ mu, const float* __restrict__ rstd,
+                   float* __restrict__ sum_dz, float* __restrict__ sum_dzx, RowsGeo g) {
   extern __shared__ float sm[];
   const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
   const bool active = tx < g.cq && ty < g.ry;
   const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
-  float acc[2][VEC], m[VEC], rs[VEC];
+  float acc[2][VEC], m[VEC], rs[VEC], sc[VEC], sh[VEC];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) { acc[0][i] = acc[1][i] = 0.f; m[i] = active ? mu[tx * VEC + i] : 0.f; rs[i] = active ? rstd[tx * VEC + i] : 0.f; }
+  for (int i = 0; i < VEC; ++i) {
+    acc[0][i] = acc[1][i] = 0.f; m[i] = active ? mu[tx * VEC + i] : 0.f; rs[i] = active ? rstd[tx * VEC + i] : 0.f;
+    sc[i] = (ACT == 2 && active) ? scale[tx * VEC + i] : 0.f; sh[i] = (ACT == 2 && active) ? shift[tx * VEC + i] : 0.f;
+  }
   if (active) {
     const long long base = ((long long)b * g.HW) * g.ld + tx * VEC;
     for (int r = r0 + ty; r < r1; r += g.ry) {
@@ -348,9 +353,11 @@ bn_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* _
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         float dz = to_acc(dv.v[i]);
+        const float xf = to_acc(xv.v[i]);
         if (ACT == 1 && !(to_acc(yv.v[i]) > 0.f)) dz = 0.f;
+        if (ACT == 2 && !(fmaf(xf, sc[i], sh[i]) > 0.f)) dz = 0.f;       // the forward's own fp32 z: identical mask, y not read
         acc[0][i] += dz;
-        acc[1][i] = fmaf(dz, (to_acc(xv.v[i]) - m[i]) * rs[i], acc[1][i]);
+        acc[1][i] = fmaf(dz, (xf - m[i]) * rs[i], acc[1][i]);
       }
     }
   }
@@ -365,16 +372,18 @@ bn_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* _
 template <typename T, int VEC, int ACT, bool RES>
 __global__ void __launch_bounds__(NT_THREADS)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ scale,
-                    const float* __restrict__ mu, const float* __restrict__ rstd, const float* __restrict__ c1,
-                    const float* __restrict__ c2, float inv_n, T* __restrict__ dx, T* __restrict__ dres, RowsGeo g) {
+                    const float* __restrict__ shift, const float* __restrict__ mu, const float* __restrict__ rstd,
+                    const float* __restrict__ c1, const float* __restrict__ c2, float inv_n, T* __restrict__ dx,
+                    T* __restrict__ dres, RowsGeo g) {
   const int tx = threadIdx.x % g.cq_pad, ty = threadIdx.x / g.cq_pad;
   if (!(tx < g.cq && ty < g.ry)) return;
   const int b = blockIdx.y, r0 = blockIdx.x * g.rows_per_cta, r1 = min(g.HW, r0 + g.rows_per_cta);
-  float sc[VEC], m[VEC], rs[VEC], k1[VEC], k2[VEC];
+  float sc[VEC], sh[VEC], m[VEC], rs[VEC], k1[VEC], k2[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const int c = tx * VEC + i;
-    sc[i] = scale[c]; m[i] = mu[c]; rs[i] = rstd[c]; k1[i] = c1 ? c1[c] * inv_n : 0.f; k2[i] = c2 ? c2[c] * inv_n : 0.f;
+    sc[i] = scale[c]; sh[i] = ACT == 2 ? shift[c] : 0.f; m[i] = mu[c]; rs[i] = rstd[c];
+    k1[i] = c1 ? c1[c] * inv_n : 0.f; k2[i] = c2 ? c2[c] * inv_n : 0.f;
   }
   const long long base = ((long long)b * g.HW) * g.ld + tx * VEC;
   for (int r = r0 + ty; r < r1; r += g.ry) {
@@ -386,8 +395,10 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       float dz = to_acc(dv.v[i]);
+      const float xf = to_acc(xv.v[i]);
       if (ACT == 1 && !(to_acc(yv.v[i]) > 0.f)) dz = 0.f;
-      o.v[i] = Elem<T>::from(sc[i] * (dz - k1[i] - (to_acc(xv.v[i]) - m[i]) * rs[i] * k2[i]));
+      if (ACT == 2 && !(fmaf(xf, sc[i], sh[i]) > 0.f)) dz = 0.f;
+      o.v[i] = Elem<T>::from(sc[i] * (dz - k1[i] - (xf - m[i]) * rs[i] * k2[i]));
       if (RES) o2.v[i] = Elem<T>::from(dz);
     }
     st_pack<T, VEC>(dx + base + (long long)r * g.ld, o);
@@ -961,16 +972,19 @@ extern "C" int cotb200_bn_apply_batch(int dtype, int B, int HW, int C, const voi
   return bn_apply_impl("bn_apply_batch", dtype, B, HW, C, x, res, nullptr, nullptr, relu, y, &f, stream);
 }
 
-extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y, const float* mu,
-                                   const float* rstd, int relu, float* sum_dz, float* sum_dzx, void* stream) {
-  if (!dy || !x || !mu || !rstd || !sum_dz || !sum_dzx || (relu && !y)) { set_error("bn_bwd_sums: NULL pointer"); return COTB200_ENULL; }
+extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y,
+                                   const float* scale, const float* shift, const float* mu, const float* rstd, int relu,
+                                   float* sum_dz, float* sum_dzx, void* stream) {
+  if (!dy || !x || !mu || !rstd || !sum_dz || !sum_dzx || (relu == 1 && !y) || (relu == 2 && (!scale || !shift))) {
+    set_error("bn_bwd_sums: NULL pointer"); return COTB200_ENULL; }
+  if (relu < 0 || relu > 2) { set_error("bn_bwd_sums: relu must be 0, 1 or 2"); return COTB200_EINVAL; }
   if (dtype == COTB200_F64) { set_error("bn_bwd_sums: fp64 not supported"); return COTB200_EDTYPE; }
   { const long long rows = (long long)B * HW; if (rows > 2147483647LL) { set_error("cotb200_bn_bwd_sums: too many rows"); return COTB200_ETOOBIG; }
     HW = (int)rows; B = 1; }      // per-channel statistics: flatten [B, HW] -> rows
   cudaStream_t st = (cudaStream_t)stream;
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
-      const int vec = pick_vec<T>(C, dy, x, y);
+      const int vec = pick_vec<T>(C, dy, x, relu == 1 ? y : nullptr);
       const int cw = col_chunk(C, vec);
       if (!cw) { set_error("bn_bwd_sums: cannot tile %d channels", C); return COTB200_EINVAL; }
       for (int c0 = 0; c0 < C; c0 += cw) {
@@ -979,12 +993,15 @@ extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* 
         if (rc) return rc;
         g.ld = C;
         const T* dp = (const T*)dy + c0; const T* xp = (const T*)x + c0; const T* yp = y ? (const T*)y + c0 : nullptr;
-        COTB200_PROF_B("bn_bwd_sums", (double)B * HW * cw * (2 + (relu ? 1 : 0)) * sizeof(T));
+        COTB200_PROF_B("bn_bwd_sums", (double)B * HW * cw * (2 + (relu == 1 ? 1 : 0)) * sizeof(T));
+        const float* scp = scale ? scale + c0 : nullptr; const float* shp = shift ? shift + c0 : nullptr;
         NT_DISPATCH_VEC(vec, {
-          if (relu) { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 1>, smem))) return rc;
-                      bn_bwd_sums_kernel<T, V, 1><<<NT_GRID, NT_THREADS, smem, st>>>(dp, xp, yp, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
+          if (relu == 1) { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 1>, smem))) return rc;
+                           bn_bwd_sums_kernel<T, V, 1><<<NT_GRID, NT_THREADS, smem, st>>>(dp, xp, yp, scp, shp, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
+          else if (relu == 2) { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 2>, smem))) return rc;
+                                bn_bwd_sums_kernel<T, V, 2><<<NT_GRID, NT_THREADS, smem, st>>>(dp, xp, nullptr, scp, shp, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
           else { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 0>, smem))) return rc;
-                 bn_bwd_sums_kernel<T, V, 0><<<NT_GRID, NT_THREADS, smem, st>>>(dp, xp, nullptr, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
+                 bn_bwd_sums_kernel<T, V, 0><<<NT_GRID, NT_THREADS, smem, st>>>(dp, xp, nullptr, scp, shp, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
         });
         if ((rc = check_launch("bn_bwd_sums"))) return rc;
       }
@@ -994,17 +1011,20 @@ extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* 
   return 0;
 }
 
+#define BN_BWD_APPLY_LAUNCH(ACT, RES, YP, DRP) bn_bwd_apply_kernel<T, V, ACT, RES><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, YP, scale + c0, shp, mu + c0, rstd + c0, k1, k2, inv_n, dxp, DRP, g)
 extern "C" int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y,
-                                    const float* scale, const float* mu, const float* rstd, const float* c1, const float* c2,
-                                    float inv_n, int relu, void* dx, void* dres, void* stream) {
-  if (!dy || !x || !scale || !mu || !rstd || !dx || (relu && !y)) { set_error("bn_bwd_apply: NULL pointer"); return COTB200_ENULL; }
+                                    const float* scale, const float* shift, const float* mu, const float* rstd,
+                                    const float* c1, const float* c2, float inv_n, int relu, void* dx, void* dres, void* stream) {
+  if (!dy || !x || !scale || !mu || !rstd || !dx || (relu == 1 && !y) || (relu == 2 && !shift)) {
+    set_error("bn_bwd_apply: NULL pointer"); return COTB200_ENULL; }
+  if (relu < 0 || relu > 2) { set_error("bn_bwd_apply: relu must be 0, 1 or 2"); return COTB200_EINVAL; }
   if (dtype == COTB200_F64) { set_error("bn_bwd_apply: fp64 not supported"); return COTB200_EDTYPE; }
   { const long long rows = (long long)B * HW; if (rows > 2147483647LL) { set_error("cotb200_bn_bwd_apply: too many rows"); return COTB200_ETOOBIG; }
     HW = (int)rows; B = 1; }      // per-channel statistics: flatten [B, HW] -> rows
   cudaStream_t st = (cudaStream_t)stream;
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
-      int vec = pick_vec<T>(C, dy, x, y, dx);
+      int vec = pick_vec<T>(C, dy, x, relu == 1 ? y : nullptr, dx);
       if (dres && ((uintptr_t)dres & (vec * sizeof(T) - 1))) vec = 1;
       const int cw = col_chunk(C, vec);
       if (!cw) { set_error("bn_bwd_apply: cannot tile %d channels", C); return COTB200_EINVAL; }
@@ -1016,12 +1036,12 @@ extern "C" int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void*
         const T* dp = (const T*)dy + c0; const T* xp = (const T*)x + c0; const T* yp = y ? (const T*)y + c0 : nullptr;
         T* dxp = (T*)dx + c0; T* drp = dres ? (T*)dres + c0 : nullptr;
         const float* k1 = c1 ? c1 + c0 : nullptr; const float* k2 = c2 ? c2 + c0 : nullptr;
-        COTB200_PROF_B("bn_bwd_apply", (double)B * HW * cw * (3 + (relu ? 1 : 0) + (dres ? 1 : 0)) * sizeof(T));
+        COTB200_PROF_B("bn_bwd_apply", (double)B * HW * cw * (3 + (relu == 1 ? 1 : 0) + (dres ? 1 : 0)) * sizeof(T));
+        const float* shp = shift ? shift + c0 : nullptr;
         NT_DISPATCH_VEC(vec, {
-          if (relu) { if (dres) bn_bwd_apply_kernel<T, V, 1, true><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, yp, scale + c0, mu + c0, rstd + c0, k1, k2, inv_n, dxp, drp, g);
-                      else bn_bwd_apply_kernel<T, V, 1, false><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, yp, scale + c0, mu + c0, rstd + c0, k1, k2, inv_n, dxp, nullptr, g); }
-          else { if (dres) bn_bwd_apply_kernel<T, V, 0, true><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, nullptr, scale + c0, mu + c0, rstd + c0, k1, k2, inv_n, dxp, drp, g);
-                 else bn_bwd_apply_kernel<T, V, 0, false><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, nullptr, scale + c0, mu + c0, rstd + c0, k1, k2, inv_n, dxp, nullptr, g); }
+          if (relu == 1) { if (dres) BN_BWD_APPLY_LAUNCH(1, true, yp, drp); else BN_BWD_APPLY_LAUNCH(1, false, yp, nullptr); }
+          else if (relu == 2) { if (dres) BN_BWD_APPLY_LAUNCH(2, true, nullptr, drp); else BN_BWD_APPLY_LAUNCH(2, false, nullptr, nullptr); }
+          else { if (dres) BN_BWD_APPLY_LAUNCH(0, true, nullptr, drp); else BN_BWD_APPLY_LAUNCH(0, false, nullptr, nullptr); }
         });
         if ((rc = check_launch("bn_bwd_apply"))) return rc;
       }

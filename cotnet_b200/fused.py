@@ -176,7 +176,9 @@ class BNActFn(Function):
             ss = _bn_prepare(bn, weight, bias, C, float(B * H * W), None, x.device, st)
             _lib.check(lib.cotb200_bn_apply(dt, B, H * W, C, x.data_ptr(), _lib.ptr(res), ss[0].data_ptr(), ss[1].data_ptr(),
                                             1 if relu else 0, y.data_ptr(), st), "bn_apply")
-        ctx.save_for_backward(x, y if relu else None, ss)
+        # ReLU mask in the backward: with a residual it must come from y; without one it is recomputed from x and the
+        # forward's own scale/shift (relu code 2) and y is neither saved nor read
+        ctx.save_for_backward(x, y if (relu and res is not None) else None, ss)
         ctx.cfg = (relu, batch, res is not None, weight.dtype, bias.dtype)
         return y
 
@@ -187,18 +189,19 @@ class BNActFn(Function):
         B, C, H, W = x.shape
         lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.dtype_code(x)
         dy = dy.contiguous(memory_format=torch.channels_last)
+        rcode = 0 if not relu else (1 if y is not None else 2)
         sums = None
         if batch or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)       # escapes as dgamma/dbeta: not from the arena
-            _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), x.data_ptr(), _lib.ptr(y), ss[2].data_ptr(),
-                                               ss[3].data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
-                       "bn_bwd_sums")
+            _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), x.data_ptr(), _lib.ptr(y), ss[0].data_ptr(),
+                                               ss[1].data_ptr(), ss[2].data_ptr(), ss[3].data_ptr(), rcode,
+                                               sums[0].data_ptr(), sums[1].data_ptr(), st), "bn_bwd_sums")
         dx = torch.empty_like(x, memory_format=torch.channels_last)
         dres = torch.empty_like(x, memory_format=torch.channels_last) if (has_res and ctx.needs_input_grad[3]) else None
         _lib.check(lib.cotb200_bn_bwd_apply(dt, B, H * W, C, dy.data_ptr(), x.data_ptr(), _lib.ptr(y), ss[0].data_ptr(),
-                                            ss[2].data_ptr(), ss[3].data_ptr(), _lib.ptr(sums[0]) if batch else None,
-                                            _lib.ptr(sums[1]) if batch else None, 1.0 / float(B * H * W), 1 if relu else 0,
-                                            dx.data_ptr(), _lib.ptr(dres), st), "bn_bwd_apply")
+                                            ss[1].data_ptr(), ss[2].data_ptr(), ss[3].data_ptr(),
+                                            _lib.ptr(sums[0]) if batch else None, _lib.ptr(sums[1]) if batch else None,
+                                            1.0 / float(B * H * W), rcode, dx.data_ptr(), _lib.ptr(dres), st), "bn_bwd_apply")
         dgamma = sums[1].to(wdt) if ctx.needs_input_grad[1] else None
         dbeta = sums[0].to(bdt) if ctx.needs_input_grad[2] else None
         return dx, dgamma, dbeta, dres, None, None
@@ -591,12 +594,13 @@ class TcConv1x1Fn(Function):
         dgamma = dbeta = dcb = None
         if has_bn:
             sums = torch.zeros(2, N, dtype=torch.float32, device=dy.device)      # escapes as dgamma/dbeta
-            _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), mean.data_ptr(),
-                                               rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
+            _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
+                                               None, mean.data_ptr(), rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(),
+                                               sums[1].data_ptr(), st),
                        "bn_bwd_sums")
             dpre = torch.empty_like(dy, memory_format=torch.channels_last)
             _lib.check(lib.cotb200_bn_bwd_apply(dt, B, H * W, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
-                                                mean.data_ptr(), rstd.data_ptr(), _lib.ptr(sums[0]) if batch else None,
+                                                None, mean.data_ptr(), rstd.data_ptr(), _lib.ptr(sums[0]) if batch else None,
                                                 _lib.ptr(sums[1]) if batch else None, 1.0 / M, 1 if relu else 0,
                                                 dpre.data_ptr(), None, st), "bn_bwd_apply")
             dgamma, dbeta = sums[1].to(bndt), sums[0].to(bndt)
@@ -660,12 +664,13 @@ class TcConv3x3Fn(Function):
         lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.BF16
         dy = dy.contiguous(memory_format=torch.channels_last)
         sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)          # escapes as dgamma/dbeta
-        _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), mean.data_ptr(),
-                                           rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(), sums[1].data_ptr(), st),
+        _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
+                                           None, mean.data_ptr(), rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(),
+                                           sums[1].data_ptr(), st),
                    "bn_bwd_sums")
         dpre = torch.empty_like(dy, memory_format=torch.channels_last)
         _lib.check(lib.cotb200_bn_bwd_apply(dt, B, H * W, C, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
-                                            mean.data_ptr(), rstd.data_ptr(), _lib.ptr(sums[0]) if batch else None,
+                                            None, mean.data_ptr(), rstd.data_ptr(), _lib.ptr(sums[0]) if batch else None,
                                             _lib.ptr(sums[1]) if batch else None, 1.0 / M, 1 if relu else 0,
                                             dpre.data_ptr(), None, st), "bn_bwd_apply")
         dx = dw = None

@@ -136,14 +136,18 @@ int cotb200_bn_apply_batch(int dtype, int B, int HW, int C, const void* x, const
                            const float* weight, const float* bias, float* running_mean, float* running_var, float n,
                            float eps, float momentum, int update_running, int relu, void* y, float* scale, float* shift,
                            float* mean, float* rstd, void* stream);
-/* dz = dy*[y>0] (relu) ; sum_dz[c] += sum dz ; sum_dzx[c] += sum dz*xhat      (y may be NULL when relu == 0) */
-int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y, const float* mu,
-                        const float* rstd, int relu, float* sum_dz, float* sum_dzx, void* stream);
+/* dz = dy*mask ; sum_dz[c] += sum dz ; sum_dzx[c] += sum dz*xhat.
+ * relu: 0 = no activation; 1 = ReLU, mask = [y > 0] read from the forward output y; 2 = ReLU, mask recomputed as
+ * [x*scale + shift > 0] from the forward's own fp32 scale/shift (identical mask, y is NOT read: one HBM pass less; only for
+ * BatchNorms without a residual input).  y may be NULL unless relu == 1; scale/shift may be NULL unless relu == 2. */
+int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y, const float* scale,
+                        const float* shift, const float* mu, const float* rstd, int relu, float* sum_dz, float* sum_dzx,
+                        void* stream);
 /* dx = scale*(dz - c1*inv_n - xhat*c2*inv_n) (c1,c2 = the raw sums of cotb200_bn_bwd_sums, NULL in eval mode) ;
  * dres = dz when dres != NULL (gradient of the residual) */
 int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y, const float* scale,
-                         const float* mu, const float* rstd, const float* c1, const float* c2, float inv_n, int relu,
-                         void* dx, void* dres, void* stream);
+                         const float* shift, const float* mu, const float* rstd, const float* c1, const float* c2,
+                         float inv_n, int relu, void* dx, void* dres, void* stream);
 /* One launch for the BatchNorm bookkeeping: from the column sums of cotb200_col_stats (or a GEMM epilogue) compute
  * scale = gamma*rstd, shift = beta - mean*scale, mean, rstd, and update running_mean / running_var like nn.BatchNorm2d
  * (momentum, unbiased variance).  use_batch = 0: eval mode, statistics read from the running buffers. */
