@@ -251,6 +251,8 @@ def main_ours(a):
     torch.cuda.set_device(dev)
     _lib.load()
     torch.backends.cudnn.benchmark = True
+    if os.environ.get("COTB200_CUDNN_BENCH_LIMIT"):       # 0 = let cuDNN's autotuner try every algorithm (default: the first 10)
+        torch.backends.cudnn.benchmark_limit = int(os.environ["COTB200_CUDNN_BENCH_LIMIT"])
     torch.manual_seed(1234 + rank)
 
     B, R = a.batch, a.res
