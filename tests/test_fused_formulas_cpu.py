@@ -117,3 +117,37 @@ def test_zero_arena_hands_out_clean_disjoint_slices():
         fused._ZeroArena.SIZE = old
         fused._ARENA.buf.pop(dev, None)
         fused.step_arena_off()
+
+
+def test_row_view_detects_pitched_nhwc_rows():
+    """fused._row_view: the pixel pitch of a [B,C,H,W] tensor whose memory is NHWC rows (channels_last tensors and channel
+    slices of them -- the gradients of a concat), None for anything the row kernels cannot address."""
+    import torch
+    from cotnet_b200 import fused
+    t = torch.zeros(2, 12, 5, 7).contiguous(memory_format=torch.channels_last)
+    assert fused._row_view(t) == 12
+    assert fused._row_view(t[:, :4]) == 12 and fused._row_view(t[:, 4:]) == 12        # channel slices keep the pitch
+    assert fused._row_view(torch.zeros(2, 12, 5, 7)) is None                            # NCHW: channel stride != 1
+    assert fused._row_view(t[:, :, ::2]) is None                                        # strided rows
+    assert fused._row_view(t[:, ::2]) is None                                           # strided channels
+    assert fused._row_view(torch.zeros(3, 4)) is None
+    one = torch.zeros(1, 8, 1, 1).contiguous(memory_format=torch.channels_last)
+    assert fused._row_view(one) == 8
+
+
+def test_tap_chunk_and_positions():
+    """Tap-major layout bookkeeping used by GroupNorm / LocalConv: chunk width and the (g, t) -> position map of
+    include/cotb200.h (COTB200_NHWC_TAP)."""
+    from cotnet_b200 import fused
+    assert fused.tap_chunk(8) == 8 and fused.tap_chunk(64) == 8
+    gc = 8
+    wc = 16
+    seen = set()
+    for g in range(wc):
+        for t in range(9):
+            pos = ((g // gc) * 9 + t) * gc + g % gc
+            assert 0 <= pos < 9 * wc
+            seen.add(pos)
+            # each chunk of 8 groups occupies the same 72 positions in both orders (what csrc/gn72.cu relies on)
+            assert pos // 72 == (g * 9 + t) // 72
+    assert len(seen) == 9 * wc
