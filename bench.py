@@ -243,7 +243,10 @@ def main_ours(a):
     from cotnet_b200 import dist as cdist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout = the one JSON line even if NCCL_DEBUG is set
+    # keep stdout = the one JSON line: NCCL writes its banner ("NCCL version ...") to stdout when NCCL_DEBUG=VERSION
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION",):
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank, local_rank, world = cdist.init_from_env()
     if world != a.gpus and world > 1:
         a.gpus = world
