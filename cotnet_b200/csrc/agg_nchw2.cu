@@ -13,24 +13,6 @@
 
 namespace cotb200 {
 
-template <typename T> struct MixN;
-template <> struct MixN<float> {
-  __device__ __forceinline__ static float fma(float a, float b, float c) { return fmaf(a, b, c); }
-};
-template <> struct MixN<__nv_bfloat16> {
-  __device__ __forceinline__ static float fma(__nv_bfloat16 a, __nv_bfloat16 b, float c) {
-    float d;
-    asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(__bfloat16_as_ushort(a)), "h"(__bfloat16_as_ushort(b)), "f"(c));
-    return d;
-  }
-};
-template <> struct MixN<__half> {
-  __device__ __forceinline__ static float fma(__half a, __half b, float c) {
-    float d;
-    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(__half_as_ushort(a)), "h"(__half_as_ushort(b)), "f"(c));
-    return d;
-  }
-};
 // fp32 accumulator times storage-type element (used where one factor is already fp32)
 template <typename T> __device__ __forceinline__ float mulacc(float a, T b, float c) { return fmaf(a, to_acc(b), c); }
 
@@ -79,7 +61,7 @@ __device__ __forceinline__ void nchw2_fwd_body(const T* __restrict__ xp, const T
 #pragma unroll
       for (int dw = -1; dw <= 1; ++dw)
 #pragma unroll
-        for (int i = 0; i < PXV; ++i) acc[i] = MixN<T>::fma(wt[(dh + 1) * 3 + dw + 1].v[i], v[i + 1 + dw], acc[i]);
+        for (int i = 0; i < PXV; ++i) acc[i] = mfma<T>(wt[(dh + 1) * 3 + dw + 1].v[i], v[i + 1 + dw], acc[i]);
     }
     Pack<T, PXV> o;
 #pragma unroll
@@ -149,7 +131,7 @@ __device__ __forceinline__ void nchw2_bwd_body(const T* __restrict__ dp, const T
         for (int dw = -1; dw <= 1; ++dw)
 #pragma unroll
           for (int i = 0; i < PXV; ++i)
-            gw[(dh + 1) * 3 + dw + 1][i] = MixN<T>::fma(xv[i + 1 + dw], dy[1][i + 1], gw[(dh + 1) * 3 + dw + 1][i]);
+            gw[(dh + 1) * 3 + dw + 1][i] = mfma<T>(xv[i + 1 + dw], dy[1][i + 1], gw[(dh + 1) * 3 + dw + 1][i]);
       }
     }
     if (DX) {
@@ -162,7 +144,7 @@ __device__ __forceinline__ void nchw2_bwd_body(const T* __restrict__ dp, const T
         for (int dw = -1; dw <= 1; ++dw)
 #pragma unroll
           for (int i = 0; i < PXV; ++i)      // output pixel (h - dh, w - dw) read (h, w) through tap (dh, dw)
-            acc[i] = MixN<T>::fma(ws[(dh + 1) * 3 + dw + 1][i], dy[1 - dh][i + 1 - dw], acc[i]);
+            acc[i] = mfma<T>(ws[(dh + 1) * 3 + dw + 1][i], dy[1 - dh][i + 1 - dw], acc[i]);
       Pack<T, PXV> o;
 #pragma unroll
       for (int i = 0; i < PXV; ++i) o.v[i] = Elem<T>::from(acc[i]);

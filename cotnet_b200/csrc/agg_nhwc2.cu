@@ -16,24 +16,6 @@
 
 namespace cotb200 {
 
-template <typename T> struct Mix;
-template <> struct Mix<float> {
-  __device__ __forceinline__ static float fma(float a, float b, float c) { return fmaf(a, b, c); }
-};
-template <> struct Mix<__nv_bfloat16> {
-  __device__ __forceinline__ static float fma(__nv_bfloat16 a, __nv_bfloat16 b, float c) {
-    float d;
-    asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(__bfloat16_as_ushort(a)), "h"(__bfloat16_as_ushort(b)), "f"(c));
-    return d;
-  }
-};
-template <> struct Mix<__half> {
-  __device__ __forceinline__ static float fma(__half a, __half b, float c) {
-    float d;
-    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(__half_as_ushort(a)), "h"(__half_as_ushort(b)), "f"(c));
-    return d;
-  }
-};
 
 template <typename T, int VEC> __device__ __forceinline__ Pack<T, VEC> zero_pack() {
   Pack<T, VEC> z;
@@ -94,7 +76,7 @@ __device__ __forceinline__ void agg3_nhwc2_body(const T* __restrict__ ab, const 
           for (int i = 0; i < VEC; ++i) {
             // plain order: element (i,t) sits at flat i*9+t of the 9 packets; TAP order: packet t, lane i
             const T wv = TAP ? wk[p][t].v[i] : wk[p][(i * 9 + t) / VEC].v[(i * 9 + t) % VEC];
-            acc[p][i] = Mix<T>::fma(wv, xv[p + dw + 1].v[i], acc[p][i]);
+            acc[p][i] = mfma<T>(wv, xv[p + dw + 1].v[i], acc[p][i]);
           }
         }
     }
@@ -117,7 +99,7 @@ __device__ __forceinline__ void agg3_nhwc2_body(const T* __restrict__ ab, const 
           const int t = (dh + 1) * 3 + (dw + 1);
           const Pack<T, VEC> wv = ld_pack<T, VEC>(wr + wpk_off_tap<VEC>(g0, t, g.gc));
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) acc[p][i] = Mix<T>::fma(wv.v[i], gv.v[i], acc[p][i]);
+          for (int i = 0; i < VEC; ++i) acc[p][i] = mfma<T>(wv.v[i], gv.v[i], acc[p][i]);
         }
       }
     }
@@ -189,7 +171,7 @@ agg3_dw_nhwc2_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __res
       if ((unsigned)hh < (unsigned)g.H && (unsigned)ww < (unsigned)g.W) {
         const Pack<T, VEC> xv = ld_pack<T, VEC>(xb + (hh * g.W + ww) * g.x_sp);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) part[t][i] = Mix<T>::fma(xv.v[i], gvv.v[i], 0.f);
+        for (int i = 0; i < VEC; ++i) part[t][i] = mfma<T>(xv.v[i], gvv.v[i], 0.f);
       }
     }
   }

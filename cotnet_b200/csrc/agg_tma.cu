@@ -18,24 +18,6 @@
 
 namespace cotb200 {
 
-template <typename T> struct MixT;
-template <> struct MixT<float> {
-  __device__ __forceinline__ static float fma(float a, float b, float c) { return fmaf(a, b, c); }
-};
-template <> struct MixT<__nv_bfloat16> {
-  __device__ __forceinline__ static float fma(__nv_bfloat16 a, __nv_bfloat16 b, float c) {
-    float d;
-    asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(__bfloat16_as_ushort(a)), "h"(__bfloat16_as_ushort(b)), "f"(c));
-    return d;
-  }
-};
-template <> struct MixT<__half> {
-  __device__ __forceinline__ static float fma(__half a, __half b, float c) {
-    float d;
-    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(__half_as_ushort(a)), "h"(__half_as_ushort(b)), "f"(c));
-    return d;
-  }
-};
 
 static constexpr int AT_MAX_STAGES = 4;
 
@@ -212,7 +194,7 @@ agg3_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
           const Pack<T, VEC> wv = lds_pack<T, VEC>(wb + t * wtap + (MODE == 0 ? 0 : r * wrow));
           const Pack<T, VEC> xv = lds_pack<T, VEC>(xb + r * 128 + ((i_ch[k] ^ (r & 7)) << 4));
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) acc[i] = MixT<T>::fma(wv.v[i], xv.v[i], acc[i]);
+          for (int i = 0; i < VEC; ++i) acc[i] = mfma<T>(wv.v[i], xv.v[i], acc[i]);
         }
         Pack<T, VEC> o;
 #pragma unroll
@@ -286,7 +268,7 @@ agg3_dw_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
             const int r = rc + (t / 3 - 1) * Wp + (t % 3 - 1);
             const Pack<T, VEC> xv = lds_pack<T, VEC>(xb + (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4)));
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[t][i] = MixT<T>::fma(xv.v[i], gvv.v[i], acc[t][i]);
+            for (int i = 0; i < VEC; ++i) acc[t][i] = mfma<T>(xv.v[i], gvv.v[i], acc[t][i]);
           }
         }
         T* wr = dw + n * p.y_sn + (long long)((h0 + hl) * p.W + wl) * p.y_sp + (g0 / p.gc) * 9 * p.gc + g0 % p.gc;
