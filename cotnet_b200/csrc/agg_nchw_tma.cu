@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cstdlib>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace cotb200 {
 
@@ -41,34 +42,6 @@ struct NchwTmaP {
   long long out_sn;       // batch stride of the output tensor (elements)
 };
 
-__device__ __forceinline__ uint32_t nt_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void nt_mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void nt_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void nt_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void nt_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (int spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (!done && spin > (1 << 22)) __trap();
-  }
-}
-__device__ __forceinline__ void nt_tma_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-
 // PXV consecutive elements at `p` (PXV*sizeof(T)-aligned) plus the element before and after: v[0], v[1..PXV], v[PXV+1]
 template <typename T, int PXV>
 __device__ __forceinline__ void nt_ld_seg(const T* p, T (&v)[PXV + 2]) {
@@ -89,8 +62,8 @@ agg3_nchw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int CW = NT_COMPUTE_THREADS / 32;
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) { nt_mbar_init(nt_smem(&s_full[s]), 1); nt_mbar_init(nt_smem(&s_empty[s]), CW); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), CW); }
+    mbar_init_fence();
   }
   __syncthreads();
 
@@ -99,16 +72,16 @@ agg3_nchw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int s = it % p.stages;
-        nt_wait(nt_smem(&s_empty[s]), ((it / p.stages) & 1) ^ 1);
+        mbar_wait(smem_u32(&s_empty[s]), ((it / p.stages) & 1) ^ 1);
         const int band = tile % p.bands, ng = tile / p.bands;
         const int g = ng % p.wc, n = ng / p.wc, h0 = band * p.TH;
-        const uint32_t full = nt_smem(&s_full[s]);
-        const uint32_t base = nt_smem(smem + (size_t)s * p.stage_bytes);
-        nt_expect_tx(full, (uint32_t)(p.a_tx + p.b_tx));
-        nt_tma_5d(base, &mapA, full, -p.halo, h0 - 1, g, 0, n);                        // haloed planes of the rep channels
-        if (MODE == 0) nt_tma_5d(base + p.a_bytes, &mapB, full, 0, h0, 0, g, n);      // weights, plain band
-        else if (MODE == 1) nt_tma_5d(base + p.a_bytes, &mapB, full, -p.halo, h0 - 1, 0, g, n);   // weights with halo
-        else nt_tma_5d(base + p.a_bytes, &mapB, full, 0, h0, g, 0, n);               // dY planes, plain band
+        const uint32_t full = smem_u32(&s_full[s]);
+        const uint32_t base = smem_u32(smem + (size_t)s * p.stage_bytes);
+        mbar_expect_tx(full, (uint32_t)(p.a_tx + p.b_tx));
+        tma_load_5d(base, &mapA, full, -p.halo, h0 - 1, g, 0, n);                        // haloed planes of the rep channels
+        if (MODE == 0) tma_load_5d(base + p.a_bytes, &mapB, full, 0, h0, 0, g, n);      // weights, plain band
+        else if (MODE == 1) tma_load_5d(base + p.a_bytes, &mapB, full, -p.halo, h0 - 1, 0, g, n);   // weights with halo
+        else tma_load_5d(base + p.a_bytes, &mapB, full, 0, h0, g, 0, n);               // dY planes, plain band
       }
     }
     return;
@@ -121,7 +94,7 @@ agg3_nchw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   int it = 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
     const int s = it % p.stages;
-    nt_wait(nt_smem(&s_full[s]), (it / p.stages) & 1);
+    mbar_wait(smem_u32(&s_full[s]), (it / p.stages) & 1);
     const int band = tile % p.bands, ng = tile / p.bands;
     const int g = ng % p.wc, n = ng / p.wc, h0 = band * p.TH;
     const T* sA = reinterpret_cast<const T*>(smem + (size_t)s * p.stage_bytes);
@@ -221,7 +194,7 @@ agg3_nchw_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
     }
     __syncwarp();
-    if (lane == 0) nt_arrive(nt_smem(&s_empty[s]));
+    if (lane == 0) mbar_arrive(smem_u32(&s_empty[s]));
   }
 }
 

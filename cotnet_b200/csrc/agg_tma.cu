@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cstdlib>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace cotb200 {
 
@@ -43,43 +44,6 @@ struct AggTmaP {
   int GQ;                 // dW: weight packets per pixel
 };
 
-__device__ __forceinline__ uint32_t at_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void at_mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void at_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void at_mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void at_mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (int spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && spin > (1 << 22)) __trap();
-  }
-}
-__device__ __forceinline__ void at_tma_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-
-__device__ __forceinline__ void at_tma_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-
 // explicit 16-byte shared-memory load from a 32-bit shared address (a generic LD would pay address translation)
 template <typename T, int VEC>
 __device__ __forceinline__ Pack<T, VEC> lds_pack(uint32_t saddr) {
@@ -98,20 +62,20 @@ __device__ __forceinline__ void at_producer(const CUtensorMap& mapX, const CUten
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
-        at_mbar_wait(at_smem_u32(&s_empty[s]), ph ^ 1);
+        mbar_wait(smem_u32(&s_empty[s]), ph ^ 1);
         const int n = tile / p.bands, h0 = (tile - n * p.bands) * p.TH;
-        const uint32_t full = at_smem_u32(&s_full[s]);
-        const uint32_t base = at_smem_u32(smem + (size_t)s * p.stage_bytes);
-        at_mbar_expect_tx(full, (uint32_t)(p.x_bytes_tx + p.w_bytes_tx));
+        const uint32_t full = smem_u32(&s_full[s]);
+        const uint32_t base = smem_u32(smem + (size_t)s * p.stage_bytes);
+        mbar_expect_tx(full, (uint32_t)(p.x_bytes_tx + p.w_bytes_tx));
         for (int sl = 0; sl < p.slabs; ++sl)      // input band + halo; OOB (w = -1 / W, h = -1 / H) zero-filled
-          at_tma_4d(base + sl * p.slab_bytes, &mapX, full, sl * (128 / (int)sizeof(T)), -1, h0 - 1, n);
+          tma_load_4d(base + sl * p.slab_bytes, &mapX, full, sl * (128 / (int)sizeof(T)), -1, h0 - 1, n);
         const uint32_t wbase = base + p.slabs * p.slab_bytes;
         if (p.mode == 2) {        // dW: second operand = dY band (no halo), one box per 128-byte channel slab
           for (int sl = 0; sl < p.slabs; ++sl)
-            at_tma_4d(wbase + sl * p.b_slab_bytes, &mapW, full, sl * (128 / (int)sizeof(T)), 0, h0, n);
+            tma_load_4d(wbase + sl * p.b_slab_bytes, &mapW, full, sl * (128 / (int)sizeof(T)), 0, h0, n);
         } else {                  // weights: [rows][J]; dX needs them at the neighbour pixels -> haloed band
           // one 5-D box {jbox, jboxes, W(+2), TH(+2), 1}: the J = jboxes*jbox weights of a pixel land contiguously
-          at_tma_5d(wbase, &mapW, full, 0, 0, -p.whalo, h0 - p.whalo, n);
+          tma_load_5d(wbase, &mapW, full, 0, 0, -p.whalo, h0 - p.whalo, n);
         }
       }
     }
@@ -130,8 +94,8 @@ agg3_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
-    for (int s = 0; s < p.stages; ++s) { at_mbar_init(at_smem_u32(&s_full[s]), 1); at_mbar_init(at_smem_u32(&s_empty[s]), ncw); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), ncw); }
+    mbar_init_fence();
   }
   __syncthreads();
 
@@ -166,14 +130,14 @@ agg3_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
         i_ob[k] = (hl * p.W + wl) * p.y_sp + c0;
       }
     }
-    const uint32_t smem_base = at_smem_u32(smem);
+    const uint32_t smem_base = smem_u32(smem);
     const int wtap = p.gc * (int)sizeof(T);                    // bytes between the packets of consecutive taps
     const int wrow = p.J * (int)sizeof(T);                     // bytes of one pixel's weight row
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int s = it % p.stages;
       const uint32_t ph = (it / p.stages) & 1;
-      at_mbar_wait(at_smem_u32(&s_full[s]), ph);
+      mbar_wait(smem_u32(&s_full[s]), ph);
       const int n = tile / p.bands, h0 = (tile - n * p.bands) * p.TH;
       const uint32_t xs = smem_base + (uint32_t)(s * p.stage_bytes);
       const uint32_t ws = xs + (uint32_t)(p.slabs * p.slab_bytes);
@@ -202,7 +166,7 @@ agg3_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
         st_pack<T, VEC>(yt + i_ob[k], o);
       }
       __syncwarp();
-      if (lane == 0) at_mbar_arrive(at_smem_u32(&s_empty[s]));   // this warp is done reading the stage
+      if (lane == 0) mbar_arrive(smem_u32(&s_empty[s]));   // this warp is done reading the stage
     }
   }
 }
@@ -225,8 +189,8 @@ agg3_dw_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapG) : "memory");
-    for (int s = 0; s < p.stages; ++s) { at_mbar_init(at_smem_u32(&s_full[s]), 1); at_mbar_init(at_smem_u32(&s_empty[s]), ncw); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), ncw); }
+    mbar_init_fence();
   }
   __syncthreads();
   if (warp == 0) {
@@ -236,12 +200,12 @@ agg3_dw_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     const int items = p.TH * p.W * p.GQ;
     const int Wp = p.W + 2;
     const int rep = p.Cf / p.wcf;                      // sharers per weight channel
-    const uint32_t smem_base = at_smem_u32(smem);
+    const uint32_t smem_base = smem_u32(smem);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int s = it % p.stages;
       const uint32_t ph = (it / p.stages) & 1;
-      at_mbar_wait(at_smem_u32(&s_full[s]), ph);
+      mbar_wait(smem_u32(&s_full[s]), ph);
       const int n = tile / p.bands, h0 = (tile - n * p.bands) * p.TH;
       const uint32_t xs = smem_base + (uint32_t)(s * p.stage_bytes);
       const uint32_t gs = xs + (uint32_t)(p.slabs * p.slab_bytes);
@@ -281,7 +245,7 @@ agg3_dw_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
         }
       }
       __syncwarp();
-      if (lane == 0) at_mbar_arrive(at_smem_u32(&s_empty[s]));
+      if (lane == 0) mbar_arrive(smem_u32(&s_empty[s]));
     }
   }
 }

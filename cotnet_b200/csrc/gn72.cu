@@ -18,6 +18,7 @@
 //     dbeta AND the bias gradient of the embed.3 convolution analytically (no extra pass over dl).
 // Algorithmic bytes: stats J, apply 2J, bwd_sums 2J, bwd_apply 3J (x px x s) -- unchanged; the point is reaching them.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace cotb200 {
 
@@ -26,36 +27,6 @@ struct GN72 {
   int bps;              // blocks of 72 per sample = HW * nchunk
   int tb;               // blocks per tile
 };
-
-__device__ __forceinline__ uint32_t g7_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void g7_mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void g7_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void g7_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (int spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (!done && spin > (1 << 22)) __trap();        // a lost copy must not hang the GPU
-  }
-}
-__device__ __forceinline__ void g7_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void g7_bulk_store(void* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void g7_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <typename T> struct G7 {
   static constexpr int NP = 72 * (int)sizeof(T) / 16;      // 16-byte packets per block: 9 (16-bit) / 18 (fp32)
@@ -101,12 +72,14 @@ gn72_stats_kernel(const T* __restrict__ l, const float* __restrict__ lbias, floa
   auto issue = [&](int tile, int stage) {
     const int nblk = min(TB, g.bps - tile * TB);
     const uint32_t bytes = (uint32_t)nblk * 72u * sizeof(T);
-    g7_expect_tx(g7_smem(&bar[stage]), bytes);
-    g7_bulk_load(g7_smem(smem) + stage * TILE, lb + (long long)tile * TB * 72, bytes, g7_smem(&bar[stage]));
+    mbar_expect_tx(smem_u32(&bar[stage]), bytes);
+    bulk_load(smem_u32(smem) + stage * TILE, lb + (long long)tile * TB * 72, bytes, smem_u32(&bar[stage]));
   };
   if (tid == 0) {
-    g7_mbar_init(g7_smem(&bar[0]), 1);
-    g7_mbar_init(g7_smem(&bar[1]), 1);
+    mbar_init(smem_u32(&bar[0]), 1);
+    mbar_init_fence();
+    mbar_init(smem_u32(&bar[1]), 1);
+    mbar_init_fence();
     if ((int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
   }
   for (int i = tid; i < 2 * g.wc; i += TB) s_acc[i] = 0.f;
@@ -123,11 +96,11 @@ gn72_stats_kernel(const T* __restrict__ l, const float* __restrict__ lbias, floa
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int stage = it & 1;
     if (tid == 0 && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, stage ^ 1);   // stage^1 was drained before the last sync
-    g7_wait(g7_smem(&bar[stage]), (it >> 1) & 1);
+    mbar_wait(smem_u32(&bar[stage]), (it >> 1) & 1);
     const int nblk = min(TB, g.bps - tile * TB);
     if (tid < nblk) {
       T v[72];
-      g7_ld_block<T>(g7_smem(smem) + stage * TILE + tid * 72 * (int)sizeof(T), v);
+      g7_ld_block<T>(smem_u32(smem) + stage * TILE + tid * 72 * (int)sizeof(T), v);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -192,9 +165,10 @@ gn72_apply_kernel(const T* __restrict__ l, const float* __restrict__ lbias, cons
   const uint32_t bytes = (uint32_t)nblk * 72u * sizeof(T);
   const long long goff = ((long long)b * g.bps + blk0) * 72;
   if (tid == 0) {
-    g7_mbar_init(g7_smem(&bar), 1);
-    g7_expect_tx(g7_smem(&bar), bytes);
-    g7_bulk_load(g7_smem(smem), l + goff, bytes, g7_smem(&bar));
+    mbar_init(smem_u32(&bar), 1);
+    mbar_init_fence();
+    mbar_expect_tx(smem_u32(&bar), bytes);
+    bulk_load(smem_u32(smem), l + goff, bytes, smem_u32(&bar));
   }
   for (int j = tid; j < g.J; j += TB) {           // j = reference index g*9 + t
     const int gi = j / 9, t = j - gi * 9;
@@ -203,9 +177,9 @@ gn72_apply_kernel(const T* __restrict__ l, const float* __restrict__ lbias, cons
     s_coef[(gi >> 3) * 72 + t * 8 + (gi & 7)] = make_float2(a, c);
   }
   __syncthreads();
-  g7_wait(g7_smem(&bar), 0);
+  mbar_wait(smem_u32(&bar), 0);
   if (tid < nblk) {
-    const uint32_t sa = g7_smem(smem) + tid * 72 * (int)sizeof(T);
+    const uint32_t sa = smem_u32(smem) + tid * 72 * (int)sizeof(T);
     T v[72], o[72];
     g7_ld_block<T>(sa, v);
     const float2* cf = s_coef + (tid % g.nchunk) * 72;
@@ -217,10 +191,10 @@ gn72_apply_kernel(const T* __restrict__ l, const float* __restrict__ lbias, cons
         o[t * 8 + i] = Elem<T>::from(fmaf(to_acc(v[i * 9 + t]), ac.x, ac.y));
       }
     g7_st_block<T>(sa, o);
-    g7_fence_async();
+    fence_proxy_async();
   }
   __syncthreads();
-  if (tid == 0) g7_bulk_store(out + goff, g7_smem(smem), bytes);
+  if (tid == 0) bulk_store_and_wait(out + goff, smem_u32(smem), bytes);
 }
 
 // ------------------------------------------------------------------------------------------------ backward sums
@@ -242,14 +216,15 @@ gn72_bwd_sums_kernel(const T* __restrict__ dg, const T* __restrict__ l, float* _
   const T* s_dg = reinterpret_cast<const T*>(smem);
   const T* s_l = reinterpret_cast<const T*>(smem + (size_t)TB * 72 * sizeof(T));
   if (tid == 0) {
-    g7_mbar_init(g7_smem(&bar), 1);
-    g7_expect_tx(g7_smem(&bar), 2 * bytes);
-    g7_bulk_load(g7_smem(s_dg), dg + goff, bytes, g7_smem(&bar));
-    g7_bulk_load(g7_smem(s_l), l + goff, bytes, g7_smem(&bar));
+    mbar_init(smem_u32(&bar), 1);
+    mbar_init_fence();
+    mbar_expect_tx(smem_u32(&bar), 2 * bytes);
+    bulk_load(smem_u32(s_dg), dg + goff, bytes, smem_u32(&bar));
+    bulk_load(smem_u32(s_l), l + goff, bytes, smem_u32(&bar));
   }
   for (int i = tid; i < 3 * g.J; i += G7_SUM_THREADS) s_p[i] = 0.f;
   __syncthreads();
-  g7_wait(g7_smem(&bar), 0);
+  mbar_wait(smem_u32(&bar), 0);
   const int RL = G7_SUM_THREADS >= g.J ? G7_SUM_THREADS / g.J : 1;        // row lanes per column
   for (int c = tid; c < g.J * RL; c += G7_SUM_THREADS) {
     const int j = c % g.J, rl = c / g.J;
@@ -350,12 +325,13 @@ gn72_bwd_apply_kernel(const T* __restrict__ dg, const T* __restrict__ l, const f
   const int blk0 = blockIdx.x * TB, nblk = min(TB, g.bps - blk0);
   const uint32_t bytes = (uint32_t)nblk * 72u * sizeof(T);
   const long long goff = ((long long)b * g.bps + blk0) * 72;
-  const uint32_t sa_dg = g7_smem(smem), sa_l = sa_dg + TB * 72 * (int)sizeof(T);
+  const uint32_t sa_dg = smem_u32(smem), sa_l = sa_dg + TB * 72 * (int)sizeof(T);
   if (tid == 0) {
-    g7_mbar_init(g7_smem(&bar), 1);
-    g7_expect_tx(g7_smem(&bar), 2 * bytes);
-    g7_bulk_load(sa_dg, dg + goff, bytes, g7_smem(&bar));
-    g7_bulk_load(sa_l, l + goff, bytes, g7_smem(&bar));
+    mbar_init(smem_u32(&bar), 1);
+    mbar_init_fence();
+    mbar_expect_tx(smem_u32(&bar), 2 * bytes);
+    bulk_load(sa_dg, dg + goff, bytes, smem_u32(&bar));
+    bulk_load(sa_l, l + goff, bytes, smem_u32(&bar));
   }
   const float inv_n = 1.f / (9.f * (float)g.HW);
   for (int j = tid; j < g.J; j += TB) {
@@ -366,7 +342,7 @@ gn72_bwd_apply_kernel(const T* __restrict__ dg, const T* __restrict__ l, const f
     if (j == gi * 9) s_bg[gi] = -rs * rs * k2;
   }
   __syncthreads();
-  g7_wait(g7_smem(&bar), 0);
+  mbar_wait(smem_u32(&bar), 0);
   if (tid < nblk) {
     const int chunk = tid % g.nchunk;
     T d[72], v[72], o[72];
@@ -384,10 +360,10 @@ gn72_bwd_apply_kernel(const T* __restrict__ dg, const T* __restrict__ l, const f
       }
     }
     g7_st_block<T>(sa_l + tid * 72 * (int)sizeof(T), o);
-    g7_fence_async();
+    fence_proxy_async();
   }
   __syncthreads();
-  if (tid == 0) g7_bulk_store(dl + goff, sa_l, bytes);
+  if (tid == 0) bulk_store_and_wait(dl + goff, sa_l, bytes);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
