@@ -9,6 +9,8 @@ Run in the build container (needs /root/reference):   python -m oracle.make_gold
 * agg_selftest_*.npz : the right-hand sides of the reference self-tests
   (aggregation_zeropad.py:238-292, aggregation_zeropad_mix.py:344-383) at their exact shapes,
   evaluated with torch's Unfold -- the reference stores no vectors, this identity is its only pin.
+* cotnet50_eval_logits.npz / cotnext50_eval_logits.npz : eval logits of the reference's unmodified ``cotnet50`` /
+  ``cotnext50_2x48d`` with seeded parameters: the pin of oracle/cot_model_ref.py (CPU baseline of bench.py).
 * se_cotnetd50_eval_logits.npz : eval logits of the reference's unmodified ``se_cotnetd_50`` (models/cotnet_hybrid.py:458)
   on a seeded input with seeded parameters (``hybrid_seeded_state``): the pin of cotnet_b200/backbone_hybrid.py.
 """
@@ -89,25 +91,25 @@ def _mix_fixture(fname, seed):
 
 def hybrid_seeded_state(model, seed):
     """Deterministic, non-trivial parameters / BatchNorm statistics for a whole-model fixture without shipping a 90 MB state
-    dict: re-initialise every tensor of `model` (any module with the SE-CoTNetD state-dict layout) from one seeded
-    generator, in state-dict order.  Used identically here (on the reference model) and in tests/test_hybrid_cpu.py (on
-    the mirror)."""
-    gen = torch.Generator().manual_seed(seed)
+    dict: every floating-point tensor of `model.state_dict()` is re-initialised from its OWN generator seeded by
+    (seed, crc32(name)), so the result depends only on the tensor's name and shape -- not on module definition order.  Used
+    identically here (on the reference models) and in the tests (on the mirrors / the oracle model)."""
+    import zlib
     with torch.no_grad():
         for name, t in model.state_dict().items():
             if not t.dtype.is_floating_point:
                 continue
+            gen = torch.Generator().manual_seed((int(seed) * 1000003 + zlib.crc32(name.encode())) % (2 ** 31))
             if name.endswith("running_var"):
                 t.copy_(torch.rand(t.shape, generator=gen) * 0.4 + 0.8)
             elif name.endswith("running_mean"):
                 t.copy_(torch.randn(t.shape, generator=gen) * 0.1)
-            elif t.dim() == 1 and (".bn" in name or name.startswith("bn") or "downsample.2" in name or "embed.1" in name
-                                   or "embed.4" in name or "key_embed.1" in name or "conv1x1.1" in name or "se.1" in name
-                                   or name.split(".")[-2].isdigit() and name.endswith("weight")):
-                t.copy_(torch.rand(t.shape, generator=gen) * 0.5 + 0.5 if name.endswith("weight")
-                        else torch.randn(t.shape, generator=gen) * 0.1)
+            elif t.dim() == 1 and name.endswith("weight"):            # norm-layer scales
+                t.copy_(torch.rand(t.shape, generator=gen) * 0.5 + 0.5)
+            elif t.dim() == 1:                                          # biases
+                t.copy_(torch.randn(t.shape, generator=gen) * 0.1)
             else:
-                fan = max(1, t[0].numel()) if t.dim() > 1 else max(1, t.numel())
+                fan = max(1, t[0].numel())
                 t.copy_(torch.randn(t.shape, generator=gen) * (1.0 / fan) ** 0.5)
     return model
 
@@ -117,6 +119,18 @@ def _hybrid_fixture(fname, seed):
     ref = ref_import.load()
     m = hybrid_seeded_state(ref.hybrid.se_cotnetd_50(), seed).eval()
     x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(seed + 1))
+    with torch.no_grad():
+        y = m(x)
+    np.savez_compressed(os.path.join(OUT, fname), x=x.numpy(), logits=y.numpy(), seed=np.int64(seed),
+                        n_params=np.int64(sum(p.numel() for p in m.parameters())))
+
+
+def _trunk_fixture(fname, entry, seed, res=64):
+    """CoTNet-50 / CoTNeXt-50 (models/cotnet.py:266-288) eval logits from the reference's own model code: the pin of
+    oracle/cot_model_ref.py (the CPU baseline / reference arm of bench.py) on boxes without the reference tree."""
+    ref = ref_import.load()
+    m = hybrid_seeded_state(getattr(ref, entry)(), seed).eval()
+    x = torch.randn(2, 3, res, res, generator=torch.Generator().manual_seed(seed + 1))
     with torch.no_grad():
         y = m(x)
     np.savez_compressed(os.path.join(OUT, fname), x=x.numpy(), logits=y.numpy(), seed=np.int64(seed),
@@ -136,6 +150,8 @@ def main():
     _agg_fixture("agg_cot_k3.npz", 3, 1, 2, 16, 2, 7, 6, 13)
     _mix_fixture("agg_mix_selftest.npz", 14)
     _hybrid_fixture("se_cotnetd50_eval_logits.npz", 2024)
+    _trunk_fixture("cotnet50_eval_logits.npz", "cotnet50", 2025)
+    _trunk_fixture("cotnext50_eval_logits.npz", "cotnext50_2x48d", 2026)
 
 
 if __name__ == "__main__":

@@ -118,3 +118,22 @@ def test_reference_kernel_cubins_are_consistent():
             assert e["grid"] == (e["nthreads"] // 2 + 1023) // 1024
         else:
             assert e["grid"] == (e["nthreads"] + 1023) // 1024
+
+
+@pytest.mark.parametrize("name,fixture", [("cotnet50", "cotnet50_eval_logits.npz"), ("cotnext50_2x48d", "cotnext50_eval_logits.npz")])
+def test_oracle_model_matches_reference_golden_logits(golden_dir, name, fixture):
+    """oracle/cot_model_ref.py (the CPU baseline and the `--impl reference` arm of bench.py, and the checker of the GPU
+    backbone tests) against eval logits of the reference's own cotnet50 / cotnext50_2x48d (oracle/make_golden.py) on the
+    same seeded parameters -- runs on every box, the reference tree is not needed."""
+    from cotnet_b200 import backbone
+    from oracle import cot_model_ref, make_golden
+    g = np.load(os.path.join(golden_dir, fixture))
+    m = make_golden.hybrid_seeded_state(backbone.MODELS[name](), int(g["seed"]))      # mirror = reference state-dict names
+    assert sum(p.numel() for p in m.parameters()) == int(g["n_params"])
+    o = cot_model_ref.build(name)
+    o.load_reference_state(m.state_dict())
+    o.eval()
+    with torch.no_grad():
+        y = o(torch.from_numpy(g["x"]))
+    err = (y - torch.from_numpy(g["logits"])).abs().max().item()
+    assert err <= 2e-5, err
