@@ -35,6 +35,17 @@ IMAGENET_MEAN = (0.485 * 255, 0.456 * 255, 0.406 * 255)
 IMAGENET_STD = (0.229 * 255, 0.224 * 255, 0.225 * 255)
 
 
+PRETTY = {"cotnet50": "CoTNet-50", "cotnext50_2x48d": "CoTNeXt-50", "cotnet101": "CoTNet-101",
+          "cotnext101_2x48d": "CoTNeXt-101", "se_cotnetd_50": "SE-CoTNetD-50", "se_cotnetd_101": "SE-CoTNetD-101",
+          "se_cotnetd_152": "SE-CoTNetD-152"}
+
+
+def metric_name(model, res, batch, fwd_only=False):
+    """ONE metric string for both arms (the driver divides lines whose `metric` matches exactly).  The CPU arm times a
+    bounded sample of this workload and says so in its `config` / `cpu_baseline.sample`."""
+    return "%s images/sec (%s, %d^2, bs%d/GPU)" % (PRETTY.get(model, model), "fwd" if fwd_only else "fwd+bwd", res, batch)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,7 +237,7 @@ def main_reference(a):
                     % (a.model, sample, a.res, a.res, CPU_THREADS["n"], os.cpu_count() or 1, usable_cores(),
                        CPU_THREADS["timing"])}
     print(json.dumps({
-        "impl": "reference", "metric": "CoTNet-50 images/sec (fwd+bwd, 224^2)", "value": v, "unit": "images/s",
+        "impl": "reference", "metric": metric_name(a.model, a.res, a.batch), "value": v, "unit": "images/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s %dx%d fwd+bwd+SGD on host CPU cores, %d images/step (bounded sample of the bs%d workload)"
@@ -437,8 +448,7 @@ def main_ours(a):
 
     if rank == 0:
         line = {
-            "metric": "CoTNet-50 images/sec (fwd+bwd, 224^2, bs256/GPU)" if a.model == "cotnet50" else
-                      "%s images/sec (fwd+bwd, %d^2, bs%d/GPU)" % (a.model, R, B),
+            "metric": metric_name(a.model, R, B, a.fwd_only),
             "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",

@@ -44,6 +44,12 @@ SYMBOLS = {
     "cotb200_agg_zeropad_bwd": (ctypes.c_int, [_DP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "cotb200_agg_zeropad_mix_fwd": (ctypes.c_int, [_DP] + [ctypes.c_int] * 4 + [_VP] * 5),
     "cotb200_agg_zeropad_mix_bwd": (ctypes.c_int, [_DP] + [ctypes.c_int] * 4 + [_VP] * 8),
+    "cotb200_agg_refpad_fwd": (ctypes.c_int, [_DP, _VP, _VP, _VP, _VP]),
+    "cotb200_agg_refpad_bwd": (ctypes.c_int, [_DP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "cotb200_agg_zeropad_dilate_fwd": (ctypes.c_int, [_DP, _VP, _VP, _VP, _VP, _VP]),
+    "cotb200_agg_zeropad_dilate_bwd": (ctypes.c_int, [_DP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "cotb200_agg_zeropad_mix_merge_fwd": (ctypes.c_int, [_DP] + [ctypes.c_int] * 4 + [_VP] * 4),
+    "cotb200_agg_zeropad_mix_merge_bwd": (ctypes.c_int, [_DP] + [ctypes.c_int] * 4 + [_VP] * 6),
     "cotb200_col_stats": (ctypes.c_int, [ctypes.c_int] * 4 + [_VP] * 4),
     "cotb200_tail_pool": (ctypes.c_int, [ctypes.c_int] * 4 + [_VP] * 6),
     "cotb200_tail_combine": (ctypes.c_int, [ctypes.c_int] * 4 + [_VP] * 7),
@@ -68,6 +74,12 @@ SYMBOLS = {
                           + [_VP, ctypes.c_longlong, _VP, _VP, ctypes.c_int, _VP, _VP, _VP]),
     "cotb200_conv3x3_bf16": (ctypes.c_int, [ctypes.c_int] * 4 + [_VP, ctypes.c_longlong, _VP, ctypes.c_int, _VP,
                                                                  ctypes.c_longlong, _VP, _VP, ctypes.c_int, _VP, _VP, _VP]),
+    "cotb200_gather_chunk": (ctypes.c_int, []),
+    "cotb200_multi_gather": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_float, _VP]),
+    "cotb200_sgd_ema_step": (ctypes.c_int, [ctypes.c_longlong, _VP, _VP, ctypes.c_int, _VP, _VP, _VP, _VP, ctypes.c_int, _VP]),
+    "cotb200_multi_lerp": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
+    "cotb200_u8_to_nhwc": (ctypes.c_int, [ctypes.c_int] * 5 + [_VP, _VP, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+                                          _VP, _VP, _VP]),
 }
 
 
@@ -113,6 +125,13 @@ def dtype_code(t: torch.Tensor) -> int:
 
 
 def stream_ptr(t: torch.Tensor) -> int:
+    """Current stream of t's device.  The C ABI launches on the CURRENT device (like the reference's
+    `with torch.cuda.device_of(input)`, cupy_layers/aggregation_zeropad.py:129): a tensor that lives on another
+    device would be launched with a foreign stream, so that is refused loudly instead of guarded silently."""
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        raise RuntimeError("cotb200: tensor on %s but the current CUDA device is cuda:%d; wrap the call in "
+                           "`with torch.cuda.device_of(tensor):` (one process per GPU is the supported layout)"
+                           % (t.device, torch.cuda.current_device()))
     return torch.cuda.current_stream(t.device).cuda_stream
 
 

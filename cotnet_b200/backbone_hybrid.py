@@ -9,7 +9,8 @@ module names so that its checkpoints load with ``strict=True``:
 ``conv2`` is the CoT layer (``cot_layer.CoTLayer``: libcotb200 kernels) where the reference uses it -- every block of
 layer4 and the even blocks of layer3 -- and ``SplitAttnConv2d`` (radix 1, swish) elsewhere (:138-156).  The BatchNorm /
 ReLU / residual glue of the bottleneck and the 3x3/s2 ``avd`` pooling reuse the fused kernels of the CoTNet trunk
-(``backbone.Bottleneck``); the split-attention convolution itself stays PyTorch in this round (next: DESIGN.md section 6).
+(``backbone.Bottleneck``); the split-attention block runs its bn0 -> SiLU -> pool -> MLP -> gate chain on the CoT tail kernels
+(``fused.split_attn_tail``), only its 3x3 convolution stays cuDNN.
 Only what ``se_cotnetd_{50,101,152}`` (:458-483) configure is implemented: deep stem, no stem max-pool, stride 2 in every
 stage, avg-pool down-sampling, optional BlurPool anti-aliasing (152).
 """
@@ -56,6 +57,10 @@ class SplitAttnConv2d(nn.Module):
         self.fc2 = nn.Conv2d(attn_chs, mid_chs, 1, groups=groups)
 
     def forward(self, x):
+        if self.radix == 1 and self.cardinality == 1 and fused.supported(x):
+            # channels_last CUDA tensors: everything after the convolution on the fused tail kernels (fused.split_attn_tail)
+            u = self.conv(x).contiguous(memory_format=torch.channels_last)
+            return fused.split_attn_tail(u, self.bn0, self.fc1, self.bn1, self.fc2)
         x = self.act0(self.bn0(self.conv(x)))
         B, RC, H, W = x.shape
         if self.radix > 1:

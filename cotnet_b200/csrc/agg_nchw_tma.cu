@@ -315,7 +315,7 @@ int nchw_tma_launch(int mode, int N, int C, int H, int W, int wc, long long a_sn
     COTB200_PROF_B(mode == 0 ? "agg3_fwd_nchw_tma" : mode == 1 ? "agg3_dx_nchw_tma" : "agg3_dw_nchw_tma", bytes);
 #define NT_GO(P, M)                                                                                                   \
   {                                                                                                                   \
-    static bool cfg = false;                                                                                          \
+    static PerDevFlag cfgd; bool& cfg = cfgd.get();                                                                   \
     if (!cfg) {                                                                                                       \
       cudaError_t e = cudaFuncSetAttribute(agg3_nchw_tma_kernel<T, P, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            220 * 1024);                                                               \

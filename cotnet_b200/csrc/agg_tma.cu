@@ -387,8 +387,8 @@ static int agg_tma_launch(int mode, const Nhwc2Args& a, const T* A, const T* Bp,
     int grid = num_sms();
     if (grid > p.total_tiles) grid = p.total_tiles;
     cudaError_t e = cudaSuccess;
-    static bool cfg[8] = {false, false, false, false, false, false, false, false};
-#define AT_CFG(idx, fn) if (!cfg[idx]) { e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); cfg[idx] = (e == cudaSuccess); }
+    static PerDevFlag cfgd[3];
+#define AT_CFG(idx, fn) if (bool& cfgf = cfgd[idx].get(); !cfgf) { e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); cfgf = (e == cudaSuccess); }
     if (mode == 0) {
       AT_CFG(0, (agg3_fwd_tma_kernel<T, 0>));
       if (e == cudaSuccess) { COTB200_PROF_B("agg3_fwd_tma", ((double)a.N * a.H * a.W) * (2.0 * a.C + 9.0 * a.wc) * sizeof(T)); agg3_fwd_tma_kernel<T, 0><<<grid, threads, smem, st>>>(ma, mb, out, p); }

@@ -815,3 +815,70 @@ extern "C" int cotb200_agg_zeropad_mix_bwd(const cotb200_agg_desc* d, int k2h, i
   });
   return 0;
 }
+
+// ---- mix_merge: the mix op with BOTH weight sets packed in one tensor w [n, heads*wc*(k1^2 + k2^2), ho, wo]
+// (cupy_layers/aggregation_zeropad_mix_merge.py:20-179; the first heads*wc*k1^2 channels are w1 viewed [heads, wc, k1^2],
+// the rest w2).  Same arithmetic as cotb200_agg_zeropad_mix_*; only the batch stride of the weights differs, so the
+// stride-aware generic kernels run it on the packed tensor in place (no split / cat copies).
+static void merge_strides(Geo& g1, Geo& g2, long long& off2) {
+  const long long plane = (long long)g1.HO * g1.WO;
+  const long long tot = (long long)g1.heads * g1.wc * (g1.K2 + g2.K2) * plane;
+  off2 = (long long)g1.heads * g1.wc * g1.K2 * plane;
+  g1.w_sn = tot; g2.w_sn = tot;
+}
+
+extern "C" int cotb200_agg_zeropad_mix_merge_fwd(const cotb200_agg_desc* d, int k2h, int k2w, int p2h, int p2w, const void* x,
+                                                 const void* w, void* y, void* stream) {
+  Geo g1, g2;
+  int rc = resolve_mix(d, k2h, k2w, p2h, p2w, g1, g2);
+  if (rc) return rc;
+  if (!x || !w || !y) { set_error("agg_zeropad_mix_merge_fwd: NULL tensor pointer"); return COTB200_ENULL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  long long off2;
+  merge_strides(g1, g2, off2);
+  const long long half = (long long)g1.heads * g1.C * g1.HO * g1.WO;
+  const long long total = (long long)g1.N * half;
+  COTB200_DISPATCH_DTYPE(d->dtype, {
+    COTB200_PROF("agg_mix_merge_fwd");
+    agg_fwd_generic<T><<<grid_for(total, 256, 16), 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, g1, total);
+    rc = check_launch("agg_mix_merge_fwd");
+    if (rc) return rc;
+    agg_fwd_generic<T><<<grid_for(total, 256, 16), 256, 0, st>>>((const T*)x, (const T*)w + off2, (T*)y + half, g2, total);
+    return check_launch("agg_mix_merge_fwd");
+  });
+  return 0;
+}
+
+extern "C" int cotb200_agg_zeropad_mix_merge_bwd(const cotb200_agg_desc* d, int k2h, int k2w, int p2h, int p2w, const void* dy,
+                                                 const void* x, const void* w, void* dx, void* dw, void* stream) {
+  Geo g1, g2;
+  int rc = resolve_mix(d, k2h, k2w, p2h, p2w, g1, g2);
+  if (rc) return rc;
+  if (!dy || (dx && !w) || (dw && !x)) { set_error("agg_zeropad_mix_merge_bwd: NULL tensor pointer"); return COTB200_ENULL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  long long off2;
+  merge_strides(g1, g2, off2);
+  const long long half = (long long)g1.heads * g1.C * g1.HO * g1.WO;
+  COTB200_DISPATCH_DTYPE(d->dtype, {
+    if (dx) {
+      const long long total = (long long)g1.N * g1.C * g1.H * g1.W;
+      COTB200_PROF("agg_mix_merge_dx");
+      agg_dx_generic2<T><<<grid_for(total, 256, 16), 256, 0, st>>>((const T*)dy, (const T*)w, g1, (const T*)dy + half,
+                                                                  (const T*)w + off2, g2, (T*)dx, total);
+      rc = check_launch("agg_mix_merge_dx");
+      if (rc) return rc;
+    }
+    if (dw) {
+      COTB200_PROF("agg_mix_merge_dw");
+      const long long t1 = (long long)g1.N * g1.heads * g1.wc * g1.K2 * g1.HO * g1.WO;
+      agg_dw_generic<T><<<grid_for(t1, 256, 16), 256, 0, st>>>((const T*)dy, (const T*)x, (T*)dw, g1, t1);
+      rc = check_launch("agg_mix_merge_dw");
+      if (rc) return rc;
+      const long long t2 = (long long)g2.N * g2.heads * g2.wc * g2.K2 * g2.HO * g2.WO;
+      agg_dw_generic<T><<<grid_for(t2, 256, 16), 256, 0, st>>>((const T*)dy + half, (const T*)x, (T*)dw + off2, g2, t2);
+      rc = check_launch("agg_mix_merge_dw");
+    }
+    return rc;
+  });
+  return 0;
+}

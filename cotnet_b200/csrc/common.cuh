@@ -38,15 +38,27 @@ struct ProfScope {
 #define COTB200_PROF(name) cotb200::ProfScope _prof_scope(name, st)
 #define COTB200_PROF_B(name, bytes) cotb200::ProfScope _prof_scope(name, st, (double)(bytes))
 
+// Per-device memo slots: a process may drive several GPUs (the reference memoises its kernels per device too,
+// cupy_layers/utils.py:14), so nothing that depends on the device is cached in a plain static.
+inline int cur_dev_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & 63;
+}
+struct PerDevFlag {
+  bool v[64] = {};
+  bool& get() { return v[cur_dev_slot()]; }
+};
 inline int num_sms() {
-  static int sms = 0;
-  if (!sms) {
+  static int sms[64] = {};
+  int& s = sms[cur_dev_slot()];
+  if (!s) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+    cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev);
+    if (s <= 0) s = 148;
   }
-  return sms;
+  return s;
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

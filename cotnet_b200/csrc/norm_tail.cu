@@ -106,11 +106,12 @@ tail_pool_kernel(const T* __restrict__ u, const T* __restrict__ k, const float* 
     #pragma unroll 2
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
-      const Pack<T, VEC> kv = ld_pack<T, VEC>(k + base + (long long)r * g.C);
+      Pack<T, VEC> kv;
+      if (k) kv = ld_pack<T, VEC>(k + base + (long long)r * g.C);      // k == NULL: SplitAttnConv2d (radix 1) pools y alone
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const float z = fmaf(to_acc(uv.v[i]), sc[i], sh[i]);
-        acc[0][i] += z * sigmoid_t<T>(z) + to_acc(kv.v[i]);
+        acc[0][i] += z * sigmoid_t<T>(z) + (k ? to_acc(kv.v[i]) : 0.f);
       }
     }
   }
@@ -137,12 +138,13 @@ tail_combine_kernel(const T* __restrict__ u, const T* __restrict__ k, const floa
   #pragma unroll 2
   for (int r = r0 + ty; r < r1; r += g.ry) {
     const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
-    const Pack<T, VEC> kv = ld_pack<T, VEC>(k + base + (long long)r * g.C);
+    Pack<T, VEC> kv;
+    if (k) kv = ld_pack<T, VEC>(k + base + (long long)r * g.C);
     Pack<T, VEC> o;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const float z = fmaf(to_acc(uv.v[i]), sc[i], sh[i]);
-      o.v[i] = Elem<T>::from(fmaf(a0[i], z * sigmoid_t<T>(z), a1[i] * to_acc(kv.v[i])));
+      o.v[i] = Elem<T>::from(k ? fmaf(a0[i], z * sigmoid_t<T>(z), a1[i] * to_acc(kv.v[i])) : a0[i] * (z * sigmoid_t<T>(z)));
     }
     st_pack<T, VEC>(out + base + (long long)r * g.C, o);
   }
@@ -167,13 +169,14 @@ tail_bwd_sums_kernel(const T* __restrict__ dout, const T* __restrict__ u, const 
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> dv = ld_pack<T, VEC>(dout + base + (long long)r * g.C);
       const Pack<T, VEC> uv = ld_pack<T, VEC>(u + base + (long long)r * g.C);
-      const Pack<T, VEC> kv = ld_pack<T, VEC>(k + base + (long long)r * g.C);
+      Pack<T, VEC> kv;
+      if (k) kv = ld_pack<T, VEC>(k + base + (long long)r * g.C);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const float z = fmaf(to_acc(uv.v[i]), sc[i], sh[i]);
         const float d = to_acc(dv.v[i]);
         acc[0][i] = fmaf(d, z * sigmoid_t<T>(z), acc[0][i]);
-        acc[1][i] = fmaf(d, to_acc(kv.v[i]), acc[1][i]);
+        if (k) acc[1][i] = fmaf(d, to_acc(kv.v[i]), acc[1][i]);
       }
     }
   }
@@ -263,7 +266,7 @@ tail_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ u, const
       o2.v[i] = Elem<T>::from(fmaf(a1[i], d, dp[i]));
     }
     st_pack<T, VEC>(du + base + (long long)r * g.C, o1);
-    st_pack<T, VEC>(dk + base + (long long)r * g.C, o2);
+    if (dk) st_pack<T, VEC>(dk + base + (long long)r * g.C, o2);
   }
 }
 
@@ -710,7 +713,7 @@ extern "C" int cotb200_col_stats(int dtype, int B, int HW, int C, const void* x,
 
 extern "C" int cotb200_tail_pool(int dtype, int B, int HW, int C, const void* u, const void* k, const float* scale,
                                  const float* shift, float* psum, void* stream) {
-  if (!u || !k || !scale || !shift || !psum) { set_error("tail_pool: NULL pointer"); return COTB200_ENULL; }
+  if (!u || !scale || !shift || !psum) { set_error("tail_pool: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("tail_pool: fp64 not supported"); return COTB200_EDTYPE; }
   cudaStream_t st = (cudaStream_t)stream;
   COTB200_DISPATCH_DTYPE(dtype, {
@@ -730,7 +733,7 @@ extern "C" int cotb200_tail_pool(int dtype, int B, int HW, int C, const void* u,
 
 extern "C" int cotb200_tail_combine(int dtype, int B, int HW, int C, const void* u, const void* k, const float* scale,
                                     const float* shift, const float* a, void* out, void* stream) {
-  if (!u || !k || !scale || !shift || !a || !out) { set_error("tail_combine: NULL pointer"); return COTB200_ENULL; }
+  if (!u || !scale || !shift || !a || !out) { set_error("tail_combine: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("tail_combine: fp64 not supported"); return COTB200_EDTYPE; }
   cudaStream_t st = (cudaStream_t)stream;
   COTB200_DISPATCH_DTYPE(dtype, {
@@ -749,7 +752,7 @@ extern "C" int cotb200_tail_combine(int dtype, int B, int HW, int C, const void*
 
 extern "C" int cotb200_tail_bwd_sums(int dtype, int B, int HW, int C, const void* dout, const void* u, const void* k,
                                      const float* scale, const float* shift, float* S, void* stream) {
-  if (!dout || !u || !k || !scale || !shift || !S) { set_error("tail_bwd_sums: NULL pointer"); return COTB200_ENULL; }
+  if (!dout || !u || !scale || !shift || !S) { set_error("tail_bwd_sums: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("tail_bwd_sums: fp64 not supported"); return COTB200_EDTYPE; }
   cudaStream_t st = (cudaStream_t)stream;
   COTB200_DISPATCH_DTYPE(dtype, {
@@ -792,7 +795,7 @@ extern "C" int cotb200_tail_bwd_apply(int dtype, int B, int HW, int C, const voi
                                       const float* shift, const float* mu, const float* rstd, const float* a,
                                       const float* dpn, const float* c1, const float* c2, float inv_n, float pscale, void* du, void* dk,
                                       void* stream) {
-  if (!dout || !u || !scale || !shift || !mu || !rstd || !a || !dpn || !du || !dk) { set_error("tail_bwd_apply: NULL pointer"); return COTB200_ENULL; }
+  if (!dout || !u || !scale || !shift || !mu || !rstd || !a || !dpn || !du) { set_error("tail_bwd_apply: NULL pointer"); return COTB200_ENULL; }
   if (dtype == COTB200_F64) { set_error("tail_bwd_apply: fp64 not supported"); return COTB200_EDTYPE; }
   cudaStream_t st = (cudaStream_t)stream;
   COTB200_DISPATCH_DTYPE(dtype, {

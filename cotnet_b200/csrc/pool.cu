@@ -12,10 +12,10 @@ namespace cotb200 {
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 avgpool3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int Ho, int Wo, int CQ) {
-  const int item = blockIdx.x * 256 + threadIdx.x;
+  const int item = blockIdx.y * 256 + threadIdx.x;
   if (item >= Wo * CQ) return;
   const int q = item % CQ, wo = item / CQ;
-  const int row = blockIdx.y, n = row / Ho, ho = row - n * Ho;
+  const int row = blockIdx.x, n = row / Ho, ho = row - n * Ho;
   const int C = CQ * VEC;
   const T* xb = x + ((long long)n * H * W) * C + q * VEC;
   float acc[VEC];
@@ -43,10 +43,10 @@ avgpool3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 avgpool3s2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int H, int W, int Ho, int Wo, int CQ) {
-  const int item = blockIdx.x * 256 + threadIdx.x;
+  const int item = blockIdx.y * 256 + threadIdx.x;
   if (item >= W * CQ) return;
   const int q = item % CQ, w = item / CQ;
-  const int row = blockIdx.y, n = row / H, h = row - n * H;
+  const int row = blockIdx.x, n = row / H, h = row - n * H;
   const int C = CQ * VEC;
   const T* gb = dy + ((long long)n * Ho * Wo) * C + q * VEC;
   float acc[VEC];
@@ -80,10 +80,10 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 maxpool3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ idx, int H, int W, int Ho, int Wo,
                       int CQ) {
-  const int item = blockIdx.x * 256 + threadIdx.x;
+  const int item = blockIdx.y * 256 + threadIdx.x;
   if (item >= Wo * CQ) return;
   const int q = item % CQ, wo = item / CQ;
-  const int row = blockIdx.y, n = row / Ho, ho = row - n * Ho;
+  const int row = blockIdx.x, n = row / Ho, ho = row - n * Ho;
   const int C = CQ * VEC;
   const T* xb = x + ((long long)n * H * W) * C + q * VEC;
   float best[VEC];
@@ -120,10 +120,10 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 maxpool3s2_bwd_kernel(const T* __restrict__ dy, const unsigned char* __restrict__ idx, T* __restrict__ dx, int H, int W, int Ho,
                       int Wo, int CQ) {
-  const int item = blockIdx.x * 256 + threadIdx.x;
+  const int item = blockIdx.y * 256 + threadIdx.x;
   if (item >= W * CQ) return;
   const int q = item % CQ, w = item / CQ;
-  const int row = blockIdx.y, n = row / H, h = row - n * H;
+  const int row = blockIdx.x, n = row / H, h = row - n * H;
   const int C = CQ * VEC;
   const long long gb = ((long long)n * Ho * Wo) * C + q * VEC;
   float acc[VEC];
@@ -182,14 +182,13 @@ extern "C" int cotb200_pool3s2_fwd(int dtype, int mode, int N, int H, int W, int
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (mode != 0 && mode != 1)) { set_error("pool3s2_fwd: bad arguments"); return COTB200_EINVAL; }
   if (dtype == COTB200_F64) { set_error("pool3s2: fp64 not supported"); return COTB200_EDTYPE; }
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  if ((long long)N * Ho > 65535LL * 32768) { set_error("pool3s2: too many rows"); return COTB200_ETOOBIG; }
+  if ((long long)N * H > 2147483647LL || (long long)W * C > 65535LL * 256) { set_error("pool3s2: tensor too large for the launch grid"); return COTB200_ETOOBIG; }
   cudaStream_t st = (cudaStream_t)stream;
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
       const int vec = pool_vec<T>(C, x, y);
       const int CQ = C / vec;
-      dim3 grid((Wo * CQ + 255) / 256, N * Ho);
-      if (grid.y > 2147483647u) return COTB200_ETOOBIG;
+      dim3 grid((unsigned)(N * Ho), (Wo * CQ + 255) / 256);   // rows on grid.x (2^31-1 limit), packets on grid.y
       COTB200_PROF_B(mode ? "maxpool3s2_fwd" : "avgpool3s2_fwd", ((double)N * C) * ((double)H * W + (double)Ho * Wo) * sizeof(T));
       POOL_DISPATCH(vec, {
         if (mode == 0) avgpool3s2_fwd_kernel<T, V><<<grid, 256, 0, st>>>((const T*)x, (T*)y, H, W, Ho, Wo, CQ);
@@ -207,12 +206,13 @@ extern "C" int cotb200_pool3s2_bwd(int dtype, int mode, int N, int H, int W, int
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (mode != 0 && mode != 1)) { set_error("pool3s2_bwd: bad arguments"); return COTB200_EINVAL; }
   if (dtype == COTB200_F64) { set_error("pool3s2: fp64 not supported"); return COTB200_EDTYPE; }
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  if ((long long)N * H > 2147483647LL || (long long)W * C > 65535LL * 256) { set_error("pool3s2: tensor too large for the launch grid"); return COTB200_ETOOBIG; }
   cudaStream_t st = (cudaStream_t)stream;
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
       const int vec = pool_vec<T>(C, dy, dx);
       const int CQ = C / vec;
-      dim3 grid((W * CQ + 255) / 256, N * H);
+      dim3 grid((unsigned)(N * H), (W * CQ + 255) / 256);
       COTB200_PROF_B(mode ? "maxpool3s2_bwd" : "avgpool3s2_bwd", ((double)N * C) * ((double)H * W + (double)Ho * Wo) * sizeof(T));
       POOL_DISPATCH(vec, {
         if (mode == 0) avgpool3s2_bwd_kernel<T, V><<<grid, 256, 0, st>>>((const T*)dy, (T*)dx, H, W, Ho, Wo, CQ);

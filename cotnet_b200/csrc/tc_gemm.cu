@@ -393,11 +393,11 @@ static int tc_launch(const CUtensorMap& a1, const CUtensorMap& b1, const CUtenso
   p.stages = TC_STAGES;
   while (p.stages > 2 && p.stages * stage_bytes + out_bytes > 104 * 1024) --p.stages;     // two CTAs per SM when possible
   const int smem = p.stages * stage_bytes + out_bytes + 1024;
-  static int configured = 0;
-  if (configured < smem) {
+  static PerDevFlag configured_d;
+  if (bool& configured = configured_d.get(); !configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    configured = 220 * 1024;
+    configured = true;
   }
   const int total = m_tiles * ((p.N + p.bn - 1) / p.bn);
   int grid = 2 * num_sms();

@@ -327,32 +327,35 @@ def fan_out(x, n):
 
 class CotTailFn(Function):
     """(u, k) -> out of models/cotnet.py:89-104.  `bn` is the nn.BatchNorm2d(dim) module (its buffers are updated in
-    training mode exactly like the module would), `se` the nn.Sequential producing the radix-2 logits."""
+    training mode exactly like the module would); `attn_fn` maps the pooled mean [B, C] (fp32, requires grad) to the
+    mixing weights a [B, C, 2] -- the radix-2 softmax of the `se` MLP for the CoT layer.  With k = None the same kernels
+    compute SplitAttnConv2d's radix-1 chain (models/layers/split_attn.py:68-86): bn0 -> SiLU -> pool -> MLP -> sigmoid
+    gate, a[..., 0] = the gate."""
 
     @staticmethod
-    def forward(ctx, u, k, bn_weight, bn_bias, bn, se, *se_params):
-        assert _is_cl(u) and _is_cl(k) and u.dtype == k.dtype and u.shape == k.shape
+    def forward(ctx, u, k, bn_weight, bn_bias, bn, attn_fn, *mlp_params):
+        assert _is_cl(u) and (k is None or (_is_cl(k) and u.dtype == k.dtype and u.shape == k.shape))
         B, C, H, W = u.shape
         HW, n = H * W, float(B * H * W)
         lib, st, dt = _lib.load(), _lib.stream_ptr(u), _lib.dtype_code(u)
-        u, k = u.detach(), k.detach()
+        u, k = u.detach(), (None if k is None else k.detach())
         ss, training = _bn_batch_stats(u, bn, bn_weight, bn_bias, lib, st, dt)     # [4,C]: scale, shift, mean, rstd
         scale, shift, mean, rstd = ss[0], ss[1], ss[2], ss[3]
         psum = _zeros((B, C,), u.device)
-        _lib.check(lib.cotb200_tail_pool(dt, B, HW, C, u.data_ptr(), k.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+        _lib.check(lib.cotb200_tail_pool(dt, B, HW, C, u.data_ptr(), _lib.ptr(k), scale.data_ptr(), shift.data_ptr(),
                                          psum.data_ptr(), st), "tail_pool")
         # the SE MLP on [B, C] (3 tiny GEMV-sized ops) stays PyTorch; its graph is kept for backward
         # ... in fp32 whatever the storage dtype: se.1 normalises over the batch, which amplifies bf16 rounding of the
         # pooled descriptor by an order of magnitude (the fp32 math costs nothing at [B, C])
         with torch.enable_grad(), torch.autocast("cuda", enabled=False):
             p_leaf = (psum / HW).requires_grad_(True)
-            a = torch.softmax(_se_fp32(se, p_leaf).view(B, C, 2), dim=2)
+            a = attn_fn(p_leaf)
         a_c = a.detach().contiguous()
         out = torch.empty_like(u, memory_format=torch.channels_last)
-        _lib.check(lib.cotb200_tail_combine(dt, B, HW, C, u.data_ptr(), k.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+        _lib.check(lib.cotb200_tail_combine(dt, B, HW, C, u.data_ptr(), _lib.ptr(k), scale.data_ptr(), shift.data_ptr(),
                                             a_c.data_ptr(), out.data_ptr(), st), "tail_combine")
         ctx.save_for_backward(u, k, scale, shift, mean, rstd, a_c)
-        ctx.graph = (p_leaf, a, [p for p in se_params])
+        ctx.graph = (p_leaf, a, [p for p in mlp_params])
         ctx.training = training
         ctx.bn_dtypes = (bn_weight.dtype, bn_bias.dtype)
         return out
@@ -360,17 +363,17 @@ class CotTailFn(Function):
     @staticmethod
     def backward(ctx, dout):
         u, k, scale, shift, mean, rstd, a_c = ctx.saved_tensors
-        p_leaf, a, se_params = ctx.graph
+        p_leaf, a, mlp_params = ctx.graph
         B, C, H, W = u.shape
         HW, n = H * W, float(B * H * W)
         lib, st, dt = _lib.load(), _lib.stream_ptr(u), _lib.dtype_code(u)
         dout = dout.contiguous(memory_format=torch.channels_last)
         S = _zeros((B, C, 2,), u.device)
-        _lib.check(lib.cotb200_tail_bwd_sums(dt, B, HW, C, dout.data_ptr(), u.data_ptr(), k.data_ptr(), scale.data_ptr(),
+        _lib.check(lib.cotb200_tail_bwd_sums(dt, B, HW, C, dout.data_ptr(), u.data_ptr(), _lib.ptr(k), scale.data_ptr(),
                                              shift.data_ptr(), S.data_ptr(), st), "tail_bwd_sums")
-        grads = torch.autograd.grad(a, [p_leaf] + se_params, grad_outputs=S, allow_unused=True)
+        grads = torch.autograd.grad(a, [p_leaf] + mlp_params, grad_outputs=S, allow_unused=True)
         dpn = grads[0].contiguous()                      # d/d(pooled mean); the kernels apply the 1/HW (pscale)
-        se_grads = [None if g is None else g for g in grads[1:]]
+        mlp_grads = [None if g is None else g for g in grads[1:]]
         sums = torch.zeros(2, C, dtype=torch.float32, device=u.device)          # escapes as dgamma/dbeta
         need_param = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         if ctx.training or need_param:
@@ -381,14 +384,14 @@ class CotTailFn(Function):
         if ctx.training:
             c1, c2 = sums[0], sums[1]
         du = torch.empty_like(u, memory_format=torch.channels_last)
-        dk = torch.empty_like(u, memory_format=torch.channels_last)
+        dk = torch.empty_like(u, memory_format=torch.channels_last) if (k is not None and ctx.needs_input_grad[1]) else None
         _lib.check(lib.cotb200_tail_bwd_apply(dt, B, HW, C, dout.data_ptr(), u.data_ptr(), scale.data_ptr(), shift.data_ptr(),
                                               mean.data_ptr(), rstd.data_ptr(), a_c.data_ptr(), dpn.data_ptr(), _lib.ptr(c1),
-                                              _lib.ptr(c2), 1.0 / n, 1.0 / HW, du.data_ptr(), dk.data_ptr(), st), "tail_bwd_apply")
+                                              _lib.ptr(c2), 1.0 / n, 1.0 / HW, du.data_ptr(), _lib.ptr(dk), st), "tail_bwd_apply")
         dgamma = sums[1].to(ctx.bn_dtypes[0]) if ctx.needs_input_grad[2] else None
         dbeta = sums[0].to(ctx.bn_dtypes[1]) if ctx.needs_input_grad[3] else None
         ctx.graph = None
-        return (du, dk, dgamma, dbeta, None, None) + tuple(se_grads)
+        return (du, dk, dgamma, dbeta, None, None) + tuple(mlp_grads)
 
 
 class AggTapFn(Function):
@@ -476,13 +479,13 @@ def tap_chunk(wc, fold=1):
     return 8 if (wc // fold) % 8 == 0 else 0
 
 
-def _se_fp32(se, p):
-    """models/cotnet.py:69-77 on p [B, C] in fp32: conv1x1 -> BatchNorm2d -> ReLU -> conv1x1, using (and updating) the
-    module's parameters / buffers; differentiable w.r.t. p and the parameters.  The BatchNorm is ONE fused ATen kernel each
-    way (F.batch_norm on private copies of the running buffers -- autograd saves those copies, so updating the module's
-    own buffers afterwards cannot invalidate the graph); the whole MLP is ~10 launches forward, ~10 backward."""
+def _mlp_fp32(c0, b1, c3, p, act):
+    """conv1x1 -> BatchNorm2d -> act -> conv1x1 on p [B, C] in fp32 (models/cotnet.py:69-77 with ReLU;
+    models/layers/split_attn.py:51-55,76-80 with SiLU), using (and updating) the modules' parameters / buffers;
+    differentiable w.r.t. p and the parameters.  The BatchNorm is ONE fused ATen kernel each way (F.batch_norm on private
+    copies of the running buffers -- autograd saves those copies, so updating the module's own buffers afterwards cannot
+    invalidate the graph); the whole MLP is ~10 launches forward, ~10 backward."""
     F = torch.nn.functional
-    c0, b1, c3 = se[0], se[1], se[3]
     z = F.linear(p, c0.weight.float().flatten(1), None if c0.bias is None else c0.bias.float())
     w1, bb1 = b1.weight.float(), b1.bias.float()
     if b1.training or b1.running_mean is None:
@@ -501,8 +504,12 @@ def _se_fp32(se, p):
                 b1.running_var.copy_(rv)
     else:
         z = F.batch_norm(z, b1.running_mean.float(), b1.running_var.float(), w1, bb1, False, 0.0, b1.eps)
-    z = torch.relu(z)
+    z = act(z)
     return F.linear(z, c3.weight.float().flatten(1), None if c3.bias is None else c3.bias.float())
+
+
+def _se_fp32(se, p):
+    return _mlp_fp32(se[0], se[1], se[3], p, torch.relu)
 
 
 def group_norm9(l, gn: torch.nn.GroupNorm, gc=0, lbias=None):
@@ -511,7 +518,21 @@ def group_norm9(l, gn: torch.nn.GroupNorm, gc=0, lbias=None):
 
 def cot_tail(u, k, bn: torch.nn.BatchNorm2d, se: torch.nn.Module):
     params = [p for p in se.parameters()]
-    return CotTailFn.apply(u, k, bn.weight, bn.bias, bn, se, *params)
+    B, C = u.shape[0], u.shape[1]
+    return CotTailFn.apply(u, k, bn.weight, bn.bias, bn, lambda p: torch.softmax(_se_fp32(se, p).view(B, C, 2), dim=2), *params)
+
+
+def split_attn_tail(u, bn0: torch.nn.BatchNorm2d, fc1, bn1, fc2):
+    """SplitAttnConv2d (radix 1) after its convolution (models/layers/split_attn.py:68-86): bn0 -> SiLU -> global average
+    pool -> fc1 -> bn1 -> SiLU -> fc2 -> sigmoid -> rescale, on the CoT tail kernels with k absent: 3 HBM passes forward
+    (statistics, pool, gate) and 3 backward instead of ~12 eager ones."""
+    params = list(fc1.parameters()) + list(bn1.parameters()) + list(fc2.parameters())
+    F = torch.nn.functional
+
+    def gate(p):
+        g = torch.sigmoid(_mlp_fp32(fc1, bn1, fc2, p, F.silu))
+        return torch.stack([g, torch.zeros_like(g)], dim=2)
+    return CotTailFn.apply(u, None, bn0.weight, bn0.bias, bn0, gate, *params)
 
 
 # ====================================================================================================================

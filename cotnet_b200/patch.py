@@ -11,28 +11,19 @@ import sys
 import types
 
 import importlib
+import importlib.abc
 
 # NB: the package re-exports functions named like these sub-modules, so fetch the MODULES explicitly
 _agg = importlib.import_module(__package__ + ".aggregation_zeropad")
 _mix = importlib.import_module(__package__ + ".aggregation_zeropad_mix")
 
-# variants imported by lr_net / botnet / flops_counter but constructed by no registered model
-_UNUSED_VARIANTS = {
-    "cupy_layers.aggregation_zeropad_dilate": ("LocalConvolutionDilate", "aggregation_zeropad_dilate"),
-    "cupy_layers.aggregation_zeropad_mix_merge": ("LocalConvolutionMixMerge", "aggregation_zeropad_mix_merge"),
-    "cupy_layers.aggregation_refpad": ("aggregation_refpad",),
-}
+_VARIANTS = {name: importlib.import_module(__package__ + "." + name)
+             for name in ("aggregation_refpad", "aggregation_zeropad_dilate", "aggregation_zeropad_mix_merge")}
 
 
-def _unsupported(name):
-    def fn(*a, **k):
-        raise NotImplementedError("%s is outside the CoT hot path implemented by cotnet_b200 (SURVEY.md section 8f)" % name)
-    fn.__name__ = name
-    return fn
-
-
-def patch_reference(swap_layers=True, stub_unused_variants=True):
-    """Alias `cupy_layers.*` to this package.  Call BEFORE importing the reference's `models` package."""
+def patch_reference(swap_layers=True):
+    """Alias `cupy_layers.*` (all five operator modules) to this package.  Call BEFORE importing the reference's `models`
+    package; the layer classes are swapped by a post-import hook."""
     pkg = sys.modules.get("cupy_layers")
     if pkg is None or not isinstance(pkg, types.ModuleType):
         pkg = types.ModuleType("cupy_layers")
@@ -42,28 +33,54 @@ def patch_reference(swap_layers=True, stub_unused_variants=True):
     sys.modules["cupy_layers.aggregation_zeropad_mix"] = _mix
     pkg.aggregation_zeropad = _agg
     pkg.aggregation_zeropad_mix = _mix
-    if stub_unused_variants:
-        for modname, names in _UNUSED_VARIANTS.items():
-            if modname in sys.modules:
-                continue
-            m = types.ModuleType(modname)
-            for n in names:
-                if n[0].isupper():
-                    setattr(m, n, type(n, (object,), {"__init__": _unsupported(n)}))
-                else:
-                    setattr(m, n, _unsupported(n))
-            sys.modules[modname] = m
-            setattr(pkg, modname.split(".")[-1], m)
+    for name, mod in _VARIANTS.items():
+        sys.modules["cupy_layers." + name] = mod
+        setattr(pkg, name, mod)
     if swap_layers:
         swap_layer_classes()
 
 
-def swap_layer_classes():
-    """If the reference's model modules are (or get) imported, point their layer classes at the fused ones."""
+def _swap_table():
     from .cot_layer import CotLayer, CoXtLayer
-    for modname, attrs in (("models.cotnet", (("CotLayer", CotLayer), ("CoXtLayer", CoXtLayer))),
-                           ("models.cotnet_hybrid", (("CoTLayer", CotLayer),))):
+    return {"models.cotnet": (("CotLayer", CotLayer), ("CoXtLayer", CoXtLayer)),
+            "models.cotnet_hybrid": (("CoTLayer", CotLayer),)}
+
+
+class _SwapOnImport(importlib.abc.MetaPathFinder):
+    """Post-import hook: when `models.cotnet` / `models.cotnet_hybrid` are imported AFTER patch_reference(), their
+    layer classes are replaced as soon as the module body has run (the zoo's factory functions look the class names up
+    at call time, models/cotnet.py:199-204, models/cotnet_hybrid.py:138-153)."""
+
+    def find_spec(self, fullname, path, target=None):
+        if fullname not in ("models.cotnet", "models.cotnet_hybrid"):
+            return None
+        for finder in sys.meta_path:
+            if finder is self or not hasattr(finder, "find_spec"):
+                continue
+            spec = finder.find_spec(fullname, path, target)
+            if spec is not None and spec.loader is not None and hasattr(spec.loader, "exec_module"):
+                inner = spec.loader.exec_module
+
+                def exec_module(module, _inner=inner, _name=fullname):
+                    _inner(module)
+                    for a, cls in _swap_table()[_name]:
+                        setattr(module, a, cls)
+                spec.loader.exec_module = exec_module
+                return spec
+        return None
+
+
+_HOOK = _SwapOnImport()
+
+
+def swap_layer_classes():
+    """Point the reference's layer classes at the fused ones: immediately for model modules that are already imported,
+    and through a post-import hook for those imported later (so the documented order -- patch_reference() BEFORE
+    `import models` -- really swaps them)."""
+    for modname, attrs in _swap_table().items():
         mod = sys.modules.get(modname)
         if mod is not None:
             for a, cls in attrs:
                 setattr(mod, a, cls)
+    if _HOOK not in sys.meta_path:
+        sys.meta_path.insert(0, _HOOK)

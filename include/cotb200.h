@@ -99,6 +99,28 @@ int cotb200_agg_zeropad_mix_bwd(const cotb200_agg_desc* d, int k2h, int k2w, int
                                 const void* dy, const void* x, const void* w1, const void* w2,
                                 void* dx, void* dw1, void* dw2, void* stream);
 
+/* ---- the remaining LocalConv variants of cupy_layers; NCHW (reference contract), any dtype ----
+ * Reflect padding instead of zero padding (cupy_layers/aggregation_refpad.py:21-127; launches :153-160,:183-207).
+ * Padding must be smaller than the input (one reflection), like nn.ReflectionPad2d.  dX is gathered directly on the
+ * un-padded grid (the reference computes it on the padded grid and folds the borders with torch ops, :188-199). */
+int cotb200_agg_refpad_fwd(const cotb200_agg_desc* d, const void* x, const void* w, void* y, void* stream);
+int cotb200_agg_refpad_bwd(const cotb200_agg_desc* d, const void* dy, const void* x, const void* w,
+                           void* dx, void* dw, void* stream);
+/* Per-weight-channel dilation (cupy_layers/aggregation_zeropad_dilate.py:20-146): 3x3, stride 1, output size = input size,
+ * weight channel g uses dilation = padding = (int)dilation[g]; `dilation` is a device array of wc elements of the SAME
+ * dtype as x (the reference passes a tensor of the input dtype, :23,:33).  d->kh = d->kw = 3; d->{s,p,d}* are ignored. */
+int cotb200_agg_zeropad_dilate_fwd(const cotb200_agg_desc* d, const void* x, const void* w, const void* dilation,
+                                   void* y, void* stream);
+int cotb200_agg_zeropad_dilate_bwd(const cotb200_agg_desc* d, const void* dy, const void* x, const void* w,
+                                   const void* dilation, void* dx, void* dw, void* stream);
+/* The mix op with both weight sets packed in ONE tensor w [n, heads*wc*(k1^2+k2^2), ho, wo]
+ * (cupy_layers/aggregation_zeropad_mix_merge.py:20-179): first heads*wc*k1^2 channels = w1 [heads, wc, k1^2], then w2.
+ * dw has the same packed layout.  Runs on the packed tensor in place (no split / cat). */
+int cotb200_agg_zeropad_mix_merge_fwd(const cotb200_agg_desc* d, int k2h, int k2w, int p2h, int p2w,
+                                      const void* x, const void* w, void* y, void* stream);
+int cotb200_agg_zeropad_mix_merge_bwd(const cotb200_agg_desc* d, int k2h, int k2w, int p2h, int p2w,
+                                      const void* dy, const void* x, const void* w, void* dx, void* dw, void* stream);
+
 /* ---- fused normalisation / split-attention kernels on NHWC tensors [B, HW, C] (channel contiguous), fp32 math ----
  * They replace chains of eager launches of the reference block (models/cotnet.py:56 and :89-104).
  * dtype: COTB200_F32 / BF16 / F16.  All float* arguments are fp32 device arrays; sums are ACCUMULATED (+=) with
@@ -106,7 +128,9 @@ int cotb200_agg_zeropad_mix_bwd(const cotb200_agg_desc* d, int k2h, int k2w, int
 
 /* sum[c] += sum_rows x, sq[c] += sum_rows x^2 : BatchNorm batch statistics (nn.BatchNorm2d training mode, :65,:89) */
 int cotb200_col_stats(int dtype, int B, int HW, int C, const void* x, float* sum, float* sq, void* stream);
-/* psum[b,c] += sum_rows( silu(u*scale+shift) + k ) : bn + SiLU (:89-90) and the pooled descriptor of :92-98 */
+/* psum[b,c] += sum_rows( silu(u*scale+shift) + k ) : bn + SiLU (:89-90) and the pooled descriptor of :92-98.
+ * In all tail kernels k (and dk) may be NULL: then they compute the SplitAttnConv2d (radix 1) chain of the SE-CoTNetD
+ * blocks -- bn0 -> SiLU -> global pool ... x * sigmoid(attn) (models/layers/split_attn.py:68-86) -- with a[b,c,0] the gate. */
 int cotb200_tail_pool(int dtype, int B, int HW, int C, const void* u, const void* k, const float* scale,
                       const float* shift, float* psum, void* stream);
 /* out = a[b,c,0]*silu(u*scale+shift) + a[b,c,1]*k : the radix-2 recombination (:101-104); a is [B,C,2] fp32 */
@@ -217,6 +241,46 @@ int cotb200_gemm_bf16(int M, int N, int K1, const void* A1, long long lda1, cons
 int cotb200_conv3x3_bf16(int B, int H, int W, int C, const void* X, long long ldx, const void* Wp, int bn,
                          void* D, long long ldd, const float* scale, const float* shift, int relu,
                          float* col_sum, float* col_sqsum, void* stream);
+
+/* ---- train-step plumbing: what the reference does per parameter tensor -- DDP bucket copy,
+ * optim.SGD(nesterov=True) (optim/optim_factory.py:54-56), ModelEmaV2.update over the state_dict (utils/model_ema.py:45-53),
+ * one AMP weight cast per convolution -- as ONE pass over flat buffers; and the loader's uint8 normalisation
+ * (datasets/loader.py:86-90) as one kernel.  Tables (cotb200_seg*) live in DEVICE memory and are built by the caller. */
+typedef struct cotb200_seg {          /* one source tensor of a gather */
+  const void* ptr;                    /* device pointer of the tensor (dense, `numel` elements in memory order) */
+  long long offset;                   /* first element of its slot in the flat bucket */
+  long long numel;
+  int dtype;                          /* COTB200_F32 / BF16 / F16 */
+  int pad_;
+} cotb200_seg;
+typedef struct cotb200_seg2 {         /* one (destination, source) pair of a multi-tensor lerp */
+  void* dst;
+  const void* src;
+  long long numel;
+  int dtype;                          /* COTB200_F32, or 100 = int64 */
+  int pad_;
+} cotb200_seg2;
+/* Elements per gather block: the caller cuts every source into ceil(numel / chunk) blocks and passes the block table
+ * blocks[2*i] = segment index, blocks[2*i+1] = chunk index inside the segment. */
+int cotb200_gather_chunk(void);
+/* dst[seg.offset + i] = (dst type)(src_seg[i] * scale) for every segment: the gradients of a step (any mix of fp32 / bf16
+ * tensors) into ONE flat fp32 or bf16 bucket = the unit of the NCCL all-reduce (replaces DDP's bucket copies, train.py:113-115). */
+int cotb200_multi_gather(const cotb200_seg* segs_dev, const int* blocks_dev, int n_blocks, int dst_dtype, void* dst,
+                         float scale, void* stream);
+/* Over a flat range of n (multiple of 4) elements: torch.optim.SGD update with momentum (nesterov flag), weight decay,
+ * then EMA  E = decay*E + (1-decay)*P  (E NULL: none) and the bf16 copy Pb of the new weights (NULL: none).
+ * G is fp32 or bf16 (g_dtype).  hyper_dev = device fp32[5] {lr, momentum, weight_decay, ema_decay, grad_scale}: device
+ * resident so that a captured CUDA graph follows the learning-rate schedule. */
+int cotb200_sgd_ema_step(long long n, float* P, float* M, int g_dtype, const void* G, float* E, void* Pb,
+                         const float* hyper_dev, int nesterov, void* stream);
+/* dst = decay*dst + (1-decay)*src per segment (fp32; int64 with the reference's float round trip): ModelEmaV2 over the
+ * BUFFERS of the state_dict (BatchNorm running statistics / counters), one launch. decay = hyper_dev[3]. */
+int cotb200_multi_lerp(const cotb200_seg2* segs_dev, int n_segs, const float* hyper_dev, void* stream);
+/* y[n,h,w,c] = (x_u8[n,c,h,w] - mean[c]) / std[c]: uint8 NCHW batch -> normalised channels_last tensor of `dtype`
+ * (PrefetchLoader, datasets/loader.py:66-67,86-90, + the channels_last / bf16 conversion of the AMP forward) in one
+ * pass.  C == 3 with H*W % 4 == 0 takes mean_host/std_host (host arrays of 3); anything else needs the device arrays. */
+int cotb200_u8_to_nhwc(int dtype, int N, int C, int H, int W, const void* x_u8, void* y, const float* mean_host,
+                       const float* std_host, const float* mean_dev, const float* std_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,13 @@ AGG_SHAPES = [
 AGG_DTYPES = {"cfg1": ("float", "double"), "selftest_k5": ("double",), "selftest_k1": ("double",), "ragged": ("float", "double")}
 # mix: (tag, N, C, H, W, heads, wc) with k1=3/pad 1, k2=5/pad 2 (aggregation_zeropad_mix.py:344-349)
 MIX_SHAPES = [("mix_selftest", 2, 8, 6, 6, 1, 4), ("mix_s1_b32", 32, 64, 56, 56, 1, 8)]
+# the other cupy_layers variants: (tag, N, C, H, W, heads, wc[, k, pad])
+REFPAD_SHAPES = [("refpad_selftest", 2, 8, 9, 9, 2, 4, 5, 2),     # aggregation_refpad.py:225-233
+                 ("refpad_k3", 3, 24, 14, 10, 1, 3, 3, 1), ("refpad_s2_b8", 8, 128, 28, 28, 1, 16, 3, 1)]
+DILATE_SHAPES = [("dilate_selftest", 2, 8, 7, 7, 2, 4),           # aggregation_zeropad_dilate.py:258-264
+                 ("dilate_s2_b8", 8, 128, 28, 28, 1, 16)]
+MERGE_SHAPES = [("merge_selftest", 2, 8, 6, 6, 2, 4),             # aggregation_zeropad_mix_merge.py:332-339
+                ("merge_s1_b8", 8, 64, 56, 56, 1, 8)]
 
 
 class _NvccModule:
@@ -108,6 +115,47 @@ def main():
                  N * C * H * W, lit, meta)                                                     # :273-274
             emit(tag, "aggregation_zeropad_mix_weight_backward_kernel", ref_mix._aggregation_zeropad_mix_weight_backward_kernel,
                  2 * N * heads * wc * H * W, lit, meta, grid_n=N * heads * wc * H * W)         # :283-284 (grid from n, loop to 2n)
+    import cupy_layers.aggregation_refpad as ref_refpad
+    import cupy_layers.aggregation_zeropad_dilate as ref_dilate
+    import cupy_layers.aggregation_zeropad_mix_merge as ref_merge
+    for tag, N, C, H, W, heads, wc, k, pad in REFPAD_SHAPES:
+        Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+        for dt in (("double", "float") if "selftest" in tag or tag == "refpad_k3" else ("float",)):
+            lit = dict(Dtype=dt, num=N, input_channels=C, weight_heads=heads, weight_channels=wc, bottom_height=H,
+                       bottom_width=W, top_height=Ho, top_width=Wo, kernel_h=k, kernel_w=k, stride_h=1, stride_w=1,
+                       dilation_h=1, dilation_w=1, pad_h=pad, pad_w=pad)
+            meta = dict(op="refpad", N=N, C=C, H=H, W=W, heads=heads, wc=wc, k=k, pad=pad, Ho=Ho, Wo=Wo)
+            emit(tag, "aggregation_refpad_forward_kernel", ref_refpad._aggregation_refpad_forward_kernel,
+                 N * heads * C * Ho * Wo, lit, meta)                                           # refpad :141-142
+            emit(tag, "aggregation_refpad_input_backward_kernel", ref_refpad._aggregation_refpad_input_backward_kernel,
+                 N * C * (H + 2 * pad) * (W + 2 * pad), lit, meta)                             # :185-187 (padded grid)
+            emit(tag, "aggregation_refpad_weight_backward_kernel", ref_refpad._aggregation_refpad_weight_backward_kernel,
+                 N * heads * wc * Ho * Wo, lit, meta)                                          # :203-205
+    for tag, N, C, H, W, heads, wc in DILATE_SHAPES:
+        for dt in (("double", "float") if "selftest" in tag else ("float",)):
+            lit = dict(Dtype=dt, num=N, input_channels=C, weight_heads=heads, weight_channels=wc, bottom_height=H,
+                       bottom_width=W, top_height=H, top_width=W, kernel_h=3, kernel_w=3, stride_h=1, stride_w=1)
+            meta = dict(op="dilate", N=N, C=C, H=H, W=W, heads=heads, wc=wc)
+            emit(tag, "aggregation_zeropad_dilate_forward_kernel", ref_dilate._aggregation_zeropad_dilate_forward_kernel,
+                 N * heads * C * H * W, lit, meta)                                             # dilate :159-160
+            emit(tag, "aggregation_zeropad_dilate_input_backward_kernel", ref_dilate._aggregation_zeropad_dilate_input_backward_kernel,
+                 N * C * H * W, lit, meta)                                                     # :203-205
+            emit(tag, "aggregation_zeropad_dilate_weight_backward_kernel", ref_dilate._aggregation_zeropad_dilate_weight_backward_kernel,
+                 N * heads * wc * H * W, lit, meta)                                            # :212-214
+    for tag, N, C, H, W, heads, wc in MERGE_SHAPES:
+        for dt in (("double", "float") if "selftest" in tag else ("float",)):
+            lit = dict(Dtype=dt, num=N, input_channels=C, weight_heads=heads, weight_channels=wc, bottom_height=H,
+                       bottom_width=W, top_height=H, top_width=W, kernel1_h=3, kernel1_w=3, kernel2_h=5, kernel2_w=5,
+                       stride_h=1, stride_w=1, dilation_h=1, dilation_w=1, pad1_h=1, pad1_w=1, pad2_h=2, pad2_w=2)
+            meta = dict(op="merge", N=N, C=C, H=H, W=W, heads=heads, wc=wc)
+            emit(tag, "aggregation_zeropad_mix_merge_forward_kernel", ref_merge._aggregation_zeropad_mix_merge_forward_kernel,
+                 N * 2 * heads * C * H * W, lit, meta)                                         # merge :196-197
+            emit(tag, "aggregation_zeropad_mix_merge_input_backward_kernel", ref_merge._aggregation_zeropad_mix_merge_input_backward_kernel,
+                 N * C * H * W, lit, meta)                                                     # :253-255
+            emit(tag, "aggregation_zeropad_mix_merge_weight_backward_kernel", ref_merge._aggregation_zeropad_mix_merge_weight_backward_kernel,
+                 2 * N * heads * wc * H * W,
+                 lit, meta)      # the kernel's own index space (2 kernels x N x heads x wc x Ho x Wo).  The reference's host code
+            # derives nthreads from weight.shape[3] of the 4-D packed weight (= Wo, :262), which over- or under-covers it.
     json.dump(manifest, open(os.path.join(OUT, "manifest.json"), "w"), indent=1)
     print("oracle/_ref: %d cubins" % len(manifest["kernels"]))
     return 0

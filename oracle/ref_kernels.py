@@ -90,6 +90,76 @@ class RefKernels:
         self.launch(self.entry("aggregation_zeropad_mix_weight_backward_kernel", tag, dt), dy, x, dw1, dw2)
         return dx, dw1, dw2
 
+    # ---- AggregationRefpad (aggregation_refpad.py:129-208): dX is computed on the padded grid, then folded (:188-199)
+    def refpad_forward(self, tag, x, w):
+        e = self.entry("aggregation_refpad_forward_kernel", tag, "float" if x.dtype == torch.float32 else "double")
+        y = torch.empty(e["N"], e["heads"] * e["C"], e["Ho"], e["Wo"], dtype=x.dtype, device=x.device)
+        self.launch(e, x, w, y)
+        return y
+
+    def refpad_backward(self, tag, dy, x, w):
+        dt = "float" if x.dtype == torch.float32 else "double"
+        e = self.entry("aggregation_refpad_input_backward_kernel", tag, dt)
+        p, H, W = e["pad"], e["H"], e["W"]
+        gi = torch.empty(e["N"], e["C"], H + 2 * p, W + 2 * p, dtype=x.dtype, device=x.device)
+        self.launch(e, dy, w, gi)
+        # the reference's host-side border fold, aggregation_refpad.py:195-199
+        gi[:, :, p + 1:2 * p + 1, :] += torch.flip(gi[:, :, :p, :], dims=[2])
+        gi[:, :, H - 1:H + p - 1, :] += torch.flip(gi[:, :, H + p:, :], dims=[2])
+        gi[:, :, :, p + 1:2 * p + 1] += torch.flip(gi[:, :, :, :p], dims=[3])
+        gi[:, :, :, W - 1:W + p - 1] += torch.flip(gi[:, :, :, W + p:], dims=[3])
+        dx = gi[:, :, p:p + H, p:p + W].contiguous()
+        dw = torch.empty_like(w)
+        self.launch(self.entry("aggregation_refpad_weight_backward_kernel", tag, dt), dy, x, dw)
+        return dx, dw
+
+    # ---- AggregationZeropadDilate (aggregation_zeropad_dilate.py:148-218)
+    def dilate_forward(self, tag, x, w, dil):
+        e = self.entry("aggregation_zeropad_dilate_forward_kernel", tag, "float" if x.dtype == torch.float32 else "double")
+        y = torch.empty(e["N"], e["heads"] * e["C"], e["H"], e["W"], dtype=x.dtype, device=x.device)
+        self.launch(e, x, w, dil, y)
+        return y
+
+    def dilate_backward(self, tag, dy, x, w, dil):
+        dt = "float" if x.dtype == torch.float32 else "double"
+        dx, dw = torch.empty_like(x), torch.empty_like(w)
+        self.launch(self.entry("aggregation_zeropad_dilate_input_backward_kernel", tag, dt), dy, w, dil, dx)
+        self.launch(self.entry("aggregation_zeropad_dilate_weight_backward_kernel", tag, dt), dy, x, dil, dw)
+        return dx, dw
+
+    # ---- AggregationZeropadMixMerge (aggregation_zeropad_mix_merge.py:180-274)
+    def merge_forward(self, tag, x, w):
+        e = self.entry("aggregation_zeropad_mix_merge_forward_kernel", tag, "float" if x.dtype == torch.float32 else "double")
+        y = torch.empty(e["N"], 2 * e["heads"] * e["C"], e["H"], e["W"], dtype=x.dtype, device=x.device)
+        self.launch(e, x, w, y)
+        return y
+
+    def merge_backward(self, tag, dy, x, w):
+        dt = "float" if x.dtype == torch.float32 else "double"
+        dx, dw = torch.empty_like(x), torch.empty_like(w)
+        self.launch(self.entry("aggregation_zeropad_mix_merge_input_backward_kernel", tag, dt), dy, w, dx)
+        self.launch(self.entry("aggregation_zeropad_mix_merge_weight_backward_kernel", tag, dt), dy, x, dw)
+        return dx, dw
+
+    def make_variant_inputs(self, tag, dtype, op, seed=0):
+        e = next(k for k in self.manifest["kernels"] if k["tag"] == tag and k["op"] == op)
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        td = _TORCH[dtype]
+        N, C, H, W, heads, wc = e["N"], e["C"], e["H"], e["W"], e["heads"], e["wc"]
+        x = torch.randn(N, C, H, W, generator=g, device="cuda", dtype=td)
+        if op == "refpad":
+            w = torch.randn(N, heads, wc, e["k"] ** 2, e["Ho"], e["Wo"], generator=g, device="cuda", dtype=td)
+            dy = torch.randn(N, heads * C, e["Ho"], e["Wo"], generator=g, device="cuda", dtype=td)
+            return e, x, w, dy
+        if op == "dilate":
+            w = torch.randn(N, heads, wc, 9, H, W, generator=g, device="cuda", dtype=td)
+            dil = torch.tensor([(1, 1, 2, 4, 3, 2, 1, 5)[i % 8] for i in range(wc)], device="cuda", dtype=td)
+            dy = torch.randn(N, heads * C, H, W, generator=g, device="cuda", dtype=td)
+            return e, x, w, dil, dy
+        w = torch.randn(N, heads * wc * 34, H, W, generator=g, device="cuda", dtype=td)
+        dy = torch.randn(N, 2 * heads * C, H, W, generator=g, device="cuda", dtype=td)
+        return e, x, w, dy
+
     def make_inputs(self, tag, dtype, op="agg", seed=0):
         e = next(k for k in self.manifest["kernels"] if k["tag"] == tag and k["op"] == op)
         g = torch.Generator(device="cuda").manual_seed(seed)

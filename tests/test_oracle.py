@@ -137,3 +137,56 @@ def test_oracle_model_matches_reference_golden_logits(golden_dir, name, fixture)
         y = o(torch.from_numpy(g["x"]))
     err = (y - torch.from_numpy(g["logits"])).abs().max().item()
     assert err <= 2e-5, err
+
+
+# ---------------------------------------------------------------- the other cupy_layers variants
+def test_refpad_loops_match_unfold_identity():
+    """aggregation_refpad.py:223-239: kernel index math (loops) == Unfold(ReflectionPad2d(x)) at the self-test shape and a
+    strided / dilated one."""
+    for k, s, p, d, H, W in [(5, 1, 2, 1, 9, 9), (3, 2, 1, 1, 9, 8), (3, 1, 2, 2, 8, 7)]:
+        gen = torch.Generator().manual_seed(k + s)
+        n, c, wc, heads = 2, 8, 4, 2
+        Ho, Wo = agg_ref.out_size(H, W, k, s, p, d)
+        x = torch.randn(n, c, H, W, generator=gen, dtype=torch.float64)
+        w = torch.randn(n, heads, wc, k * k, Ho, Wo, generator=gen, dtype=torch.float64)
+        a = agg_ref.agg_refpad_unfold(x, w, k, s, p, d).numpy()
+        b = agg_ref.agg_refpad_fwd_loops(x.numpy(), w.numpy(), k, s, p, d)
+        assert np.abs(a - b).max() < TOL
+
+
+def test_dilate_loops_match_unfold_identity():
+    """aggregation_zeropad_dilate.py:258-296 (dilation_arr = [1, 1, 2, 4])."""
+    gen = torch.Generator().manual_seed(3)
+    n, c, wc, heads, H, W = 2, 8, 4, 2, 7, 7
+    x = torch.randn(n, c, H, W, generator=gen, dtype=torch.float64)
+    w = torch.randn(n, heads, wc, 9, H, W, generator=gen, dtype=torch.float64)
+    dil = [1, 1, 2, 4]
+    a = agg_ref.agg_dilate_unfold(x, w, dil).numpy()
+    b = agg_ref.agg_dilate_fwd_loops(x.numpy(), w.numpy(), dil)
+    assert np.abs(a - b).max() < TOL
+    # the reference's own formulation of the identity (:266-295): three dilation groups, channel-interleaved
+    split = [2, 1, 1]
+    w1, w2, w3 = torch.split(w, split, dim=2)
+    xs = torch.split(x.view(n, c // 4, 4, H, W), split, dim=2)
+    ys = []
+    for xi, wi, dd, sp in zip(xs, (w1, w2, w3), (1, 2, 4), split):
+        xi = xi.reshape(n, -1, H, W)
+        u = torch.nn.Unfold(kernel_size=3, dilation=dd, padding=dd, stride=1)(xi).view(n, xi.shape[1] // sp, sp, 9, H, W)
+        ys.append((wi.unsqueeze(2) * u.unsqueeze(1)).sum(-3).view(n, heads * xi.shape[1], H, W).view(n, -1, sp, H, W))
+    y2 = torch.cat(ys, dim=2).view(n, -1, H, W)
+    assert (y2 - torch.from_numpy(b)).abs().max() < TOL
+
+
+def test_mix_merge_matches_mix_on_split_weights():
+    """aggregation_zeropad_mix_merge.py:332-351: the packed weight is cat([w1.view(n,-1,h,w), w2.view(n,-1,h,w)], 1)."""
+    gen = torch.Generator().manual_seed(4)
+    n, c, wc, heads, H, W = 2, 8, 4, 2, 6, 6
+    x = torch.randn(n, c, H, W, generator=gen, dtype=torch.float64)
+    w1 = torch.randn(n, heads, wc, 9, H, W, generator=gen, dtype=torch.float64)
+    w2 = torch.randn(n, heads, wc, 25, H, W, generator=gen, dtype=torch.float64)
+    w = torch.cat([w1.view(n, -1, H, W), w2.view(n, -1, H, W)], dim=1)
+    a = agg_ref.agg_zeropad_mix_merge_unfold(x, w, heads, wc, 3, 5, 1, 1, 2, 1)
+    b = agg_ref.agg_zeropad_mix_unfold(x, w1, w2, 3, 5, 1, 1, 2, 1)
+    assert (a - b).abs().max() < TOL
+    c2 = agg_ref.agg_zeropad_mix_merge_fwd_loops(x.numpy(), w.numpy(), heads, wc, 3, 5, 1, 1, 2, 1)
+    assert np.abs(c2 - b.numpy()).max() < TOL

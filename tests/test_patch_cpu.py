@@ -21,8 +21,8 @@ class CfgNode(dict):
 yc.CfgNode = CfgNode; yacs.config = yc; sys.modules["yacs"] = yacs; sys.modules["yacs.config"] = yc
 import cotnet_b200.patch as p
 p.patch_reference()
-import models.cotnet as mc
-p.swap_layer_classes()
+import models.cotnet as mc            # imported AFTER patch_reference(): the post-import hook swaps the layer classes
+import models.cotnet_hybrid as mh
 from cotnet_b200.cot_layer import CotLayer
 from cotnet_b200.aggregation_zeropad import LocalConvolution
 import cupy_layers.aggregation_zeropad as ca
@@ -32,6 +32,12 @@ layers = [x for x in m.modules() if isinstance(x, CotLayer)]
 assert len(layers) == 16, len(layers)
 assert isinstance(layers[0].local_conv, LocalConvolution)
 assert sum(q.numel() for q in m.parameters()) == 22222416
+assert mc.CotLayer is CotLayer and mh.CoTLayer is CotLayer
+# the rest of the zoo and the flops counter import all five cupy_layers operator modules: every one resolves to a mirror
+import models.lr_net, models.san_lowrank, models.botnet, utils.flops_counter
+import cupy_layers.aggregation_zeropad_dilate as cd, cupy_layers.aggregation_zeropad_mix_merge as cm, cupy_layers.aggregation_refpad as cr
+assert cd.__name__.startswith("cotnet_b200") and cm.__name__.startswith("cotnet_b200") and cr.__name__.startswith("cotnet_b200")
+assert "cupy" not in sys.modules
 print("OK")
 '''
 
