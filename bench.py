@@ -58,11 +58,17 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fwd-only", action="store_true", help="diagnostic: time the forward pass only (not the headline)")
-    ap.add_argument("--dp", default="flat", choices=["flat", "ddp"],
-                    help="N>1: 'flat' = replicas + one flat-bucket NCCL all-reduce per step (graph-replayable); "
-                         "'ddp' = torch DistributedDataParallel (eager)")
-    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the whole fwd+bwd+SGD step from CUDA graphs (auto: on unless --dp ddp)")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"], help="replay the whole step from a CUDA graph")
+    ap.add_argument("--weights", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16: >=2-D weights kept as a bf16 copy written by the optimizer kernel (fp32 master in the flat state); "
+                         "fp32: parameters are the fp32 masters and autocast casts them every step")
+    ap.add_argument("--bucket", default="auto", choices=["auto", "bf16", "fp32"], help="dtype of the all-reduced gradient bucket")
+    ap.add_argument("--chunks", type=int, default=3, help="N>1: ranges of the gradient bucket all-reduced separately (overlap)")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce after backward instead of chunked overlap")
+    ap.add_argument("--no-nccl-capture", action="store_true", help="N>1: keep NCCL out of the CUDA graph (two graphs + eager collectives)")
+    ap.add_argument("--no-ema", action="store_true", help="skip the EMA of the weights (the reference's configs enable it)")
+    ap.add_argument("--no-cot-leg", action="store_true", help="skip the CoT-layers-only forward measurement")
+    ap.add_argument("--exposed-comm", action="store_true", default=True)
     return ap.parse_args()
 
 
@@ -249,8 +255,69 @@ def main_reference(a):
 
 
 # ----------------------------------------------------------------------------------------------- our arm
+def build_model(name, **kw):
+    from cotnet_b200 import backbone, backbone_hybrid
+    ctor = backbone.MODELS.get(name) or backbone_hybrid.MODELS.get(name)
+    if ctor is None:
+        raise SystemExit("bench.py: unknown model %r (have: %s)" % (name, sorted(list(backbone.MODELS) + list(backbone_hybrid.MODELS))))
+    return ctor(**kw)
+
+
+def peaks_all():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def cot_forward_leg(model, x, steps):
+    """Eval-mode bf16 forward with CUDA events around every CoT layer: the north-star number "CoT layers forward as a
+    fraction of the CoT-block roofline" (SURVEY 8d), measured inside the real model (inputs = real activations, every
+    layer's working set >> L2 at bs256)."""
+    from cotnet_b200.cot_layer import CotLayer, CoXtLayer
+    layers = [(n, m) for n, m in model.named_modules() if isinstance(m, (CotLayer, CoXtLayer))]
+    ev = {n: [] for n, _ in layers}
+    hooks = []
+    for n, m in layers:
+        def pre(mod, inp, n=n):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev[n].append([e, None])
+
+        def post(mod, inp, out, n=n):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev[n][-1][1] = e
+        hooks.append(m.register_forward_pre_hook(pre))
+        hooks.append(m.register_forward_hook(post))
+    was = model.training
+    model.eval()
+    xb = x.to(torch.bfloat16)
+    try:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            for _ in range(3):
+                model(xb)
+            for v in ev.values():
+                v.clear()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                model(xb)
+            e1.record()
+            torch.cuda.synchronize()
+    finally:
+        for h in hooks:
+            h.remove()
+        model.train(was)
+    per = {n: sum(a.elapsed_time(b) for a, b in v) / max(1, len(v)) for n, v in ev.items()}
+    return per, e0.elapsed_time(e1) / steps
+
+
 def main_ours(a):
-    from cotnet_b200 import _lib, backbone, fused
+    from cotnet_b200 import _lib, roofline, trainer
     from cotnet_b200 import dist as cdist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -270,177 +337,158 @@ def main_ours(a):
     torch.manual_seed(1234 + rank)
 
     B, R = a.batch, a.res
-    model = backbone.MODELS[a.model](zero_init_last_bn=False).to(dev).to(memory_format=torch.channels_last).train()
-    params = [p for p in model.parameters()]
-    try:
-        opt = torch.optim.SGD(params, lr=0.05, momentum=0.9, nesterov=True, weight_decay=1e-4, fused=True)
-    except Exception:
-        opt = torch.optim.SGD(params, lr=0.05, momentum=0.9, nesterov=True, weight_decay=1e-4, foreach=True)
-    net = model
-    flat = None
-    if world > 1 and a.dp == "flat":
-        # replicas + ONE flat gradient bucket all-reduced (mean) over NCCL/NVLink per step; no autograd hooks, so the
-        # step still replays from CUDA graphs (cotnet_b200/dist.py FlatGrads)
+    model = build_model(a.model, zero_init_last_bn=False).to(dev).to(memory_format=torch.channels_last).train()
+    if world > 1:
         cdist.broadcast_module_(model, 0)
-        flat = cdist.FlatGrads(params)
-    elif world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
-                                                        gradient_as_bucket_view=True)
+    # One data-parallel training step = cotnet_b200.trainer.TrainStep (reference: train.py:255-277 + DDP): fp32 master
+    # weights / momentum / EMA in flat buffers, bf16 weight copy for the convolutions, gradients gathered into one bucket,
+    # NCCL all-reduce overlapped with backward, ONE optimizer(+EMA) kernel; the whole step replays from one CUDA graph.
+    ts = trainer.TrainStep(model, lr=0.05, momentum=0.9, weight_decay=1e-4, nesterov=True,
+                           ema_decay=None if a.no_ema else 0.9999, weights=a.weights,
+                           bucket_dtype={"bf16": torch.bfloat16, "fp32": torch.float32, "auto": None}[a.bucket],
+                           comm_chunks=a.chunks, overlap=not a.no_overlap)
     gen = torch.Generator().manual_seed(1234 + rank)
     host_u8 = torch.randint(0, 256, (B, 3, R, R), generator=gen, dtype=torch.uint8).pin_memory()
     host_lab = torch.randint(0, 1000, (B,), generator=gen, dtype=torch.int64).pin_memory()
-    mean = torch.tensor(IMAGENET_MEAN, device=dev).view(1, 3, 1, 1)
-    std = torch.tensor(IMAGENET_STD, device=dev).view(1, 3, 1, 1)
 
     def to_device_batch():
+        """pinned uint8 NCHW host batch -> device -> ONE kernel: (x - mean)/std, bf16, channels_last (datasets/loader.py:86-90)"""
         u8 = host_u8.to(dev, non_blocking=True)
         lab = host_lab.to(dev, non_blocking=True)
-        x = ((u8.float() - mean) / std).contiguous(memory_format=torch.channels_last)
-        return x, lab
-
-    def fwd_bwd(x, lab):
-        fused.step_begin(dev)             # accumulator scratch of the fused kernels: one memset per step
-        if flat is not None:
-            flat.zero_()
-        else:
-            opt.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            out = net(x)
-            loss = torch.nn.functional.cross_entropy(out.float(), lab)
-        if not a.fwd_only:
-            loss.backward()
-        return loss
-
-    def train_step(x, lab):
-        loss = fwd_bwd(x, lab)
-        if not a.fwd_only:
-            if flat is not None:
-                flat.all_reduce_mean_()
-            opt.step()
-        return loss
+        return trainer.normalize_u8(u8, IMAGENET_MEAN, IMAGENET_STD, torch.bfloat16), lab
 
     x_res, lab_res = to_device_batch()           # resident inputs for `value`
     torch.cuda.synchronize()
 
-    # ---- whole-step CUDA graph: the step is ~4000 small launches, replaying them from one graph removes the host
-    #      launch overhead (Blackwell guide: "capture launch-bound inner loops in CUDA graphs").  Same kernels, same math.
-    graph_info = {"cuda_graph": False}
-    use_graph = (a.graph == "on") or (a.graph == "auto" and (world == 1 or flat is not None) and not a.fwd_only)
-    graphed = None
-    if use_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):                       # warm-up: cuDNN autotune, optimizer state, one-time attributes
-                    train_step(x_res, lab_res)
-            torch.cuda.current_stream().wait_stream(side)
+    if a.fwd_only:
+        # diagnostic leg (not the headline): eval-mode bf16 forward of the whole model, no autograd
+        model.eval()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            for _ in range(max(a.warmup, 3)):
+                model(x_res)
             torch.cuda.synchronize()
-            g_x, g_lab = x_res.clone(), lab_res.clone()
-            cg = torch.cuda.CUDAGraph()
-            cg_opt = None
-            if flat is None:
-                opt.zero_grad(set_to_none=True)
-            lc0 = _lib.launch_count()
-            with torch.cuda.graph(cg):
-                g_loss = fwd_bwd(g_x, g_lab)
-                if flat is None:
-                    opt.step()
-            captured = _lib.launch_count() - lc0
-            if flat is not None:             # the all-reduce runs eagerly between the two graphs
-                if not flat.attached():
-                    raise RuntimeError("gradient views were detached from the flat bucket")
-                cg_opt = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(cg_opt):
-                    opt.step()
-            graphed = (cg, g_x, g_lab, g_loss, cg_opt)
-            graph_info = {"cuda_graph": True, "libcotb200_kernels_per_replay": captured}
-            if flat is not None:
-                graph_info["data_parallel"] = "fwd+bwd graph -> NCCL all-reduce(mean) of one %.0f MB flat bucket -> optimizer graph" % (
-                    flat.flat.numel() * 4 / 1e6)
-        except Exception as e:      # noqa: BLE001 -- never lose the bench line to a capture problem
-            graph_info = {"cuda_graph": False, "cuda_graph_error": repr(e)[:300]}
-            graphed = None
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.steps):
+                model(x_res)
+            e1.record()
             torch.cuda.synchronize()
+        ms = cdist.max_over_ranks(e0.elapsed_time(e1), dev)
+        graph_info = {"cuda_graph": False}
+        launches, clk, e2e = 0, None, None
+        model.train()
+    else:
+        graph_info = {"cuda_graph": False}
+        if a.graph != "off":
+            try:
+                graph_info = ts.capture(x_res, lab_res, warmup=3, capture_nccl=not a.no_nccl_capture)
+            except Exception as e:      # noqa: BLE001 -- never lose the bench line to a capture problem
+                graph_info = {"cuda_graph": False, "cuda_graph_error": repr(e)[:300]}
+                torch.cuda.synchronize()
+        if ts._graph is not None:
+            x_res, lab_res = ts.static_inputs        # the graph's static input buffers ARE the resident inputs
 
-    def run_step(x, lab):
-        """one training step on device-resident (x, lab); returns the loss tensor"""
-        if graphed is None:
-            return train_step(x, lab)
-        cg, g_x, g_lab, g_loss, cg_opt = graphed
-        if x is not g_x:
-            g_x.copy_(x, non_blocking=True)
-            g_lab.copy_(lab, non_blocking=True)
-        cg.replay()
-        if cg_opt is not None:
-            flat.all_reduce_mean_()
-            cg_opt.replay()
-        return g_loss
+        def timed(fn, steps):
+            cdist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            cdist.barrier()
+            return cdist.max_over_ranks(e0.elapsed_time(e1), dev)
 
-    def timed(fn, steps):
-        cdist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        cdist.barrier()
-        return cdist.max_over_ranks(e0.elapsed_time(e1), dev)
+        # ---- value: resident inputs
+        for _ in range(max(a.warmup, 3)):
+            ts.step(x_res, lab_res)
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        l0 = _lib.launch_count()
+        ms = timed(lambda: ts.step(x_res, lab_res), a.steps)
+        launches = _lib.launch_count() - l0
+        if ts._graph is not None:      # replayed launches do not pass through the host-side counter: kernels captured x replays
+            launches = graph_info.get("libcotb200_kernels_per_replay", 0) * a.steps
+        clk = clocks.stop() if rank == 0 else None
 
-    # ---- value: resident inputs
-    if graphed is not None:
-        x_res, lab_res = graphed[1], graphed[2]          # the graph's static input buffers ARE the resident inputs
-    for _ in range(max(a.warmup, 3)):
-        run_step(x_res, lab_res)
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    l0 = _lib.launch_count()
-    ms = timed(lambda: run_step(x_res, lab_res), a.steps)
-    launches = _lib.launch_count() - l0
-    if graphed is not None:      # replayed launches do not pass through the host-side counter: kernels captured x replays
-        launches = graph_info["libcotb200_kernels_per_replay"] * a.steps
-    clk = clocks.stop() if rank == 0 else None
+        # ---- e2e: host buffers, H2D + normalise + step + loss read back every step
+        e2e = None
+        if not a.no_e2e:
+            def e2e_step():
+                x, lab = to_device_batch()
+                return float(ts.step(x, lab).item())
+            for _ in range(2):
+                e2e_step()
+            ms_e = timed(e2e_step, a.steps)
+            e2e = {"value": world * B * a.steps / (ms_e / 1e3), "unit": "images/s",
+                   "h2d_bytes_per_step": host_u8.numel() + host_lab.numel() * 8, "d2h_bytes_per_step": 4,
+                   "ms_per_step": ms_e / a.steps}
     value = world * B * a.steps / (ms / 1e3)
 
-    # ---- e2e: host buffers, H2D + step + loss read back every step
-    e2e = None
-    if not a.no_e2e:
-        def e2e_step():
-            x, lab = to_device_batch()
-            return float(run_step(x, lab).item())
-        for _ in range(2):
-            e2e_step()
-        ms_e = timed(e2e_step, a.steps)
-        e2e = {"value": world * B * a.steps / (ms_e / 1e3), "unit": "images/s",
-               "h2d_bytes_per_step": host_u8.numel() + host_lab.numel() * 8, "d2h_bytes_per_step": 4,
-               "ms_per_step": ms_e / a.steps}
-
-    # ---- roofline: per-kernel CUDA-event times of OUR kernels over 2 more steps of the same workload
+    # ---- roofline 1: per-kernel CUDA-event times of OUR kernels over 2 eager steps of the same workload
+    hbm, tf_burst, tf_sust, src = peaks_all()
     roof = None
-    _lib.prof_enable(True)            # eager (not graph-replayed) steps: the per-launch events are recorded by the library
-    for _ in range(2):
-        train_step(x_res, lab_res)
-    torch.cuda.synchronize()
-    prof = _lib.prof_report()
-    _lib.prof_enable(False)
-    if prof and rank == 0:
-        # dominant kernel = most device time among OUR kernels; algorithmic bytes are recorded by the library per launch
-        # (DESIGN.md section 4 formulas evaluated on the actual launch dimensions)
-        kname, (cnt, tot_ms, tot_bytes) = max(prof.items(), key=lambda kv: kv[1][1])
-        peak, src = measured_peaks()
-        if tot_bytes > 0 and tot_ms > 0:
-            ach = tot_bytes / (tot_ms / 1e3) / 1e9
-            roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "peak_source": src, "traffic": ncu_traffic(kname), "launches_per_step": cnt // 2,
-                    "avg_launch_us": 1e3 * tot_ms / cnt, "algorithmic_bytes_per_launch": tot_bytes / cnt,
-                    "kernel_share_of_step": (tot_ms / 2) / (ms / a.steps),
-                    "our_kernels_share_of_step": sum(v[1] for v in prof.values()) / 2 / (ms / a.steps),
-                    "all_kernels": {k: {"ms_per_step": round(v[1] / 2, 4), "launches_per_step": v[0] // 2,
-                                        "GBps": round(v[2] / (v[1] / 1e3) / 1e9, 1) if v[1] > 0 else None}
-                                    for k, v in sorted(prof.items())}}
+    extra = {}
+    if not a.fwd_only:
+        _lib.prof_enable(True)            # eager (not graph-replayed) steps: the per-launch events are recorded by the library
+        for _ in range(2):
+            ts.step_eager(x_res, lab_res)
+        torch.cuda.synchronize()
+        prof = _lib.prof_report()
+        _lib.prof_enable(False)
+        if prof and rank == 0:
+            cand = {k: v for k, v in prof.items() if v[2] > 0}
+            kname, (cnt, tot_ms, tot_bytes) = max(cand.items(), key=lambda kv: kv[1][1])
+            if tot_bytes > 0 and tot_ms > 0:
+                ach = tot_bytes / (tot_ms / 1e3) / 1e9
+                ours_ms = sum(v[1] for v in prof.values()) / 2
+                w_frac = sum(v[2] for v in cand.values()) / 1e9 / (sum(v[1] for v in cand.values()) / 1e3) / hbm
+                roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                        "peak_source": src, "traffic": ncu_traffic(kname), "launches_per_step": cnt // 2,
+                        "avg_launch_us": 1e3 * tot_ms / cnt, "algorithmic_bytes_per_launch": tot_bytes / cnt,
+                        "kernel_share_of_step": (tot_ms / 2) / (ms / a.steps),
+                        "our_kernels_share_of_step": ours_ms / (ms / a.steps),
+                        "our_kernels_time_weighted_frac": w_frac,
+                        "all_kernels": {k: {"ms_per_step": round(v[1] / 2, 4), "launches_per_step": v[0] // 2,
+                                            "GBps": round(v[2] / (v[1] / 1e3) / 1e9, 1) if v[1] > 0 and v[2] > 0 else None}
+                                        for k, v in sorted(prof.items())}}
+    # ---- roofline 2: whole step against the arithmetic-intensity roofline (SURVEY 8d), and the CoT layers alone (N = 1)
+    if rank == 0:
+        try:
+            model.eval()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                rows = roofline.layer_table(model, x_res[:2], s=2, batch=B)
+            model.train()
+            sr = roofline.step_roofline(rows, hbm, tf_sust)
+            t_step = ms / a.steps
+            extra["step_roofline"] = {
+                "definition": "sum over layers of max(FLOPs / %.0f TF/s sustained, compulsory bytes / %.0f GB/s): every conv reads "
+                              "input+weights once and writes its output once, a CoT block moves only its input and output, "
+                              "norm/activation/pool/residual fused away; backward = 2x FLOPs, 2x bytes" % (tf_sust, hbm),
+                "fwd_ms": sr["fwd_ms"], "fwd_bwd_ms": sr["fwd_bwd_ms"], "cot_layers_fwd_ms": sr["cot_fwd_ms"],
+                "cot_layers_fwd_bwd_ms": sr["cot_fwd_bwd_ms"], "flops_fwd": sr["flops_fwd"],
+                "frac": (sr["fwd_ms"] if a.fwd_only else sr["fwd_bwd_ms"]) / t_step, "measured_ms": t_step}
+            if world == 1 and not a.no_cot_leg:
+                per, fwd_ms = cot_forward_leg(model, x_res, 3)
+                cot_ms = sum(per.values())
+                rb = roofline.step_roofline([r for r in rows if r["kind"] == "cot"], hbm, tf_burst)
+                extra["cot_forward"] = {"cot_layers_ms": cot_ms, "roofline_ms": rb["cot_fwd_ms"], "frac": rb["cot_fwd_ms"] / cot_ms,
+                                        "model_forward_ms": fwd_ms, "layers": len(per), "mode": "eval, bf16, no_grad, eager, "
+                                        "CUDA events around every CoT layer inside the model; roofline at burst peaks",
+                                        "slowest_layer_ms": max(per.values()), "fastest_layer_ms": min(per.values())}
+        except Exception as e:          # noqa: BLE001
+            extra["step_roofline_error"] = repr(e)[:200]
+    # ---- exposed communication: the same captured step without any collective (N > 1)
+    if world > 1 and not a.fwd_only and a.exposed_comm:
+        try:
+            ms_nc = ts.time_without_comm(a.steps, timed)
+            extra["comm"] = {"exposed_ms_per_step": ms / a.steps - ms_nc / a.steps, "ms_per_step_without_collectives": ms_nc / a.steps,
+                             "bucket_MB": ts.G_big.numel() * ts.G_big.element_size() / 1e6, "bucket_dtype": str(ts.G_big.dtype),
+                             "chunks": len(ts.plan["chunks"]), "overlap": ts.overlap}
+        except Exception as e:          # noqa: BLE001
+            extra["comm_error"] = repr(e)[:200]
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -452,16 +500,20 @@ def main_ours(a):
             "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "%s %dx%d bs%d/GPU fwd+bwd+SGD-nesterov, bf16 autocast over fp32 master weights, "
-                                   "channels_last%s" % (a.model, R, R, B, " [FORWARD ONLY diagnostic]" if a.fwd_only else ""),
+            "config": {"workload": "%s %dx%d bs%d/GPU %s, bf16 compute over fp32 master weights, channels_last"
+                                   % (a.model, R, R, B, "[FORWARD ONLY diagnostic, eval mode]" if a.fwd_only else
+                                      "fwd+bwd+SGD-nesterov(+EMA %s)" % ("off" if a.no_ema else "0.9999")),
                        "global_batch": B * world, "parallelism": "dp%d" % world,
                        "l2": "per-step working set (activations, several GB) >> 126 MB L2; no explicit flush needed",
+                       "step": "cotnet_b200.trainer.TrainStep: weights %s, gradient bucket %s, %d comm chunk(s), overlap %s"
+                               % (a.weights, str(ts.G_big.dtype), len(ts.plan["chunks"]), ts.overlap),
                        "cot_path": "libcotb200: LocalConv fwd/dX/dW, GroupNorm(9 taps) fwd/bwd, bn+SiLU+pool+radix-2 "
-                                   "recombination fwd/bwd, fused BatchNorm(+ReLU,+residual) of the block and of the "
-                                   "enclosing bottleneck, NHWC pooling, gradient fan-in; embed.0 of every CoT layer = tcgen05 two-pair GEMM "
-                                   "(no concat, BN statistics in the epilogue), the other convolutions cuDNN"},
+                                   "recombination fwd/bwd (also SplitAttnConv2d's tail), fused BatchNorm(+ReLU,+residual), NHWC "
+                                   "pooling, gradient fan-in, embed.0 = tcgen05 two-pair GEMM, gradient gather + SGD/EMA/bf16-copy "
+                                   "kernel, uint8->bf16 NHWC normalise; remaining convolutions cuDNN"},
             "e2e": e2e, "gpu_launches": int(launches), "launch_mode": graph_info, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -117,6 +117,11 @@ class _GatherTable:
 
 
 class TrainStep:
+    #: tests/test_dist_cpu.py drives the bucket / chunk / hook / all-reduce logic on CPU tensors over gloo through a subclass
+    #: that sets this flag and replaces the two kernel-launching methods (_launch_gather, optimizer_step) with torch ops.
+    #: The product class refuses CPU models.
+    _host_logic_only = False
+
     def __init__(self, model, lr=0.05, momentum=0.9, weight_decay=1e-4, nesterov=True, ema_decay=None,
                  loss_fn=None, amp_dtype=torch.bfloat16, weights="bf16", bucket_dtype=None, comm_chunks=3, overlap=True,
                  process_group=None):
@@ -127,11 +132,12 @@ class TrainStep:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         dev = next(model.parameters()).device
-        if dev.type != "cuda":
+        self._cuda = dev.type == "cuda"
+        if not self._cuda and not self._host_logic_only:
             raise RuntimeError("TrainStep: the model must live on a CUDA device (libcotb200 has no CPU path)")
         self.dev = dev
-        self.lib = _lib.load()
-        self.chunk_elems = int(self.lib.cotb200_gather_chunk())
+        self.lib = _lib.load() if self._cuda else None
+        self.chunk_elems = int(self.lib.cotb200_gather_chunk()) if self._cuda else 8192
         self.overlap = bool(overlap) and self.world > 1
         plan = plan_flat(list(model.named_parameters()), comm_chunks if self.overlap else 1)
         self.plan = plan
@@ -166,7 +172,7 @@ class TrainStep:
             if self.ema:
                 bufs = [b for _, b in model.named_buffers()]
                 self.ema_buffers = [b.detach().clone() for b in bufs]
-                segs = (_Seg2 * len(bufs))()
+                segs = (_Seg2 * max(1, len(bufs)))()
                 keep = 0
                 for b, e in zip(bufs, self.ema_buffers):
                     if b.dtype == torch.float32:
@@ -177,8 +183,10 @@ class TrainStep:
                         continue
                     segs[keep].dst, segs[keep].src, segs[keep].numel, segs[keep].dtype = e.data_ptr(), b.data_ptr(), b.numel(), code
                     keep += 1
-                raw = torch.frombuffer(bytearray(bytes(segs)), dtype=torch.uint8)[:keep * ctypes.sizeof(_Seg2)]
-                self._lerp_tab = raw.to(dev) if keep else None
+                self._lerp_tab = None
+                if keep:
+                    raw = torch.frombuffer(bytearray(bytes(segs)), dtype=torch.uint8)[:keep * ctypes.sizeof(_Seg2)]
+                    self._lerp_tab = raw.to(dev)
                 self._lerp_n = keep
         self.hyper = torch.tensor([lr, momentum, weight_decay, ema_decay if self.ema else 0.0, 1.0], **f32)
         self.hyper_small = self.hyper.clone()
@@ -188,8 +196,11 @@ class TrainStep:
         # gather tables: one per comm chunk of the big bucket + one for the small bucket
         def blocks_of(items):
             return sum((p.numel() + self.chunk_elems - 1) // self.chunk_elems for _, p, _ in items)
-        self._tabs = [_GatherTable(len(idx), blocks_of([plan["big"][i] for i in idx]), dev) for _, _, idx in plan["chunks"]]
-        self._tab_small = _GatherTable(max(1, len(plan["small"])), max(1, blocks_of(plan["small"])), dev)
+        if self._cuda:
+            self._tabs = [_GatherTable(len(idx), blocks_of([plan["big"][i] for i in idx]), dev) for _, _, idx in plan["chunks"]]
+            self._tab_small = _GatherTable(max(1, len(plan["small"])), max(1, blocks_of(plan["small"])), dev)
+        else:
+            self._tabs, self._tab_small = [None] * len(plan["chunks"]), None
         self._chunk_of = {}
         for c, (_, _, idx) in enumerate(plan["chunks"]):
             for i in idx:
@@ -197,7 +208,7 @@ class TrainStep:
         self._pending = [0] * len(plan["chunks"])
         self._flushed = [False] * len(plan["chunks"])
         self._capturing = False
-        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.comm_stream = torch.cuda.Stream(device=dev) if (self.world > 1 and self._cuda) else None
         self._graph = None
         self.exposed_comm_ms = None
         if self.overlap:
@@ -238,6 +249,9 @@ class TrainStep:
             bucket[lo:hi].zero_()
         if not ent:
             return
+        self._launch_gather(tab, ent, bucket, [p.grad for _, p, _ in items if p.grad is not None])
+
+    def _launch_gather(self, tab, ent, bucket, grads):
         nb = tab.fill(ent, self.chunk_elems)
         tab.upload(self._capturing)
         st = torch.cuda.current_stream(self.dev).cuda_stream
@@ -250,16 +264,22 @@ class TrainStep:
         else:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
 
+    def _all_reduce_side(self, t):
+        """All-reduce on the communication stream, ordered after everything issued so far on the current stream."""
+        if self.comm_stream is None:
+            self._all_reduce(t)
+            return
+        self.comm_stream.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.comm_stream):
+            self._all_reduce(t)
+
     def _flush_chunk(self, c):
         """Gather chunk c of the big bucket on the current (backward) stream and all-reduce it on the side stream."""
         lo, hi, idx = self.plan["chunks"][c]
         self._flushed[c] = True
         self._gather(self._tabs[c], [self.plan["big"][i] for i in idx], self.G_big, lo, hi)
         if self.world > 1:
-            cur = torch.cuda.current_stream(self.dev)
-            self.comm_stream.wait_stream(cur)
-            with torch.cuda.stream(self.comm_stream):
-                self._all_reduce(self.G_big[lo:hi])
+            self._all_reduce_side(self.G_big[lo:hi])
 
     def _finish_grads(self):
         for c in range(len(self.plan["chunks"])):
@@ -268,16 +288,14 @@ class TrainStep:
         if self.plan["small"]:
             self._gather(self._tab_small, self.plan["small"], self.G_small, 0, self.plan["n_small"])
             if self.world > 1:
-                cur = torch.cuda.current_stream(self.dev)
-                self.comm_stream.wait_stream(cur)
-                with torch.cuda.stream(self.comm_stream):
-                    self._all_reduce(self.G_small)
-        if self.world > 1:
+                self._all_reduce_side(self.G_small)
+        if self.world > 1 and self.comm_stream is not None:
             torch.cuda.current_stream(self.dev).wait_stream(self.comm_stream)
 
     # ------------------------------------------------------------------ the step
     def forward_backward(self, x, lab):
-        fused.step_begin(self.dev)
+        if self._cuda:
+            fused.step_begin(self.dev)
         for _, p, _ in self.plan["big"]:
             p.grad = None
         for _, p, _ in self.plan["small"]:
@@ -285,7 +303,7 @@ class TrainStep:
         for c, (_, _, idx) in enumerate(self.plan["chunks"]):
             self._pending[c] = len(idx)
             self._flushed[c] = False
-        with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
+        with torch.autocast(self.dev.type, dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             out = self.model(x)
             loss = self.loss_fn(out, lab)
         loss.backward()
@@ -375,6 +393,32 @@ class TrainStep:
                 self._all_reduce(self.G_small)
             self._graph[2].replay()
         return self._gloss
+
+    def time_without_comm(self, steps, timed):
+        """Step time (ms for `steps` steps, via the caller's `timed`) of the SAME step with every collective removed: what the
+        bench subtracts to report the exposed (non-overlapped) communication time.  Captures a second graph when graphs are
+        in use.  The weights still move (identical arithmetic per rank, no averaging), so call it after the real timing."""
+        world, self.world = self.world, 1
+        try:
+            if self._graph is None:
+                return timed(lambda: self.step_eager(self._gx, self._glab), steps)
+            if self._graph[0] == "two":
+                def run():
+                    self._graph[1].replay()
+                    self._graph[2].replay()
+                return timed(run, steps)
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            self._capturing = True
+            with torch.cuda.graph(g):
+                self.step_eager(self._gx, self._glab)
+            self._capturing = False
+            for _ in range(2):
+                g.replay()
+            return timed(g.replay, steps)
+        finally:
+            self._capturing = False
+            self.world = world
 
     @property
     def static_inputs(self):

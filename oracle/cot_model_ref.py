@@ -1,4 +1,4 @@
-"""CPU restatement of the CoTNet-50 / CoTNeXt-50 model (the caller of the hot path).  TEST INFRASTRUCTURE ONLY.
+"""CPU restatement of the CoTNet / CoTNeXt / SE-CoTNetD models (the callers of the hot path).  TEST INFRASTRUCTURE ONLY.
 
 Used as (i) the checker for the product backbone in tests and (ii) the timed CPU baseline of ``bench.py``
 (``cpu_baseline`` / ``--impl reference``): the reference has no CPU implementation of the LocalConv op
@@ -106,7 +106,108 @@ class OracleCoTResNet(nn.Module):
         return self.fc(x.mean((2, 3)))
 
 
+# ------------------------------------------------------------------------------------------------ SE-CoTNetD (hybrid)
+class OracleSplitAttn(nn.Module):
+    """models/layers/split_attn.py:31-88 with radix 1, groups 1, swish: conv -> bn0 -> SiLU -> GAP -> fc1 -> bn1 -> SiLU ->
+    fc2 -> sigmoid (RadixSoftmax with radix 1, :26-27) -> rescale."""
+
+    def __init__(self, ch, stride):
+        super().__init__()
+        attn = max(ch // 4, 32)
+        self.conv = nn.Conv2d(ch, ch, 3, stride, 1, bias=False)
+        self.bn0 = nn.BatchNorm2d(ch)
+        self.fc1 = nn.Conv2d(ch, attn, 1)
+        self.bn1 = nn.BatchNorm2d(attn)
+        self.fc2 = nn.Conv2d(attn, ch, 1)
+
+    def forward(self, x):
+        x = F.silu(self.bn0(self.conv(x)))
+        g = x.mean((2, 3), keepdim=True)
+        return x * torch.sigmoid(self.fc2(F.silu(self.bn1(self.fc1(g)))))
+
+
+def _blur_pool(x):
+    """models/layers/blur_pool.py:19-58, filt_size 3, stride 2: reflect-pad 1, depthwise binomial [1,2,1]^2/16."""
+    c = torch.tensor([0.25, 0.5, 0.25], dtype=x.dtype, device=x.device)
+    f = (c[:, None] * c[None, :])[None, None].repeat(x.shape[1], 1, 1, 1)
+    return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), f, stride=2, groups=x.shape[1])
+
+
+class OracleHybridBottleneck(nn.Module):
+    """models/cotnet_hybrid.py:118-204 (cardinality 1, no drop block / drop path)."""
+
+    def __init__(self, inpl, planes, stride, down, use_cot, blur, avd, avd_first):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inpl, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.pool, self.avd_first, self.blur = False, avd_first, blur
+        if use_cot:
+            self.conv2 = OracleCotLayer("cot", planes)
+            self.pool = stride > 1
+        else:
+            if stride > 1 and avd:
+                self.pool, stride = True, 1
+            self.conv2 = OracleSplitAttn(planes, stride)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.downsample = down
+
+    def _avd(self, x):
+        return _blur_pool(x) if self.blur else F.avg_pool2d(x, 3, 2, 1)
+
+    def forward(self, x):
+        r = x
+        x = F.relu(self.bn1(self.conv1(x)))
+        if self.pool and self.avd_first:
+            x = self._avd(x)
+        x = self.conv2(x)
+        if self.pool and not self.avd_first:
+            x = self._avd(x)
+        x = self.bn3(self.conv3(x))
+        if self.downsample is not None:
+            r = self.downsample(r)
+        return F.relu(x + r)
+
+
+class OracleHybridNet(nn.Module):
+    """models/cotnet_hybrid.py:338-452 as configured by se_cotnetd_{50,101,152} (:458-482): deep stem, avg-pool down-sampling,
+    stride 2 in every stage, SplitAttn in layers 1-2 and the odd blocks of layer 3, CoT layer elsewhere."""
+
+    def __init__(self, layers, stem_width, blur=False, avd=False, avd_first=True, num_classes=1000):
+        super().__init__()
+        inpl = stem_width * 2
+        self.conv1 = nn.Sequential(
+            nn.Conv2d(3, stem_width, 3, 2, 1, bias=False), nn.BatchNorm2d(stem_width), nn.ReLU(),
+            nn.Conv2d(stem_width, stem_width, 3, 1, 1, bias=False), nn.BatchNorm2d(stem_width), nn.ReLU(),
+            nn.Conv2d(stem_width, inpl, 3, 1, 1, bias=False))
+        self.bn1 = nn.BatchNorm2d(inpl)
+        for i, (planes, n) in enumerate(zip((64, 128, 256, 512), layers)):
+            blocks = []
+            for b in range(n):
+                s = 2 if b == 0 else 1
+                down = None
+                if b == 0:
+                    down = nn.Sequential(nn.AvgPool2d(2, 2, ceil_mode=True, count_include_pad=False),
+                                         nn.Conv2d(inpl, planes * 4, 1, bias=False), nn.BatchNorm2d(planes * 4))
+                use_cot = planes == 512 or (planes == 256 and b % 2 == 0)         # conv_dim={64,128}, c4_dim=256, c4_idx=even (:138)
+                blocks.append(OracleHybridBottleneck(inpl, planes, s, down, use_cot, blur, avd, avd_first))
+                inpl = planes * 4
+            setattr(self, "layer%d" % (i + 1), nn.Sequential(*blocks))
+        self.fc = nn.Linear(inpl, num_classes)
+
+    load_reference_state = OracleCoTResNet.load_reference_state
+
+    def forward(self, x):
+        x = F.relu(self.bn1(self.conv1(x)))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        return self.fc(x.mean((2, 3)))
+
+
 def build(name="cotnet50"):
     cfg = {"cotnet50": ((3, 4, 6, 3), 1, 64), "cotnext50_2x48d": ((3, 4, 6, 3), 2, 48),
-           "cotnet101": ((3, 4, 23, 3), 1, 64), "cotnext101_2x48d": ((3, 4, 23, 3), 2, 48)}[name]
-    return OracleCoTResNet(*cfg)
+           "cotnet101": ((3, 4, 23, 3), 1, 64), "cotnext101_2x48d": ((3, 4, 23, 3), 2, 48)}
+    hyb = {"se_cotnetd_50": dict(layers=(3, 4, 6, 3), stem_width=32), "se_cotnetd_101": dict(layers=(3, 4, 23, 3), stem_width=64),
+           "se_cotnetd_152": dict(layers=(3, 8, 36, 3), stem_width=64, blur=True, avd=True, avd_first=False)}
+    if name in hyb:
+        return OracleHybridNet(**hyb[name])
+    return OracleCoTResNet(*cfg[name])

@@ -137,7 +137,82 @@ def _trunk_fixture(fname, entry, seed, res=64):
                         n_params=np.int64(sum(p.numel() for p in m.parameters())))
 
 
+def proj_vector(name, shape, seed):
+    """The fixed random direction a gradient is projected on in the train-step fixtures (regenerated from the tensor's
+    name by the tests; storing <grad, r> and ||grad|| per parameter pins every gradient in two floats)."""
+    import zlib
+    gen = torch.Generator().manual_seed((int(seed) * 7919 + zlib.crc32(name.encode())) % (2 ** 31))
+    return torch.randn(shape, generator=gen, dtype=torch.float64)
+
+
+def train_batch(seed, B, res):
+    """Image-like synthetic batch: smooth low-frequency content (bilinearly up-sampled 6x6 noise) + fine noise, per-sample
+    contrast and per-sample colour offset.  i.i.d. N(0,1) images all pool to the same descriptor, which makes every
+    batch-statistics BatchNorm behind a global pool (se.1, bn1 of SplitAttn) normalise pure noise and the training-mode
+    gradients of the net chaotic (fp32 vs fp64 of the SAME code differ by 4 % with i.i.d. images, 1 % with these)."""
+    gen = torch.Generator().manual_seed(int(seed) + 17)
+    lo = torch.randn(B, 3, 6, 6, generator=gen)
+    x = torch.nn.functional.interpolate(lo, size=(res, res), mode="bilinear", align_corners=False) * 2.0
+    x = x + 0.5 * torch.randn(B, 3, res, res, generator=gen)
+    x = x * (torch.rand(B, 1, 1, 1, generator=gen) * 1.5 + 0.5) + torch.randn(B, 3, 1, 1, generator=gen)
+    y = torch.randint(0, 1000, (B,), generator=gen)
+    return x, y
+
+
+def _train_fixture(fname, entry, seed, res, B, round_bf16):
+    """Eval logits + one training step (loss, every parameter gradient as norm + fixed random projection, a few updated
+    running statistics) of the reference's OWN model code in fp64 on name-seeded parameters.  round_bf16: parameters and
+    the batch are rounded to bf16-representable values first (the protocol of SURVEY 8d for bf16 runs)."""
+    ref = ref_import.load()
+    ctor = getattr(ref, entry) if hasattr(ref, entry) else getattr(ref.hybrid, entry)
+    m = hybrid_seeded_state(ctor(), seed)
+    if round_bf16:
+        with torch.no_grad():
+            for t in m.state_dict().values():
+                if t.dtype.is_floating_point:
+                    t.copy_(t.bfloat16().float())
+    m = m.double()
+    x, y = train_batch(seed, B, res)
+    if round_bf16:
+        x = x.bfloat16().float()
+    x = x.double()
+    m.eval()
+    with torch.no_grad():
+        logits = m(x)
+    m.train()
+    loss = torch.nn.functional.cross_entropy(m(x), y)
+    loss.backward()
+    names, gn, gp = [], [], []
+    for n, p_ in m.named_parameters():
+        names.append(n)
+        gn.append(p_.grad.norm().item())
+        gp.append((p_.grad * proj_vector(n, p_.shape, seed)).sum().item())
+    sd = m.state_dict()
+    rm_names = [k for k in sd if k.endswith("running_mean") or k.endswith("running_var")]
+    rm_names = rm_names[:4] + rm_names[-4:]
+    np.savez_compressed(os.path.join(OUT, fname), logits=logits.numpy().astype(np.float32), loss=np.float64(loss.item()),
+                        names=np.array(names), gnorm=np.array(gn), gproj=np.array(gp), seed=np.int64(seed), res=np.int64(res),
+                        B=np.int64(B), round_bf16=np.int64(1 if round_bf16 else 0), rm_names=np.array(rm_names),
+                        rm_values=np.concatenate([sd[k].numpy().reshape(-1)[:8] for k in rm_names]),
+                        n_params=np.int64(sum(p_.numel() for p_ in m.parameters())))
+    print("wrote", fname, "loss", loss.item())
+
+
+TRAIN_FIXTURES = [("cotnet50_train_bf16w.npz", "cotnet50", 3001, 224, 16, True),
+                  ("cotnext50_train_bf16w.npz", "cotnext50_2x48d", 3002, 224, 16, True),
+                  ("se_cotnetd101_train.npz", "se_cotnetd_101", 3003, 224, 8, False),
+                  ("se_cotnetd152_train_320.npz", "se_cotnetd_152", 3004, 320, 4, False)]
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        os.makedirs(OUT, exist_ok=True)
+        torch.set_num_threads(8)
+        for f in TRAIN_FIXTURES:
+            if len(sys.argv) > 2 and sys.argv[2] not in f[0]:
+                continue
+            _train_fixture(*f)
+        return
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.load()
     torch.set_num_threads(4)

@@ -89,14 +89,24 @@ def test_stage_shapes_vs_oracle(kind, cls, dim, H, dtype, cl, training):
     want = fn(x64, {k: v.clone() for k, v in sd64.items()}, training=training)
     with torch.set_grad_enabled(training):
         got = m(x)
-    tol = 1e-3 if dtype == torch.float32 else 1e-2
-    # intermediate tensors are rounded to bf16 between the (unfused) stages of this path, so the bound is
-    # relative to the output scale
+    # Gates.  fp32: the north-star bar, allclose(atol = rtol = 1e-3) relative to the output scale (x4 in training mode: four
+    # batch-statistics BatchNorms + the batch-normalised SE bottleneck).  bf16: the op itself meets 1e-2 elementwise
+    # (tests/test_agg_gpu.py, test_ref_kernels_gpu.py); the BLOCK stores six intermediates (k, e, l, w, v, u) in bf16, each a
+    # 2^-9 relative rounding, and normalises four of them by batch / group statistics -- an elementwise 1e-2 bound on the
+    # block output does not hold for ANY bf16 pipeline (the reference under AMP included).  The gate is therefore the
+    # relative L2 error: <= 1e-2 eval, <= 2e-2 training (budget: sqrt(6) * 2^-9 = 4.8e-3 of independent rounding noise,
+    # x2 for the normalisations' gain in eval, x4 with batch statistics), plus a max-abs sanity bound.
     scale = max(1.0, want.abs().max().item())
-    err = (got.double().cpu() - want).abs()
-    # training mode: four batch-statistics BatchNorms + the batch-normalised SE bottleneck amplify bf16 rounding
-    lim = (tol * (10 if training else 4) if dtype == torch.bfloat16 else tol * (4 if training else 1)) * scale
-    assert err.max().item() <= lim, "max err %.3e (limit %.3e, |ref|max %.3e)" % (err.max().item(), lim, scale)
+    diff = got.double().cpu() - want
+    err = diff.abs()
+    rel_l2 = (diff.norm() / want.norm().clamp_min(1e-12)).item()
+    if dtype == torch.float32:
+        lim = 1e-3 * (4 if training else 1) * scale
+        assert err.max().item() <= lim, "max err %.3e (limit %.3e, |ref|max %.3e)" % (err.max().item(), lim, scale)
+        assert rel_l2 <= (2e-3 if training else 5e-4), rel_l2
+    else:
+        assert rel_l2 <= (2e-2 if training else 1e-2), "relative L2 %.3e (max abs %.3e, |ref|max %.3e)" % (rel_l2, err.max().item(), scale)
+        assert err.max().item() <= (1e-1 if training else 4e-2) * scale, "max err %.3e (|ref|max %.3e)" % (err.max().item(), scale)
     assert got.shape == x.shape and got.dtype == dtype
     if cl:
         assert got.is_contiguous(memory_format=torch.channels_last)

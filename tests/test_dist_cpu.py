@@ -77,3 +77,112 @@ def test_shard_range_edges():
     from cotnet_b200.dist import shard_range
     assert [shard_range(5, r, 8) for r in range(8)] == [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 5), (5, 5), (5, 5)]
     assert shard_range(0, 0, 2) == (0, 0)
+
+
+# ------------------------------------------------------------------------------------------------ TrainStep host logic over gloo
+def _trainstep_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import copy
+    import torch.distributed as dist
+    from cotnet_b200 import dist as cdist, trainer
+    cdist.init_from_env(backend="gloo")
+
+    class HostTrainStep(trainer.TrainStep):
+        """The product's bucket / chunk / hook / all-reduce logic on CPU tensors: only the two kernel launches are replaced by
+        torch ops (test infrastructure; the product class refuses CPU models)."""
+        _host_logic_only = True
+
+        def _launch_gather(self, tab, ent, bucket, grads):
+            for (_, off, n, _), g in zip(ent, grads):
+                bucket[off:off + n] = g.reshape(-1).to(bucket.dtype)
+
+        def optimizer_step(self):
+            for P, M, G, E, h in ((self.P_big, self.M_big, self.G_big, self.E_big, self.hyper),
+                                  (self.P_small, self.M_small, self.G_small, self.E_small, self.hyper_small)):
+                lr, mu, wd, dec, gs = [float(v) for v in h]
+                g = G.float() * gs + wd * P
+                M.mul_(mu).add_(g)
+                P.sub_(lr * (g + mu * M))
+                if E is not None:
+                    E.mul_(dec).add_((1 - dec) * P)
+
+    torch.manual_seed(7)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, bias=True), torch.nn.ReLU(), torch.nn.Conv2d(8, 8, 3), torch.nn.Flatten(),
+                              torch.nn.Linear(8 * 4 * 4, 16), torch.nn.ReLU(), torch.nn.Linear(16, 5))
+    ref = copy.deepcopy(net)
+    lr, mu, wd = 0.1, 0.9, 1e-2
+    ts = HostTrainStep(net, lr=lr, momentum=mu, weight_decay=wd, nesterov=True, ema_decay=0.9, amp_dtype=None, weights="fp32",
+                       comm_chunks=2, overlap=True)
+    assert len(ts.plan["chunks"]) == 2 and ts.overlap and ts.world == 2
+    decay = [p for n, p in ref.named_parameters() if not (p.dim() == 1 or n.endswith(".bias"))]
+    no_decay = [p for n, p in ref.named_parameters() if (p.dim() == 1 or n.endswith(".bias"))]
+    opt = torch.optim.SGD([{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": wd}], lr=lr, momentum=mu, nesterov=True)
+    flushed_in_hooks = []
+    orig_flush = ts._flush_chunk
+    in_backward = {"v": False}
+
+    def spy(c):
+        flushed_in_hooks.append((c, in_backward["v"]))
+        orig_flush(c)
+    ts._flush_chunk = spy
+    orig_fb = ts.forward_backward
+
+    worst = 0.0
+    for step in range(2):
+        g = torch.Generator().manual_seed(100 * step + rank)
+        x = torch.randn(4, 3, 8, 8, generator=g)
+        y = torch.randint(0, 5, (4,), generator=g)
+        in_backward["v"] = True
+        ts.step_eager(x, y)
+        in_backward["v"] = False
+        opt.zero_grad(set_to_none=True)
+        torch.nn.functional.cross_entropy(ref(x), y).backward()
+        for p in ref.parameters():
+            dist.all_reduce(p.grad)
+            p.grad /= world
+        opt.step()
+        ms = ts.master_state()
+        for n, p in ref.named_parameters():
+            worst = max(worst, (ms[n] - p.detach()).abs().max().item())
+    q.put((rank, worst, [c for c, _ in flushed_in_hooks], float(ts.P_big.sum()), float(ts.hyper[4])))
+    dist.destroy_process_group()
+
+
+def test_trainstep_bucket_logic_two_rank_gloo():
+    """TrainStep's flat buckets, chunk planning, post-accumulate hooks (last chunk flushed first, during backward),
+    chunked all-reduce(mean) and the update arithmetic, 2 ranks over gloo, against optim.SGD(nesterov, add_weight_decay) on
+    all-reduced gradients."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_trainstep_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, worst, order, psum, gscale in res:
+        assert worst <= 1e-5, worst
+        assert order == [1, 0, 1, 0], order                 # backward produces the LAST chunk's gradients first, every step
+        assert abs(gscale - 0.5) < 1e-12                    # gloo: SUM all-reduce, 1/world applied by the update
+    assert abs(res[0][3] - res[1][3]) <= 1e-4               # replicas stay in lock-step
+
+
+def test_plan_flat_partition():
+    from cotnet_b200 import backbone, trainer
+    m = backbone.cotnet50()
+    plan = trainer.plan_flat(list(m.named_parameters()), 3)
+    big, small = plan["big"], plan["small"]
+    assert len(big) + len(small) == len(list(m.parameters()))
+    assert all(p.dim() >= 2 for _, p, _ in big) and all(p.dim() == 1 for _, p, _ in small)      # optim_factory.add_weight_decay split
+    offs = [o for _, _, o in big]
+    assert offs == sorted(offs) and all(o % trainer.ALIGN == 0 for o in offs)
+    assert all(o2 - o1 >= p.numel() for (_, p, o1), o2 in zip(big, offs[1:] + [plan["n_big"]]))    # slots do not overlap
+    ch = plan["chunks"]
+    assert len(ch) == 3 and ch[0][0] == 0 and ch[-1][1] == plan["n_big"]
+    assert all(a[1] == b[0] for a, b in zip(ch, ch[1:]))                                           # contiguous cover
+    assert sorted(i for c in ch for i in c[2]) == list(range(len(big)))
+    sizes = [hi - lo for lo, hi, _ in ch]
+    assert max(sizes) <= 1.6 * (plan["n_big"] / 3)                                                  # roughly balanced

@@ -190,3 +190,40 @@ def test_mix_merge_matches_mix_on_split_weights():
     assert (a - b).abs().max() < TOL
     c2 = agg_ref.agg_zeropad_mix_merge_fwd_loops(x.numpy(), w.numpy(), heads, wc, 3, 5, 1, 1, 2, 1)
     assert np.abs(c2 - b.numpy()).max() < TOL
+
+
+def test_oracle_model_train_step_matches_reference_golden(golden_dir):
+    """oracle/cot_model_ref.py (the checker of the GPU model tests and the CPU arm of bench.py) against a TRAINING step of the
+    reference's own cotnet50 (fixture from oracle/make_golden.py train: loss + every parameter gradient as norm and fixed random
+    projection).  The fixture's own batch (16 x 224^2) in fp64."""
+    import zlib  # noqa: F401
+    from oracle import cot_model_ref, make_golden
+    g = np.load(os.path.join(golden_dir, "cotnet50_train_bf16w.npz"))
+    seed = int(g["seed"])
+    o = cot_model_ref.build("cotnet50")
+    # name-seeded state on a module tree with the REFERENCE's names: the product backbone carries them (tests/test_hybrid_cpu.py,
+    # tests/test_patch_cpu.py pin that), the oracle loads from it
+    from cotnet_b200 import backbone
+    src = make_golden.hybrid_seeded_state(backbone.cotnet50(), seed)
+    with torch.no_grad():
+        for t in src.state_dict().values():
+            if t.dtype.is_floating_point:
+                t.copy_(t.bfloat16().float())
+    o.load_reference_state(src.state_dict())
+    o = o.double()      # fp64 like the fixture: training-mode gradients of this net amplify fp32 rounding to the percent level
+    x, y = make_golden.train_batch(seed, int(g["B"]), int(g["res"]))
+    x = x.bfloat16().double()
+    o.train()
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    loss = torch.nn.functional.cross_entropy(o(x), y)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-4 * float(g["loss"])
+    grads = {k.replace("__", "."): p.grad for k, p in o.named_parameters()}
+    worst = 0.0
+    floor = 1e-4 * float(np.median(g["gnorm"]))      # biases in front of a BatchNorm have an exactly-zero gradient (fp64: 1e-17)
+    for n, gn, gp in zip([str(n) for n in g["names"]], g["gnorm"], g["gproj"]):
+        t = grads[n].double()
+        r = make_golden.proj_vector(n, t.shape, seed)
+        d = max(gn, floor)
+        worst = max(worst, abs(t.norm().item() - gn) / d, abs((t * r).sum().item() - gp) / (d * r.norm().item()))
+    assert worst <= 1e-6, worst
