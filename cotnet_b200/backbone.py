@@ -61,14 +61,14 @@ class Bottleneck(nn.Module):
         kernels (2 passes each way) instead of ATen's channels_last batch-norm kernels."""
         cl = torch.channels_last
         residual = x
-        y = fused.bn_act(self.conv1(x).contiguous(memory_format=cl), self.bn1, relu=True)
+        y = fused.conv1x1_bn(x, self.conv1, self.bn1, relu=True)
         if self.avd is not None:
             y = fused.avg_pool3x3s2(y)              # nn.AvgPool2d(3, 2, padding=1) on the fused NHWC kernel
         y = self.conv2(y.contiguous(memory_format=cl))
         if self.downsample is not None:
-            residual = fused.bn_act(self.downsample[0](x).contiguous(memory_format=cl), self.downsample[1], relu=False)
-        return fused.bn_act(self.conv3(y).contiguous(memory_format=cl), self.bn3, relu=True,
-                            res=residual.contiguous(memory_format=cl))
+            residual = fused.conv1x1_bn(x, self.downsample[0], self.downsample[1], relu=False)
+        return fused.conv1x1_bn(y.contiguous(memory_format=cl), self.conv3, self.bn3, relu=True,
+                                res=residual.contiguous(memory_format=cl))
 
 
 class CoTResNet(nn.Module):

@@ -124,7 +124,7 @@ class CoTBottleneck(nn.Module):
     def forward(self, x):
         cl = torch.channels_last
         if fused.supported(x):      # channels_last CUDA tensors: fused BatchNorm(+ReLU,+residual) glue like backbone.Bottleneck
-            y = fused.bn_act(self.conv1(x).contiguous(memory_format=cl), self.bn1, relu=True)
+            y = fused.conv1x1_bn(x, self.conv1, self.bn1, relu=True)
             if self.avd is not None and self.avd_first:
                 y = self._pool(y)
             y = self.conv2(y.contiguous(memory_format=cl))
@@ -133,9 +133,9 @@ class CoTBottleneck(nn.Module):
             residual = x
             if self.downsample is not None:
                 d = self.downsample
-                residual = fused.bn_act(d[1](d[0](x)).contiguous(memory_format=cl), d[2], relu=False)
-            return fused.bn_act(self.conv3(y.contiguous(memory_format=cl)).contiguous(memory_format=cl), self.bn3, relu=True,
-                                res=residual.contiguous(memory_format=cl))
+                residual = fused.conv1x1_bn(d[0](x).contiguous(memory_format=cl), d[1], d[2], relu=False)
+            return fused.conv1x1_bn(y.contiguous(memory_format=cl), self.conv3, self.bn3, relu=True,
+                                    res=residual.contiguous(memory_format=cl))
         residual = x
         y = self.act1(self.bn1(self.conv1(x)))
         if self.avd is not None and self.avd_first:

@@ -82,21 +82,21 @@ class CotLayer(nn.Module):
         xk, xc, xv = fused.fan_out(x, 3)
         k = fused.bn_act(self.key_embed[0](xk).contiguous(memory_format=cl), self.key_embed[1], relu=True)
         kc, kt = fused.fan_out(k, 2)
-        hybrid = (self.train_conv_backend in ("tc_e0", "tc_1x1", "tc_e0e3") and fused.tc_supported(x, self.dim)
+        hybrid = (self.train_conv_backend in ("tc_e0", "tc_1x1", "tc_e0e3", "tc_all1x1") and fused.tc_supported(x, self.dim)
                   and k.dtype == x.dtype)
         if hybrid:      # embed.0 as ONE tcgen05 GEMM over the operand pairs (x, W_x), (k, W_k): no concat, statistics in the epilogue
             em = self.embed
-            e = fused.TcConv1x1Fn.apply(xc, kc, em[0].weight, None, em[1].weight, em[1].bias, em[1], True)
+            e = fused.TcConv1x1Fn.apply(xc, kc, em[0].weight, None, em[1].weight, em[1].bias, em[1], True, None)
         else:
             e = fused.bn_act(self.embed[0](torch.cat([xc, kc], dim=1)).contiguous(memory_format=cl), self.embed[1], relu=True)
         # embed.3 runs bias-free; its bias is added (and differentiated) inside the GroupNorm kernels
-        if hybrid and self.train_conv_backend == "tc_e0e3":
-            l = fused.TcConv1x1Fn.apply(e, None, self.embed[3].weight, None, None, None, None, False)
+        if hybrid and self.train_conv_backend in ("tc_e0e3", "tc_all1x1"):
+            l = fused.TcConv1x1Fn.apply(e, None, self.embed[3].weight, None, None, None, None, False, None)
         else:
             l = F.conv2d(e, self.embed[3].weight, None)
-        if hybrid and self.train_conv_backend == "tc_1x1":
+        if hybrid and self.train_conv_backend in ("tc_1x1", "tc_all1x1"):
             cv = self.conv1x1
-            v = fused.TcConv1x1Fn.apply(xv, None, cv[0].weight, None, cv[1].weight, cv[1].bias, cv[1], False)
+            v = fused.TcConv1x1Fn.apply(xv, None, cv[0].weight, None, cv[1].weight, cv[1].bias, cv[1], False, None)
         else:
             v = fused.bn_act(self.conv1x1[0](xv).contiguous(memory_format=cl), self.conv1x1[1], relu=False)
         if l.dtype != v.dtype:
@@ -161,9 +161,9 @@ class CotLayer(nn.Module):
         B, C, H, W = x.shape
         ke, em, cv = self.key_embed, self.embed, self.conv1x1
         k = fused.TcConv3x3Fn.apply(x, ke[0].weight, ke[1].weight, ke[1].bias, ke[1], 4, True)
-        e = fused.TcConv1x1Fn.apply(x, k, em[0].weight, None, em[1].weight, em[1].bias, em[1], True)
-        l = fused.TcConv1x1Fn.apply(e, None, em[3].weight, em[3].bias, None, None, None, False)
-        v = fused.TcConv1x1Fn.apply(x, None, cv[0].weight, None, cv[1].weight, cv[1].bias, cv[1], False)
+        e = fused.TcConv1x1Fn.apply(x, k, em[0].weight, None, em[1].weight, em[1].bias, em[1], True, None)
+        l = fused.TcConv1x1Fn.apply(e, None, em[3].weight, em[3].bias, None, None, None, False, None)
+        v = fused.TcConv1x1Fn.apply(x, None, cv[0].weight, None, cv[1].weight, cv[1].bias, cv[1], False, None)
         gc = fused.tap_chunk(C // 8)
         w = fused.group_norm9(l, em[4], gc)
         u = fused.AggTapFn.apply(v, w, 1, gc)

@@ -539,7 +539,7 @@ def split_attn_tail(u, bn0: torch.nn.BatchNorm2d, fc1, bn1, fc2):
 # Dense parts of the block on the tcgen05 kernels, with autograd.
 #   forward      : tc GEMM / implicit-GEMM conv; training-mode BatchNorm statistics come out of the GEMM epilogue
 #   data gradient: the same tc kernels (transposed weights; the 3x3 conv with flipped taps)
-#   weight grad  : cuBLAS / cuDNN through torch (the MN-major tcgen05 variant is future work)
+#   weight grad  : 1x1: the MN-major tcgen05 kernel (tc_wgrad.cu); the grouped 3x3 still goes through cuDNN
 # ====================================================================================================================
 from . import tc as _tc  # noqa: E402
 
@@ -569,8 +569,9 @@ class TcConv1x1Fn(Function):
     bn = nn.BatchNorm2d or None (then `cbias` is the conv bias or None)."""
 
     @staticmethod
-    def forward(ctx, a1, a2, weight, cbias, bn_w, bn_b, bn, relu):
+    def forward(ctx, a1, a2, weight, cbias, bn_w, bn_b, bn, relu, res=None):
         assert _is_cl(a1) and a1.dtype == torch.bfloat16 and (a2 is None or (_is_cl(a2) and a2.dtype == a1.dtype))
+        assert res is None or (bn is not None and _is_cl(res) and res.dtype == a1.dtype)
         B, K1, H, W = a1.shape
         K2 = 0 if a2 is None else a2.shape[1]
         N = weight.shape[0]
@@ -590,31 +591,39 @@ class TcConv1x1Fn(Function):
             sums = _zeros((2, N,), a1.device)
             pre = torch.empty_like(out, memory_format=torch.channels_last)
             _tc.gemm_bf16(a1, b1, a2, b2, stats=(sums[0], sums[1]), out=_rows2d(pre))
-            ss = _bn_apply_batch(pre, None, sums, bn, bn_w, bn_b, relu, out, lib, st, dt)
+            ss = _bn_apply_batch(pre, None if res is None else res.detach(), sums, bn, bn_w, bn_b, relu, out, lib, st, dt)
             scale, shift, mean, rstd = ss[0], ss[1], ss[2], ss[3]
         else:
             scale, shift, mean, rstd = _bn_eval_fold(bn, bn_w, bn_b)
-            _tc.gemm_bf16(a1, b1, a2, b2, scale=scale, shift=shift, relu=relu, out=out2d)
+            if res is None:
+                _tc.gemm_bf16(a1, b1, a2, b2, scale=scale, shift=shift, relu=relu, out=out2d)
+            else:       # eval mode with a residual: raw GEMM, then the fused scale/shift + residual + ReLU kernel
+                pre = torch.empty_like(out, memory_format=torch.channels_last)
+                _tc.gemm_bf16(a1, b1, a2, b2, out=_rows2d(pre))
+                _lib.check(lib.cotb200_bn_apply(dt, B, H * W, N, pre.data_ptr(), res.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                                1 if relu else 0, out.data_ptr(), st), "bn_apply")
         need_bwd = any(ctx.needs_input_grad)
         if need_bwd and bn is not None and pre is None:      # eval-mode module under grad: BN backward needs the raw conv output
             pre = torch.empty_like(out, memory_format=torch.channels_last)
             _tc.gemm_bf16(a1, b1, a2, b2, out=_rows2d(pre))
         ctx.save_for_backward(a1, a2, wb, pre, out if relu else None, scale, mean, rstd)
         ctx.cfg = (relu, batch, bn is not None, cbias is not None, weight.dtype, weight.shape,
-                   None if bn_w is None else bn_w.dtype, None if cbias is None else cbias.dtype, K1, K2)
+                   None if bn_w is None else bn_w.dtype, None if cbias is None else cbias.dtype, K1, K2, res is not None)
         return out
 
     @staticmethod
     def backward(ctx, dy):
         a1, a2, wb, pre, y, scale, mean, rstd = ctx.saved_tensors
-        relu, batch, has_bn, has_bias, wdt, wshape, bndt, cbdt, K1, K2 = ctx.cfg
+        relu, batch, has_bn, has_bias, wdt, wshape, bndt, cbdt, K1, K2, has_res = ctx.cfg
         B, N, H, W = dy.shape
         M = B * H * W
         lib, st, dt = _lib.load(), _lib.stream_ptr(dy), _lib.BF16
         dy = dy.contiguous(memory_format=torch.channels_last)
-        dgamma = dbeta = dcb = None
+        dgamma = dbeta = dcb = dres = None
         if has_bn:
             sums = torch.zeros(2, N, dtype=torch.float32, device=dy.device)      # escapes as dgamma/dbeta
+            if has_res and ctx.needs_input_grad[8]:
+                dres = torch.empty_like(dy, memory_format=torch.channels_last)
             _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
                                                None, mean.data_ptr(), rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(),
                                                sums[1].data_ptr(), st),
@@ -623,7 +632,7 @@ class TcConv1x1Fn(Function):
             _lib.check(lib.cotb200_bn_bwd_apply(dt, B, H * W, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
                                                 None, mean.data_ptr(), rstd.data_ptr(), _lib.ptr(sums[0]) if batch else None,
                                                 _lib.ptr(sums[1]) if batch else None, 1.0 / M, 1 if relu else 0,
-                                                dpre.data_ptr(), None, st), "bn_bwd_apply")
+                                                dpre.data_ptr(), _lib.ptr(dres), st), "bn_bwd_apply")
             dgamma, dbeta = sums[1].to(bndt), sums[0].to(bndt)
         else:
             dpre = dy if not relu else dy * (y > 0)
@@ -640,11 +649,12 @@ class TcConv1x1Fn(Function):
             _tc.gemm_bf16(dpre, wt[K1:], out=_rows2d(da2))
         dw = None
         if ctx.needs_input_grad[2]:
-            parts = [torch.mm(d2.t(), _rows2d(a1))]               # weight gradient: cuBLAS (see module docstring)
-            if a2 is not None:
-                parts.append(torch.mm(d2.t(), _rows2d(a2)))
-            dw = torch.cat(parts, 1).reshape(wshape).to(wdt)
-        return da1, da2, dw, dcb, dgamma, dbeta, None, None
+            # weight gradient dW = dpre^T [a1 | a2] on the MN-major tcgen05 kernel (csrc/tc_wgrad.cu): the NHWC tiles are
+            # consumed as they land, fp32 accumulation, one launch for both operand pairs
+            acc = _zeros((N, K1 + K2,), dy.device)
+            _tc.wgrad_bf16(dpre, a1, a2, out=acc)
+            dw = acc.reshape(wshape).to(wdt)
+        return da1, da2, dw, dcb, dgamma, dbeta, None, None, dres
 
 
 class TcConv3x3Fn(Function):
@@ -702,6 +712,25 @@ class TcConv3x3Fn(Function):
             # weight gradient: cuDNN grouped wgrad through torch
             dw = torch.nn.grad.conv2d_weight(x, weight.shape, dpre, stride=1, padding=1, dilation=1, groups=groups).to(weight.dtype)
         return dx, dw, sums[1].to(bndt), sums[0].to(bndt), None, None, None
+
+
+#: which 1x1 convolutions of the ENCLOSING bottleneck (conv1 / conv3 / stride-1 downsample) run on the tcgen05 kernels in
+#: training: "tc_all1x1" = all of them (forward with the BatchNorm statistics in the epilogue, data and weight gradients),
+#: anything else = cuDNN + the fused BatchNorm kernels.  Same environment variable as CotLayer.train_conv_backend.
+import os as _os  # noqa: E402
+trunk_conv_backend = _os.environ.get("COTB200_TRAIN_CONV", "tc_e0")
+
+
+def conv1x1_bn(x, conv, bn, relu, res=None):
+    """act(BN(conv1x1(x)) (+ res)) for the bottleneck's 1x1 convolutions (models/cotnet.py:229-235,249-262): on the tcgen05
+    GEMMs when the backend says so and the geometry allows (bf16 channels_last, stride 1, dense, no bias), else cuDNN + the
+    fused BatchNorm kernels."""
+    w = conv.weight
+    if (trunk_conv_backend == "tc_all1x1" and x.dtype == torch.bfloat16 and supported(x) and conv.kernel_size == (1, 1)
+            and conv.stride == (1, 1) and conv.groups == 1 and conv.bias is None and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0
+            and (torch.is_grad_enabled() or not bn.training)):
+        return TcConv1x1Fn.apply(x, None, w, None, bn.weight, bn.bias, bn, relu, res)
+    return bn_act(conv(x).contiguous(memory_format=torch.channels_last), bn, relu=relu, res=res)
 
 
 def tc_supported(x, dim):

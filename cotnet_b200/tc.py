@@ -39,6 +39,35 @@ def gemm_bf16(a1, b1, a2=None, b2=None, scale=None, shift=None, relu=False, stat
     return out
 
 
+def wgrad_bf16(dy, a1, a2=None, out=None):
+    """dW [N, K1 (+K2)] fp32 = dy[M, N]^T @ [a1 | a2][M, K]: the weight gradient of a 1x1 convolution with output gradient dy and
+    input(s) a1 (, a2).  Operands: 2-D row-major or channels_last activations (rows = pixels), bf16.  `out` (fp32, zeroed) may be
+    given; the kernel ADDS into it."""
+    M, N, ldy = _rows(dy)
+    M1, K1, lda1 = _rows(a1)
+    assert M1 == M and dy.dtype == torch.bfloat16 and a1.dtype == torch.bfloat16
+    K2, lda2 = 0, 0
+    if a2 is not None:
+        M2, K2, lda2 = _rows(a2)
+        assert M2 == M and a2.dtype == torch.bfloat16
+    K = K1 + K2
+    if out is None:
+        out = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
+    assert out.shape == (N, K) and out.dtype == torch.float32 and out.stride(1) == 1
+    lib = _lib.load()
+    # orientation: rows of the MMA tile (128 per CTA) from dy or from the input -- whichever needs fewer tiles
+    t0 = ((N + 127) // 128) * ((K + 255) // 256)
+    t1 = ((K + 127) // 128) * ((N + 255) // 256)
+    if a2 is None and t1 < t0:
+        rc = lib.cotb200_wgrad_bf16(M, K1, a1.data_ptr(), lda1, N, dy.data_ptr(), ldy, 0, None, 0, out.data_ptr(), out.stride(0), 1,
+                                    _lib.stream_ptr(dy))
+    else:
+        rc = lib.cotb200_wgrad_bf16(M, N, dy.data_ptr(), ldy, K1, a1.data_ptr(), lda1, K2, _lib.ptr(a2), lda2, out.data_ptr(),
+                                    out.stride(0), 0, _lib.stream_ptr(dy))
+    _lib.check(rc, "wgrad_bf16")
+    return out
+
+
 def conv_tile(C, groups):
     """N tile (output channels per CTA) used by conv3x3_bf16 for a grouped conv, or None if unsupported."""
     cg = C // groups

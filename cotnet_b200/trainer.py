@@ -236,7 +236,7 @@ class TrainStep:
             if g is None:
                 missing = True
                 continue
-            if g.stride() != p.stride():                 # autograd normally matches the parameter's layout; be safe
+            if any(a_ != b_ for a_, b_, n_ in zip(g.stride(), p.stride(), p.shape) if n_ != 1):   # same memory order? (size-1 dims are free)
                 t = torch.empty_strided(p.size(), p.stride(), dtype=g.dtype, device=g.device)
                 t.copy_(g)
                 p.grad = g = t

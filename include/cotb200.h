@@ -242,6 +242,16 @@ int cotb200_conv3x3_bf16(int B, int H, int W, int C, const void* X, long long ld
                          void* D, long long ldd, const float* scale, const float* shift, int relu,
                          float* col_sum, float* col_sqsum, void* stream);
 
+/* cotb200_wgrad_bf16: weight gradient of a 1x1 convolution,  OUT += A[M,R]^T [B1[M,C1] | B2[M,C2]]  (contraction over the M
+ *   pixels; A = dY, B = the convolution input(s); bf16 operands, fp32 accumulation in TMEM, fp32 OUT).  Replaces cuDNN's wgrad
+ *   for embed.0 / embed.3 / conv1x1.0 (models/cotnet.py:52,55,60) and the bottleneck's 1x1 convolutions (:228-264).
+ *   Both operands are consumed MN-major straight from their NHWC tiles (no transposes).  Split over pixel ranges across the
+ *   SMs; partial tiles are added to OUT with global reductions, so the caller ZEROES OUT first.
+ *   transpose = 0: OUT[r*ldo + c] (r < R, c < C1+C2); transpose = 1: OUT[c*ldo + r].
+ *   Requirements: R, C1, C2 multiples of 8 (C1 a multiple of 64 when C2 > 0); operands 16-byte aligned. */
+int cotb200_wgrad_bf16(int M, int R, const void* A, long long lda, int C1, const void* B1, long long ldb1,
+                       int C2, const void* B2, long long ldb2, float* out, long long ldo, int transpose, void* stream);
+
 /* ---- train-step plumbing: what the reference does per parameter tensor -- DDP bucket copy,
  * optim.SGD(nesterov=True) (optim/optim_factory.py:54-56), ModelEmaV2.update over the state_dict (utils/model_ema.py:45-53),
  * one AMP weight cast per convolution -- as ONE pass over flat buffers; and the loader's uint8 normalisation

@@ -78,6 +78,38 @@ def test_conv3x3(C, groups, H, B):
     _close(dx, want_dx)
 
 
+@pytest.mark.parametrize("M,N,K1,K2", [(3136, 64, 256, 0), (3136, 256, 64, 0), (1000, 32, 64, 64), (12544, 72, 32, 0), (200, 128, 128, 0),
+                                       (6272, 512, 2048, 0), (6272, 2048, 512, 0), (4096, 64, 64, 64), (70, 16, 24, 0)])
+def test_wgrad(M, N, K1, K2):
+    """dW = dY^T [A1 | A2] on the MN-major tcgen05 kernel (TMA tiles consumed as they land) vs fp32 matmul."""
+    import os
+    tc = _tc()
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    dy = torch.randn(M, N, generator=g, device="cuda").bfloat16()
+    a1 = torch.randn(M, K1, generator=g, device="cuda").bfloat16()
+    a2 = torch.randn(M, K2, generator=g, device="cuda").bfloat16() if K2 else None
+    want = dy.float().t() @ (torch.cat([a1, a2], 1) if K2 else a1).float()
+    res = {}
+    for variant in ("0", "1"):
+        os.environ["COTB200_WG_DESC"] = variant
+        got = tc.wgrad_bf16(dy, a1, a2)
+        res[variant] = ((got - want).norm() / want.norm()).item()
+    os.environ.pop("COTB200_WG_DESC", None)
+    print("wgrad relative L2 per descriptor variant:", res)
+    assert res["0"] <= 2e-3, res          # fp32 accumulation of exact bf16 products: only the summation order differs
+
+
+def test_wgrad_channels_last_views_and_accumulate():
+    tc = _tc()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    dy = torch.randn(4, 96, 14, 14, generator=g, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    x = torch.randn(4, 192, 14, 14, generator=g, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    want = torch.einsum("bnhw,bkhw->nk", dy.float(), x.float())
+    out = torch.ones(96, 192, device="cuda")
+    tc.wgrad_bf16(dy, x, out=out)                                         # the kernel ADDS into `out`
+    assert ((out - 1.0 - want).norm() / want.norm()).item() <= 2e-3
+
+
 def _cl(t):
     return t.contiguous(memory_format=torch.channels_last)
 
@@ -111,7 +143,7 @@ def test_tc_conv1x1_fn_autograd(training, two):
     a1 = _cl(torch.randn(B, K1, H, H, generator=g, device="cuda").bfloat16()).requires_grad_(True)
     a2 = _cl(torch.randn(B, K2, H, H, generator=g, device="cuda").bfloat16()).requires_grad_(True) if two else None
     cot = _cl(torch.randn(B, N, H, H, generator=g, device="cuda").bfloat16())
-    y = fused.TcConv1x1Fn.apply(a1, a2, conv.weight, None, bn.weight, bn.bias, bn, True)
+    y = fused.TcConv1x1Fn.apply(a1, a2, conv.weight, None, bn.weight, bn.bias, bn, True, None)
     ins = [a1, conv.weight, bn.weight, bn.bias] + ([a2] if two else [])
     grads = torch.autograd.grad(y, ins, cot)
     a1r = a1.detach().float().requires_grad_(True)
@@ -124,6 +156,36 @@ def test_tc_conv1x1_fn_autograd(training, two):
         _rel_l2(a, b)
     if training:
         assert torch.allclose(bn.running_mean, bn_r.running_mean, atol=2e-2)
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_tc_conv1x1_fn_residual(training):
+    """The bottleneck's conv3 -> bn3 -> (+ residual) -> ReLU (models/cotnet.py:249-262) as one TcConv1x1Fn: forward,
+    data / weight / residual gradients vs eager fp32."""
+    import copy
+    import torch.nn as nn
+    from cotnet_b200 import fused
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, K, N, H = 8, 64, 256, 14
+    conv = nn.Conv2d(K, N, 1, bias=False).cuda()
+    bn = nn.BatchNorm2d(N).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.bfloat16().float())
+        bn.weight.uniform_(0.5, 1.5, generator=g); bn.bias.normal_(0, 0.3, generator=g)
+        bn.running_mean.normal_(0, 0.3, generator=g); bn.running_var.uniform_(0.5, 2, generator=g)
+    conv_r, bn_r = copy.deepcopy(conv), copy.deepcopy(bn)
+    bn.train(training); bn_r.train(training)
+    x = _cl(torch.randn(B, K, H, H, generator=g, device="cuda").bfloat16()).requires_grad_(True)
+    res = _cl(torch.randn(B, N, H, H, generator=g, device="cuda").bfloat16()).requires_grad_(True)
+    cot = _cl(torch.randn(B, N, H, H, generator=g, device="cuda").bfloat16())
+    y = fused.TcConv1x1Fn.apply(x, None, conv.weight, None, bn.weight, bn.bias, bn, True, res)
+    grads = torch.autograd.grad(y, [x, conv.weight, bn.weight, bn.bias, res], cot)
+    xr, rr = x.detach().float().requires_grad_(True), res.detach().float().requires_grad_(True)
+    yr = torch.relu(bn_r(conv_r(xr)) + rr)
+    grads_r = torch.autograd.grad(yr, [xr, conv_r.weight, bn_r.weight, bn_r.bias, rr], cot.float())
+    _close(y, yr, 3e-2)
+    for a, b in zip(grads, grads_r):
+        _rel_l2(a, b)
 
 
 @pytest.mark.parametrize("training", [False, True])

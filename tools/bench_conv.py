@@ -56,7 +56,7 @@ def main():
             return torch.autograd.grad(y, (x, wb, bn.weight, bn.bias), cot)
 
         def tc_fb():
-            y = fused.TcConv1x1Fn.apply(x, None, conv.weight, None, bn.weight, bn.bias, bn, True)
+            y = fused.TcConv1x1Fn.apply(x, None, conv.weight, None, bn.weight, bn.bias, bn, True, None)
             return torch.autograd.grad(y, (x, conv.weight, bn.weight, bn.bias), cot)
 
         def cudnn_f():
@@ -65,7 +65,7 @@ def main():
 
         def tc_f():
             with torch.no_grad():
-                return fused.TcConv1x1Fn.apply(x, None, conv.weight, None, bn.weight, bn.bias, bn, True)
+                return fused.TcConv1x1Fn.apply(x, None, conv.weight, None, bn.weight, bn.bias, bn, True, None)
 
         rec = {"name": name, "HW": HW, "K": K, "N": N,
                "cudnn_fwd_us": round(timeit(cudnn_f, a.iters), 1), "tc_fwd_us": round(timeit(tc_f, a.iters), 1),

@@ -36,7 +36,7 @@ def conv1x1(two, training):
     a1 = cl(torch.randn(B, K1, H, H, generator=g, device="cuda").bfloat16()).requires_grad_(True)
     a2 = cl(torch.randn(B, K2, H, H, generator=g, device="cuda").bfloat16()).requires_grad_(True) if two else None
     cot = cl(torch.randn(B, N, H, H, generator=g, device="cuda").bfloat16())
-    y = fused.TcConv1x1Fn.apply(a1, a2, conv.weight, None, bn.weight, bn.bias, bn, True)
+    y = fused.TcConv1x1Fn.apply(a1, a2, conv.weight, None, bn.weight, bn.bias, bn, True, None)
     ins = [a1, conv.weight, bn.weight, bn.bias] + ([a2] if two else [])
     grads = torch.autograd.grad(y, ins, cot)
     a1r = a1.detach().float().requires_grad_(True)
