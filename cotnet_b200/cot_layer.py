@@ -40,6 +40,35 @@ def _keep_format(out, like):
     return out.contiguous()
 
 
+def _dense_from_grouped(w, groups):
+    """[N, K/groups, kh, kw] weight of a grouped convolution -> the block-diagonal dense weight [N, K, kh, kw] of the same
+    convolution (exact zeros outside the blocks).  Differentiable: the gradient of the grouped parameter is the blocks of the
+    dense weight gradient."""
+    if groups == 1:
+        return w
+    N, kg = w.shape[0], w.shape[1]
+    ng = N // groups
+    out = w.new_zeros((N, kg * groups) + tuple(w.shape[2:]))
+    for g in range(groups):
+        out[g * ng:(g + 1) * ng, g * kg:(g + 1) * kg] = w[g * ng:(g + 1) * ng]
+    return out
+
+
+def _coxt_embed0_dense(w, groups):
+    """embed.0 of CoXtLayer (models/cotnet.py:122-123) consumes qk = [x0, k0, x1, k1, ...] (:153-154) with `groups` groups:
+    group g sees the interleave of x[g*Ch:(g+1)*Ch] and k[g*Ch:(g+1)*Ch], Ch = C/groups.  Returns (Wx, Wk), dense [N, C]
+    weights with  embed.0(qk) == x @ Wx^T + k @ Wk^T  -- the operand pairs of the concat-free GEMM."""
+    N, kg = w.shape[0], w.shape[1]                 # kg = 2C / groups
+    ng, ch = N // groups, kg // 2
+    w2 = w.reshape(N, kg)
+    wx = w.new_zeros((N, ch * groups))
+    wk = w.new_zeros((N, ch * groups))
+    for g in range(groups):
+        wx[g * ng:(g + 1) * ng, g * ch:(g + 1) * ch] = w2[g * ng:(g + 1) * ng, 0::2]
+        wk[g * ng:(g + 1) * ng, g * ch:(g + 1) * ch] = w2[g * ng:(g + 1) * ng, 1::2]
+    return wx, wk
+
+
 class CotLayer(nn.Module):
     def __init__(self, dim, kernel_size):
         super(CotLayer, self).__init__()
@@ -231,22 +260,46 @@ class CoXtLayer(nn.Module):
             nn.Conv2d(attn_chs, self.radix * dim, 1))
 
     def _forward_fused(self, x):
+        """channels_last fast path.  The grouped convolutions (groups 8 / 2 / 2 / 2, :113-133) run as DENSE convolutions with
+        block-diagonal weights built from the grouped parameters (differentiable scatter, exact zeros elsewhere -- the same
+        arithmetic): cuDNN's grouped NHWC kernels for 12..96-channel groups spend most of their time in layout transforms
+        (profiles/r02_prof_cotnext50_*.md: 47 % of the step in tensorTransformGeneric), the extra dense FLOPs are free on an
+        HBM-bound block, and the dense form puts embed.0 on the concat-free two-pair tcgen05 GEMM like the CoT layer (the
+        channel interleave of qk, :153-154, becomes a column permutation of the weight)."""
         B, C, H, W = x.shape
-        ks = self.kernel_size
         cl = torch.channels_last
+        G = self.dw_group
         xk, xc, xv = fused.fan_out(x, 3)
-        k = fused.bn_act(self.key_embed[0](xk).contiguous(memory_format=cl), self.key_embed[1], relu=True)
+        wkey = _dense_from_grouped(self.key_embed[0].weight, self.key_embed[0].groups)
+        k = fused.bn_act(F.conv2d(xk, wkey, None, 1, self.kernel_size // 2).contiguous(memory_format=cl), self.key_embed[1], relu=True)
         kc, kt = fused.fan_out(k, 2)
-        qk = torch.stack([xc, kc], dim=2).reshape(B, 2 * C, H, W).contiguous(memory_format=cl)
-        e = fused.bn_act(self.embed[0](qk).contiguous(memory_format=cl), self.embed[1], relu=True)
-        l = F.conv2d(e, self.embed[3].weight, None, groups=self.embed[3].groups)
-        v = fused.bn_act(self.conv1x1[0](xv).contiguous(memory_format=cl), self.conv1x1[1], relu=False)
+        wx, wk = _coxt_embed0_dense(self.embed[0].weight, G)
+        w0 = torch.cat([wx, wk], 1).reshape(C // 2, 2 * C, 1, 1)
+        be = self.train_conv_backend
+        use_tc = be != "cudnn" and x.dtype == torch.bfloat16 and C % 16 == 0 and k.dtype == x.dtype and w0.dtype == x.dtype
+        em, cv = self.embed, self.conv1x1
+        if use_tc:
+            e = fused.TcConv1x1Fn.apply(xc, kc, w0, None, em[1].weight, em[1].bias, em[1], True, None)
+        else:
+            e = fused.bn_act(F.conv2d(torch.cat([xc, kc], dim=1), w0).contiguous(memory_format=cl), em[1], relu=True)
+        w3 = _dense_from_grouped(em[3].weight, G)
+        if use_tc and be in ("tc_e0e3", "tc_all1x1", "tc") and w3.shape[0] % 8 == 0:
+            l = fused.TcConv1x1Fn.apply(e, None, w3, None, None, None, None, False, None)
+        else:
+            l = F.conv2d(e, w3, None)
+        wv = _dense_from_grouped(cv[0].weight, G)
+        if use_tc and be in ("tc_1x1", "tc_all1x1", "tc"):
+            v = fused.TcConv1x1Fn.apply(xv, None, wv, None, cv[1].weight, cv[1].bias, cv[1], False, None)
+        else:
+            v = fused.bn_act(F.conv2d(xv, wv).contiguous(memory_format=cl), cv[1], relu=False)
         if l.dtype != v.dtype:
             l = l.to(v.dtype)
         gc = fused.tap_chunk(C // 8, self.dw_group)
         w = fused.group_norm9(l.contiguous(memory_format=torch.channels_last), self.embed[4], gc, self.embed[3].bias)
         u = fused.AggTapFn.apply(v.contiguous(memory_format=torch.channels_last), w, self.dw_group, gc)
         return fused.cot_tail(u, kt.contiguous(memory_format=torch.channels_last), self.bn, self.se)
+
+    train_conv_backend = os.environ.get("COTB200_TRAIN_CONV", "tc_e0")
 
     def forward(self, x):
         B, C, H, W = x.shape

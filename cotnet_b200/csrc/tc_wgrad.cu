@@ -202,10 +202,9 @@ extern "C" int cotb200_wgrad_bf16(int M, int R, const void* A, long long lda, in
   const int per = (p.kb_total + splits - 1) / splits;
   splits = (p.kb_total + per - 1) / per;                       // no empty splits
   p.splits = splits;
-  // MN blocks of 64 channels are one box (8 KB) apart = LBO; 8-pixel K groups are 1024 B apart = SBO.
-  // COTB200_WG_DESC=1 swaps the two (bring-up switch for the descriptor convention; tests/test_tc_gemm_gpu.py reports both).
+  // MN blocks of 64 channels are one box (8 KB) apart = LBO; 8-pixel K groups are 1024 B apart = SBO (validated on the B200
+  // against fp32 matmul; the swapped convention reads past the operand tiles).
   p.lbo = WG_BOX_BYTES; p.sbo = 1024;
-  if (const char* v = getenv("COTB200_WG_DESC")) { if (v[0] == '1') { p.lbo = 1024; p.sbo = WG_BOX_BYTES; } }
   CUtensorMap ma, mb1, mb2;
   int rc;
   if ((rc = wg_make_map(&ma, A, M, R, lda))) return rc;

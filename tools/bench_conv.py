@@ -67,7 +67,29 @@ def main():
             with torch.no_grad():
                 return fused.TcConv1x1Fn.apply(x, None, conv.weight, None, bn.weight, bn.bias, bn, True, None)
 
-        rec = {"name": name, "HW": HW, "K": K, "N": N,
+        # raw pieces: our kernels vs the library kernels cuDNN picks for the same contraction (bytes = operands once + result once)
+        from cotnet_b200 import tc
+        M = a.batch * HW * HW
+        wk = conv.weight.detach().reshape(N, K).to(torch.bfloat16).contiguous()
+        wkt = wk.t().contiguous()
+        cs, cq = torch.zeros(N, device=dev), torch.zeros(N, device=dev)
+        outb = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        dxb = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
+        dwf = torch.zeros(N, K, device=dev)
+        x2, c2 = x.detach().permute(0, 2, 3, 1).reshape(M, K), cot.permute(0, 2, 3, 1).reshape(M, N)
+        xd = x.detach()
+        raw = {
+            "tc_fwd_stats_us": timeit(lambda: tc.gemm_bf16(x2, wk, stats=(cs, cq), out=outb), a.iters),
+            "tc_dgrad_us": timeit(lambda: tc.gemm_bf16(c2, wkt, out=dxb), a.iters),
+            "tc_wgrad_us": timeit(lambda: tc.wgrad_bf16(c2, x2, out=dwf), a.iters),
+            "cudnn_fprop_us": timeit(lambda: F.conv2d(xd, wb.detach()), a.iters),
+            "cudnn_dgrad_us": timeit(lambda: torch.nn.grad.conv2d_input(xd.shape, wb.detach(), cot), a.iters),
+            "cudnn_wgrad_us": timeit(lambda: torch.nn.grad.conv2d_weight(xd, wb.shape, cot), a.iters),
+        }
+        by = 2.0 * M * (K + N) + 2.0 * N * K
+        raw["roof_us_at_6485GBps"] = round(by / 6485.2e3, 1)
+        raw = {k_: round(v_, 1) for k_, v_ in raw.items()}
+        rec = {"name": name, "HW": HW, "K": K, "N": N, "raw": raw,
                "cudnn_fwd_us": round(timeit(cudnn_f, a.iters), 1), "tc_fwd_us": round(timeit(tc_f, a.iters), 1),
                "cudnn_fwdbwd_us": round(timeit(cudnn_fb, a.iters), 1), "tc_fwdbwd_us": round(timeit(tc_fb, a.iters), 1)}
         rec["tc_over_cudnn_fwdbwd"] = round(rec["tc_fwdbwd_us"] / rec["cudnn_fwdbwd_us"], 3)
