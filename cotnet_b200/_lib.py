@@ -72,10 +72,14 @@ SYMBOLS = {
     "cotb200_gemm_bf16": (ctypes.c_int, [ctypes.c_int] * 3 + [_VP, ctypes.c_longlong, _VP, ctypes.c_longlong]
                           + [ctypes.c_int, _VP, ctypes.c_longlong, _VP, ctypes.c_longlong]
                           + [_VP, ctypes.c_longlong, _VP, _VP, ctypes.c_int, _VP, _VP, _VP]),
+    "cotb200_gemm_bf16_samplestats": (ctypes.c_int, [ctypes.c_int] * 3 + [_VP, ctypes.c_longlong, _VP, ctypes.c_longlong, _VP, ctypes.c_longlong,
+                                                     _VP, _VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP]),
+    "cotb200_gn9_from_colsums": (ctypes.c_int, [ctypes.c_int] * 4 + [_VP, _VP, _VP, ctypes.c_float, _VP, _VP, _VP]),
     "cotb200_conv3x3_bf16": (ctypes.c_int, [ctypes.c_int] * 4 + [_VP, ctypes.c_longlong, _VP, ctypes.c_int, _VP,
                                                                  ctypes.c_longlong, _VP, _VP, ctypes.c_int, _VP, _VP, _VP]),
     "cotb200_wgrad_bf16": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _VP, ctypes.c_longlong, ctypes.c_int, _VP, ctypes.c_longlong,
                                           ctypes.c_int, _VP, ctypes.c_longlong, _VP, ctypes.c_longlong, ctypes.c_int, _VP]),
+    "cotb200_se_eval": (ctypes.c_int, [ctypes.c_int] * 3 + [_VP, ctypes.c_float] + [_VP] * 8),
     "cotb200_gather_chunk": (ctypes.c_int, []),
     "cotb200_multi_gather": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_float, _VP]),
     "cotb200_sgd_ema_step": (ctypes.c_int, [ctypes.c_longlong, _VP, _VP, ctypes.c_int, _VP, _VP, _VP, _VP, ctypes.c_int, _VP]),

@@ -176,11 +176,17 @@ class CotLayer(nn.Module):
         p = self._tc_params(x.device)
         k = tc.conv3x3_bf16(x, p["wk"], p["bnk"], scale=p["k_ss"][0], shift=p["k_ss"][1], relu=True)
         e = tc.gemm_bf16(x, p["we1x"], k, p["we1k"], scale=p["e_ss"][0], shift=p["e_ss"][1], relu=True)
-        l = tc.gemm_bf16(e, p["we2"], shift=p["be2"])
-        v = tc.gemm_bf16(x, p["wv"], scale=p["v_ss"][0], shift=p["v_ss"][1])
-        J = l.shape[1]
         gc = fused.tap_chunk(C // 8)
-        w = fused.group_norm9(l.view(B, H, W, J).permute(0, 3, 1, 2), self.embed[4], gc)
+        if H * W >= 32:     # GroupNorm statistics from the logits GEMM's own epilogue: no statistics pass over l
+            l, cs, cq = tc.gemm_bf16_samplestats(e, p["we2"], H * W, shift=p["be2"])
+            v = tc.gemm_bf16(x, p["wv"], scale=p["v_ss"][0], shift=p["v_ss"][1])
+            J = l.shape[1]
+            w = fused.group_norm9_from_colsums(l.view(B, H, W, J).permute(0, 3, 1, 2), self.embed[4], gc, cs, cq, p["be2"])
+        else:
+            l = tc.gemm_bf16(e, p["we2"], shift=p["be2"])
+            v = tc.gemm_bf16(x, p["wv"], scale=p["v_ss"][0], shift=p["v_ss"][1])
+            J = l.shape[1]
+            w = fused.group_norm9(l.view(B, H, W, J).permute(0, 3, 1, 2), self.embed[4], gc)
         u = fused.AggTapFn.apply(v.view(B, H, W, C).permute(0, 3, 1, 2), w, 1, gc)
         return fused.cot_tail(u, k, self.bn, self.se)
 

@@ -244,3 +244,88 @@ extern "C" int cotb200_u8_to_nhwc(int dtype, int N, int C, int H, int W, const v
   });
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ SE MLP of the CoT tail (eval)
+// a[b, c, 0:2] = softmax_r( W3[2c+r, :] . relu(s1 * (W0 . p[b] + b0) + t1) + b3[2c+r] ),  p[b] = psum[b] * inv_hw
+// (models/cotnet.py:69-77,92-101 with the BatchNorm of `se` folded: s1 = gamma * rstd, t1 = beta - mean * s1).
+// The eager form is ~10 launches of GEMV-sized ops per CoT layer; here one kernel, SE_S samples per CTA so that the two
+// weight matrices are read once per SE_S samples.  fp32 throughout ([B, C] inputs are tiny).
+namespace cotb200 {
+static constexpr int SE_S = 8;
+__global__ void __launch_bounds__(256)
+se_eval_kernel(const float* __restrict__ psum, float inv_hw, const float* __restrict__ W0, const float* __restrict__ b0,
+               const float* __restrict__ s1, const float* __restrict__ t1, const float* __restrict__ W3, const float* __restrict__ b3,
+               float* __restrict__ a, int B, int C, int A) {
+  extern __shared__ float se_sm[];                 // p [SE_S][C] | z [SE_S][A]
+  float* p = se_sm;
+  float* z = se_sm + SE_S * C;
+  const int b0i = blockIdx.x * SE_S;
+  const int ns = min(SE_S, B - b0i);
+  for (int i = threadIdx.x; i < SE_S * C; i += 256) {
+    const int s = i / C, c = i - s * C;
+    p[i] = s < ns ? psum[(long long)(b0i + s) * C + c] * inv_hw : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < A; j += 8) {               // one warp per hidden unit: coalesced row of W0
+    float acc[SE_S];
+#pragma unroll
+    for (int s = 0; s < SE_S; ++s) acc[s] = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float w = __ldg(W0 + (long long)j * C + c);
+#pragma unroll
+      for (int s = 0; s < SE_S; ++s) acc[s] = fmaf(w, p[s * C + c], acc[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < SE_S; ++s) {
+      float v = acc[s];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) z[s * A + j] = fmaxf(fmaf(v + (b0 ? __ldg(b0 + j) : 0.f), __ldg(s1 + j), __ldg(t1 + j)), 0.f);
+    }
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += 8) {               // one warp per channel: the two logits 2c, 2c+1
+    float a0[SE_S], a1[SE_S];
+#pragma unroll
+    for (int s = 0; s < SE_S; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
+    for (int j = lane; j < A; j += 32) {
+      const float w0 = __ldg(W3 + (long long)(2 * c) * A + j), w1 = __ldg(W3 + (long long)(2 * c + 1) * A + j);
+#pragma unroll
+      for (int s = 0; s < SE_S; ++s) { a0[s] = fmaf(w0, z[s * A + j], a0[s]); a1[s] = fmaf(w1, z[s * A + j], a1[s]); }
+    }
+#pragma unroll
+    for (int s = 0; s < SE_S; ++s) {
+      float u = a0[s], v = a1[s];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) { u += __shfl_xor_sync(0xffffffffu, u, o); v += __shfl_xor_sync(0xffffffffu, v, o); }
+      if (lane == 0 && s < ns) {
+        u += b3 ? __ldg(b3 + 2 * c) : 0.f; v += b3 ? __ldg(b3 + 2 * c + 1) : 0.f;
+        const float m = fmaxf(u, v), eu = __expf(u - m), ev = __expf(v - m), inv = 1.f / (eu + ev);
+        a[((long long)(b0i + s) * C + c) * 2] = eu * inv;
+        a[((long long)(b0i + s) * C + c) * 2 + 1] = ev * inv;
+      }
+    }
+  }
+}
+}  // namespace cotb200
+
+extern "C" int cotb200_se_eval(int B, int C, int A, const float* psum, float inv_hw, const float* W0, const float* b0,
+                               const float* s1, const float* t1, const float* W3, const float* b3, float* a, void* stream) {
+  if (!psum || !W0 || !s1 || !t1 || !W3 || !a) { set_error("se_eval: NULL pointer"); return COTB200_ENULL; }
+  if (B <= 0 || C <= 0 || A <= 0) { set_error("se_eval: non-positive dims"); return COTB200_EINVAL; }
+  const size_t smem = (size_t)SE_S * (C + A) * sizeof(float);
+  if (smem > 200 * 1024) { set_error("se_eval: C=%d A=%d too large for the shared-memory staging", C, A); return COTB200_ETOOBIG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (smem > 48 * 1024) {
+    static PerDevFlag cfgd;
+    if (bool& cfg = cfgd.get(); !cfg) {
+      cudaError_t e = cudaFuncSetAttribute(se_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+      cfg = true;
+    }
+  }
+  COTB200_PROF("se_eval");
+  se_eval_kernel<<<(B + SE_S - 1) / SE_S, 256, smem, st>>>(psum, inv_hw, W0, b0, s1, t1, W3, b3, a, B, C, A);
+  return check_launch("se_eval");
+}

@@ -44,6 +44,7 @@ struct TcParams {
   const float* shift;       // [N] or null (=0)
   float* col_sum;           // [N] or null
   float* col_sqsum;         // [N] or null
+  int rows_per_sample;      // > 0: col_sum / col_sqsum are PER SAMPLE, [M / rows_per_sample, N] (GroupNorm statistics of the logits)
 };
 
 // Butterfly transpose-reduce: each lane holds 32 column values of ITS row; afterwards lane j holds the sum over
@@ -228,7 +229,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (stats) {
+        if (stats && p.rows_per_sample > 0) {
+          // per-sample column sums (GroupNorm over the 9 taps x H x W of one sample, models/cotnet.py:56): a warp's 32 rows
+          // touch at most two samples (rows_per_sample >= 32 is checked on the host); one butterfly per sample, straight to global
+          const long long row0 = m0 + quad * 32;
+          const int s_lo = (int)(row0 / p.rows_per_sample);
+          const int rb = (int)min((long long)32, (long long)(s_lo + 1) * p.rows_per_sample - row0);   // first row of sample s_lo + 1
+          const bool col_ok = n0 + c * 32 + lane < p.N;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            if (half == 1 && rb >= 32) break;                                  // warp-uniform
+            float a[32], b[32];
+            const bool mine = row_ok && ((lane < rb) == (half == 0));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { a[j] = mine ? v[j] : 0.f; b[j] = a[j] * a[j]; }
+            const float cs = warp_colsum32(a);
+            const float cq = warp_colsum32(b);
+            const long long srow = (long long)(s_lo + half) * p.N + n0 + c * 32 + lane;
+            if (col_ok && (row0 + (half ? rb : 0)) < p.M) {
+              atomicAdd(p.col_sum + srow, cs);
+              atomicAdd(p.col_sqsum + srow, cq);
+            }
+          }
+        } else if (stats) {
           float a[32], b[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) { a[j] = row_ok ? v[j] : 0.f; b[j] = a[j] * a[j]; }
@@ -275,7 +298,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      if (stats) {
+      if (stats && p.rows_per_sample == 0) {
         const int t = et;
         for (int j = t; j < p.bn; j += 128) {
           if (n0 + j < p.N) {
@@ -409,6 +432,27 @@ extern "C" int cotb200_gemm_bf16(int M, int N, int K1, const void* A1, long long
   } else { a2 = a1; b2 = b1; }
   return tc_launch(a1, b1, a2, b2, p, (M + TC_BM - 1) / TC_BM, st, "tc_gemm_1x1",
                    2.0 * ((double)M * (K1 + K2 + N) + (double)N * (K1 + K2)));
+}
+
+// Same GEMM; col_sum / col_sqsum are accumulated PER SAMPLE of rows_per_sample consecutive rows: [M / rows_per_sample, N].
+extern "C" int cotb200_gemm_bf16_samplestats(int M, int N, int K1, const void* A1, long long lda1, const void* B1, long long ldb1, void* D,
+                                             long long ldd, const float* scale, const float* shift, int relu, int rows_per_sample,
+                                             float* samp_sum, float* samp_sqsum, void* stream) {
+  if (M <= 0 || N <= 0 || K1 <= 0) { set_error("gemm_bf16_samplestats: bad dims"); return COTB200_EINVAL; }
+  if (!A1 || !B1 || !D || !samp_sum || !samp_sqsum) { set_error("gemm_bf16_samplestats: NULL operand"); return COTB200_ENULL; }
+  if ((N & 7) || (K1 & 7) || (ldd & 7)) { set_error("gemm_bf16_samplestats: N, K, ldd must be multiples of 8"); return COTB200_EALIGN; }
+  if (rows_per_sample < 32 || M % rows_per_sample) { set_error("gemm_bf16_samplestats: rows_per_sample=%d must be >= 32 and divide M=%d", rows_per_sample, M); return COTB200_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  TcParams p{};
+  p.M = M; p.N = N; p.rows_per_tile = TC_BM; p.bn = pick_bn(N); p.mode = 0;
+  p.kb1 = (K1 + TC_BK - 1) / TC_BK; p.kb2 = 0;
+  p.relu = relu; p.ldd = ldd; p.D = (__nv_bfloat16*)D; p.scale = scale; p.shift = shift; p.col_sum = samp_sum; p.col_sqsum = samp_sqsum;
+  p.rows_per_sample = rows_per_sample;
+  CUtensorMap a1, b1;
+  int rc;
+  if ((rc = make_map_2d(&a1, A1, M, K1, lda1, TC_BM))) return rc;
+  if ((rc = make_map_2d(&b1, B1, N, K1, ldb1, p.bn))) return rc;
+  return tc_launch(a1, b1, a1, b1, p, (M + TC_BM - 1) / TC_BM, st, "tc_gemm_1x1", 2.0 * ((double)M * (K1 + N) + (double)N * K1));
 }
 
 // 3x3 / pad 1 / stride 1 convolution, NHWC bf16, with dense-per-N-tile prepared weights

@@ -516,7 +516,63 @@ def group_norm9(l, gn: torch.nn.GroupNorm, gc=0, lbias=None):
     return GroupNorm9Fn.apply(l, gn.weight, gn.bias, gn.eps, gc, lbias)
 
 
+def _se_eval_params(se):
+    """fp32 weights of the `se` MLP with its BatchNorm folded (eval mode), cached until a parameter / buffer changes."""
+    key = tuple(t._version for t in list(se.parameters()) + list(se.buffers())) + (str(next(se.parameters()).device),)
+    cache = getattr(se, "_cotb200_eval_cache", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    c0, b1, c3 = se[0], se[1], se[3]
+    with torch.no_grad():
+        rstd = torch.rsqrt(b1.running_var.float() + b1.eps)
+        s1 = (b1.weight.float() * rstd).contiguous()
+        t1 = (b1.bias.float() - b1.running_mean.float() * s1).contiguous()
+        prm = (c0.weight.detach().float().flatten(1).contiguous(), None if c0.bias is None else c0.bias.detach().float().contiguous(), s1, t1,
+               c3.weight.detach().float().flatten(1).contiguous(), None if c3.bias is None else c3.bias.detach().float().contiguous())
+    se._cotb200_eval_cache = (key, prm)
+    return prm
+
+
+def _cot_tail_eval(u, k, bn, se):
+    """Inference form of models/cotnet.py:89-104 in three launches: pool (bn + SiLU + (y + k) summed over the pixels), the
+    whole SE MLP + radix-2 softmax (cotb200_se_eval), recombination."""
+    B, C, H, W = u.shape
+    lib, st, dt = _lib.load(), _lib.stream_ptr(u), _lib.dtype_code(u)
+    ss = _bn_prepare(bn, bn.weight, bn.bias, C, float(B * H * W), None, u.device, st)
+    psum = torch.zeros(B, C, dtype=torch.float32, device=u.device)
+    _lib.check(lib.cotb200_tail_pool(dt, B, H * W, C, u.data_ptr(), k.data_ptr(), ss[0].data_ptr(), ss[1].data_ptr(), psum.data_ptr(), st),
+               "tail_pool")
+    w0, b0, s1, t1, w3, b3 = _se_eval_params(se)
+    a = torch.empty(B, C, 2, dtype=torch.float32, device=u.device)
+    _lib.check(lib.cotb200_se_eval(B, C, w0.shape[0], psum.data_ptr(), 1.0 / (H * W), w0.data_ptr(), _lib.ptr(b0), s1.data_ptr(),
+                                   t1.data_ptr(), w3.data_ptr(), _lib.ptr(b3), a.data_ptr(), st), "se_eval")
+    out = torch.empty_like(u, memory_format=torch.channels_last)
+    _lib.check(lib.cotb200_tail_combine(dt, B, H * W, C, u.data_ptr(), k.data_ptr(), ss[0].data_ptr(), ss[1].data_ptr(), a.data_ptr(),
+                                        out.data_ptr(), st), "tail_combine")
+    return out
+
+
+def group_norm9_from_colsums(l, gn: torch.nn.GroupNorm, gc, csum, csq, lbias_in_stats):
+    """Inference GroupNorm(9 taps) whose statistics come from the logits GEMM's epilogue (per-sample column sums of the raw
+    accumulator, cotb200_gemm_bf16_samplestats): one tiny kernel turns them into mean / rstd, then the apply kernel.  `l` already
+    contains the embed.3 bias; `lbias_in_stats` is that bias (it was NOT in the accumulator the sums were taken from)."""
+    B, J, H, W = l.shape
+    wc = J // 9
+    lib, st, dt = _lib.load(), _lib.stream_ptr(l), _lib.dtype_code(l)
+    mr = torch.empty(2, B * wc, dtype=torch.float32, device=l.device)
+    _lib.check(lib.cotb200_gn9_from_colsums(B, H * W, wc, 0, csum.data_ptr(), csq.data_ptr(), _lib.ptr(lbias_in_stats), float(gn.eps),
+                                            mr[0].data_ptr(), mr[1].data_ptr(), st), "gn9_from_colsums")
+    g32, b32 = _f32(gn.weight), _f32(gn.bias)
+    out = torch.empty_like(l, memory_format=torch.channels_last)
+    _lib.check(lib.cotb200_gn9_apply(dt, B, H * W, wc, gc, l.data_ptr(), None, mr[0].data_ptr(), mr[1].data_ptr(), g32.data_ptr(),
+                                     b32.data_ptr(), out.data_ptr(), st), "gn9_apply")
+    return out
+
+
 def cot_tail(u, k, bn: torch.nn.BatchNorm2d, se: torch.nn.Module):
+    if (not torch.is_grad_enabled() and not bn.training and not se[1].training and k is not None and se[1].running_mean is not None
+            and bn.running_mean is not None and isinstance(se[2], torch.nn.ReLU)):
+        return _cot_tail_eval(u.detach(), k.detach(), bn, se)
     params = [p for p in se.parameters()]
     B, C = u.shape[0], u.shape[1]
     return CotTailFn.apply(u, k, bn.weight, bn.bias, bn, lambda p: torch.softmax(_se_fp32(se, p).view(B, C, 2), dim=2), *params)

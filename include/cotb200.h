@@ -148,6 +148,12 @@ int cotb200_tail_bwd_dz_sums(int dtype, int B, int HW, int C, const void* dout, 
 int cotb200_tail_bwd_apply(int dtype, int B, int HW, int C, const void* dout, const void* u, const float* scale,
                            const float* shift, const float* mu, const float* rstd, const float* a, const float* dpn,
                            const float* c1, const float* c2, float inv_n, float pscale, void* du, void* dk, void* stream);
+/* The SE MLP of the split attention in EVAL mode, one launch (models/cotnet.py:69-77,92-101):
+ *   a[b,c,0:2] = softmax_r( W3[2c+r,:] . relu(s1*(W0 . (psum[b]*inv_hw) + b0) + t1) + b3[2c+r] )
+ * with the BatchNorm of `se` folded into s1 / t1.  psum [B,C] is what cotb200_tail_pool accumulates; a [B,C,2] is what
+ * cotb200_tail_combine takes.  All fp32; W0 [A,C], W3 [2C,A] row-major; b0 / b3 may be NULL. */
+int cotb200_se_eval(int B, int C, int A, const float* psum, float inv_hw, const float* W0, const float* b0,
+                    const float* s1, const float* t1, const float* W3, const float* b3, float* a, void* stream);
 /* BatchNorm2d (+ReLU) (+residual add) on NHWC tensors: y = act(x*scale + shift (+ res)).  With cotb200_col_stats this
  * replaces nn.BatchNorm2d / nn.ReLU pairs of the block (models/cotnet.py:45-46,53-54,61-62) and of the enclosing
  * bottleneck (models/cotnet.py:231-235,:249-262) in 2 forward + 2 backward HBM passes.  relu: 0/1; res may be NULL. */
@@ -231,6 +237,18 @@ int cotb200_gemm_bf16(int M, int N, int K1, const void* A1, long long lda1, cons
                       int K2, const void* A2, long long lda2, const void* B2, long long ldb2,
                       void* D, long long ldd, const float* scale, const float* shift, int relu,
                       float* col_sum, float* col_sqsum, void* stream);
+
+/* cotb200_gemm_bf16_samplestats: the single-product GEMM above whose statistics epilogue accumulates PER SAMPLE:
+ *   samp_sum / samp_sqsum [M / rows_per_sample, N] += column sums / sums of squares of the RAW accumulator over the
+ *   rows_per_sample consecutive rows (= H*W pixels) of each sample.  With cotb200_gn9_from_colsums this gives the GroupNorm
+ *   statistics of the attention logits (models/cotnet.py:55-56) without a pass over them.  rows_per_sample >= 32, M % it == 0. */
+int cotb200_gemm_bf16_samplestats(int M, int N, int K1, const void* A1, long long lda1, const void* B1, long long ldb1,
+                                  void* D, long long ldd, const float* scale, const float* shift, int relu,
+                                  int rows_per_sample, float* samp_sum, float* samp_sqsum, void* stream);
+/* mean[b,g], rstd[b,g] of GroupNorm(wc groups of 9 taps) from per-sample column sums csum / csq [B, 9*wc] of the logits
+ * BEFORE the bias (bias [9*wc] or NULL is accounted for analytically); column order given by gc like cotb200_gn9_apply. */
+int cotb200_gn9_from_colsums(int B, int HW, int wc, int gc, const float* csum, const float* csq, const float* bias,
+                             float eps, float* mean, float* rstd, void* stream);
 
 /* cotb200_conv3x3_bf16: 3x3 / stride 1 / zero-pad 1 grouped convolution on an NHWC bf16 tensor X[B,H,W,C] (pixel pitch
  *   ldx) as an im2col-free implicit GEMM; replaces key_embed.0 = nn.Conv2d(dim, dim, 3, padding=1, groups=4)

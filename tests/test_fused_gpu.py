@@ -234,3 +234,34 @@ def test_pool3x3s2(dtype, C, H, W, mode):
     assert y.shape == yr.shape and y.is_contiguous(memory_format=torch.channels_last)
     assert (y.float() - yr).abs().max().item() <= tol * max(1.0, yr.abs().max().item())
     assert (gx.float() - gxr).abs().max().item() <= tol * max(1.0, gxr.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,H,B", [(64, 14, 5), (512, 7, 17), (96, 8, 3)])
+def test_cot_tail_eval_kernel_path(dtype, C, H, B):
+    """Inference tail (tail_pool -> cotb200_se_eval -> tail_combine, no autograd) against the autograd-capable path (PyTorch
+    SE MLP) and against the plain formula of models/cotnet.py:89-104."""
+    import torch.nn as nn
+    from cotnet_b200 import fused
+    g = torch.Generator(device="cuda").manual_seed(C + B)
+    A = max(C // 2, 32)
+    bn = nn.BatchNorm2d(C).cuda()
+    se = nn.Sequential(nn.Conv2d(C, A, 1), nn.BatchNorm2d(A), nn.ReLU(inplace=True), nn.Conv2d(A, 2 * C, 1)).cuda()
+    with torch.no_grad():
+        for m in (bn, se[1]):
+            m.weight.uniform_(0.5, 1.5, generator=g); m.bias.normal_(0, 0.3, generator=g)
+            m.running_mean.normal_(0, 0.3, generator=g); m.running_var.uniform_(0.5, 2.0, generator=g)
+    bn.eval(); se.eval()
+    u = torch.randn(B, C, H, H, generator=g, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    k = torch.relu(torch.randn(B, C, H, H, generator=g, device="cuda")).to(dtype).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        got = fused.cot_tail(u, k, bn, se)                       # kernel path (grad disabled, eval)
+        y = torch.nn.functional.silu(bn(u.float()))
+        gap = (y + k.float()).mean((2, 3), keepdim=True)
+        a = torch.softmax(se(gap).view(B, C, 2), dim=2)
+        want = y * a[:, :, 0].reshape(B, C, 1, 1) + k.float() * a[:, :, 1].reshape(B, C, 1, 1)
+    with torch.enable_grad():
+        ref2 = fused.cot_tail(u.clone().requires_grad_(True), k, bn, se)     # autograd path (PyTorch MLP)
+    tol = 1e-4 if dtype == torch.float32 else 1.5e-2
+    assert torch.allclose(got.float(), want, atol=tol, rtol=tol), (got.float() - want).abs().max().item()
+    assert torch.allclose(got.float(), ref2.float(), atol=tol, rtol=tol)
