@@ -24,7 +24,7 @@ namespace cotb200 {
 
 static constexpr int TC_BM = 128;      // UMMA M (cta_group::1)
 static constexpr int TC_BK = 64;       // 64 bf16 = 128 B = one swizzle atom
-static constexpr int TC_STAGES = 4;
+static constexpr int TC_STAGES = 6;
 static constexpr int TC_THREADS = 192;
 
 struct TcParams {
@@ -192,9 +192,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     }
   } else {
     // ===================== epilogue (4 warps, TMEM lane quadrant = warp % 4) =====================
-    // TMEM -> registers -> (scale/shift/ReLU, bf16) -> 128B-swizzled smem tile -> ONE TMA store per 64-column slab.
-    // (The first version stored 16 B per thread straight to global: rows are ldd*2 bytes apart, so every warp-wide store
-    //  touched 32 lines and the epilogue, not HBM, set the pace -- profiles/r01_tma_tc_ncu_v2.md.)
+    // TMEM -> registers -> (scale/shift/ReLU, bf16) -> 128B-swizzled smem SLAB of 64 columns -> one TMA store per slab.
+    // Two slab buffers alternate, so the store of slab i overlaps the conversion of slab i+1 and the staging area is 32 KB
+    // whatever the N tile (the first version staged the whole tile: 64 KB at N = 256 left room for two pipeline stages only and
+    // one CTA per SM -- profiles/r02_bench_conv_callC.json: 329 us for the stage-1 conv3 against cuDNN's 81).
+    // BatchNorm statistics are taken from the staged bf16 slab (what the normalisation will read back), one column pair per
+    // thread with the mixed-precision FMA -- the register butterfly of the first version cost 4 x 100 instructions per slab.
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const int et = threadIdx.x - 64;                     // 0..127 among the epilogue threads
@@ -202,6 +205,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     const uint32_t out_base = smem_u32(out_tile);
     const int nslab = (p.bn + 63) / 64;
     int ti = 0, last_n0 = -1;
+    uint32_t slab_ctr = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int tile_m = tile % p.m_tiles, n0 = (tile / p.m_tiles) * p.bn;
       int b0, h0, rows_valid; long long m0;
@@ -217,90 +221,109 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         }
         last_n0 = n0;
       }
-      // the previous tile's TMA store must have finished READING the smem tile before it is overwritten
-      if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(smem_u32(&s_tfull[acc]), use & 1);
       __syncwarp();
       tc_fence_after();
-      for (int c = 0; c * 32 < p.bn; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn + c * 32), raw);
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (stats && p.rows_per_sample > 0) {
-          // per-sample column sums (GroupNorm over the 9 taps x H x W of one sample, models/cotnet.py:56): a warp's 32 rows
-          // touch at most two samples (rows_per_sample >= 32 is checked on the host); one butterfly per sample, straight to global
-          const long long row0 = m0 + quad * 32;
-          const int s_lo = (int)(row0 / p.rows_per_sample);
-          const int rb = (int)min((long long)32, (long long)(s_lo + 1) * p.rows_per_sample - row0);   // first row of sample s_lo + 1
-          const bool col_ok = n0 + c * 32 + lane < p.N;
+      for (int sl = 0; sl < nslab; ++sl, ++slab_ctr) {
+        const uint32_t buf = out_base + (slab_ctr & 1u) * (uint32_t)(TC_BM * 128);
+        // the store that read this buffer two slabs ago must have finished READING it (at most the latest group may be pending)
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            if (half == 1 && rb >= 32) break;                                  // warp-uniform
-            float a[32], b[32];
-            const bool mine = row_ok && ((lane < rb) == (half == 0));
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = sl * 2 + cc;
+          if (c * 32 >= p.bn) break;
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn + c * 32), raw);
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { a[j] = mine ? v[j] : 0.f; b[j] = a[j] * a[j]; }
-            const float cs = warp_colsum32(a);
-            const float cq = warp_colsum32(b);
-            const long long srow = (long long)(s_lo + half) * p.N + n0 + c * 32 + lane;
-            if (col_ok && (row0 + (half ? rb : 0)) < p.M) {
-              atomicAdd(p.col_sum + srow, cs);
-              atomicAdd(p.col_sqsum + srow, cq);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (stats && p.rows_per_sample > 0) {
+            // per-sample column sums (GroupNorm over the 9 taps x H x W of one sample, models/cotnet.py:56): a warp's 32 rows
+            // touch at most two samples (rows_per_sample >= 32 is checked on the host); one butterfly per sample, straight to global
+            const long long row0 = m0 + quad * 32;
+            const int s_lo = (int)(row0 / p.rows_per_sample);
+            const int rb = (int)min((long long)32, (long long)(s_lo + 1) * p.rows_per_sample - row0);   // first row of sample s_lo + 1
+            const bool col_ok = n0 + c * 32 + lane < p.N;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              if (half == 1 && rb >= 32) break;                                  // warp-uniform
+              float a[32], b[32];
+              const bool mine = row_ok && ((lane < rb) == (half == 0));
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { a[j] = mine ? v[j] : 0.f; b[j] = a[j] * a[j]; }
+              const float cs = warp_colsum32(a);
+              const float cq = warp_colsum32(b);
+              const long long srow = (long long)(s_lo + half) * p.N + n0 + c * 32 + lane;
+              if (col_ok && (row0 + (half ? rb : 0)) < p.M) {
+                atomicAdd(p.col_sum + srow, cs);
+                atomicAdd(p.col_sqsum + srow, cq);
+              }
             }
           }
-        } else if (stats) {
-          float a[32], b[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { a[j] = row_ok ? v[j] : 0.f; b[j] = a[j] * a[j]; }
-          const float cs = warp_colsum32(a);
-          const float cq = warp_colsum32(b);
-          atomicAdd(&s_sum[c * 32 + lane], cs);
-          atomicAdd(&s_sq[c * 32 + lane], cq);
-        }
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const int col = c * 32 + j8 * 8;               // column inside the N tile
+            if (col < p.bn) {
+              const float4 sc0 = *reinterpret_cast<const float4*>(&s_scale[col]), sc1 = *reinterpret_cast<const float4*>(&s_scale[col + 4]);
+              const float4 sh0 = *reinterpret_cast<const float4*>(&s_shift[col]), sh1 = *reinterpret_cast<const float4*>(&s_shift[col + 4]);
+              const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+              const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+              uint32_t pk[4];
 #pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          const int col = c * 32 + j8 * 8;               // column inside the N tile
-          if (col < p.bn) {
-            const float4 sc0 = *reinterpret_cast<const float4*>(&s_scale[col]), sc1 = *reinterpret_cast<const float4*>(&s_scale[col + 4]);
-            const float4 sh0 = *reinterpret_cast<const float4*>(&s_shift[col]), sh1 = *reinterpret_cast<const float4*>(&s_shift[col + 4]);
-            const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-            const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float lo = fmaf(v[j8 * 8 + 2 * e], scv[2 * e], shv[2 * e]);
-              float hi = fmaf(v[j8 * 8 + 2 * e + 1], scv[2 * e + 1], shv[2 * e + 1]);
-              if (p.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+              for (int e = 0; e < 4; ++e) {
+                float lo = fmaf(v[j8 * 8 + 2 * e], scv[2 * e], shv[2 * e]);
+                float hi = fmaf(v[j8 * 8 + 2 * e + 1], scv[2 * e + 1], shv[2 * e + 1]);
+                if (p.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              const int chunk = cc * 4 + j8;               // 16-byte chunk inside the 128-byte slab row
+              const uint32_t dst = buf + (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
             }
-            const int slab = col >> 6, chunk = (col & 63) >> 3;
-            const uint32_t dst = out_base + (uint32_t)(slab * (TC_BM * 128) + r * 128 + ((chunk ^ (r & 7)) << 4));
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
           }
         }
-      }
-      // accumulator buffer drained: hand it back to the MMA issuer
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tempty[acc])) : "memory");
-      // make the generic-proxy smem writes visible to the async proxy, then one thread issues the bulk tensor stores
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et == 0) {
-        for (int sl = 0; sl < nslab; ++sl) {
+        if (sl == nslab - 1) {                             // accumulator buffer drained: hand it back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tempty[acc])) : "memory");
+        }
+        // make the generic-proxy smem writes visible to the async proxy, then one thread issues the bulk tensor store
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
           if (n0 + sl * 64 < p.N)
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(&mapD), "r"(out_base + (uint32_t)(sl * (TC_BM * 128))), "r"(n0 + sl * 64), "r"((int)m0) : "memory");
+                         ::"l"(&mapD), "r"(buf), "r"(n0 + sl * 64), "r"((int)m0) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (stats && p.rows_per_sample == 0) {
+          // column sums of the staged slab: thread = (column pair tp, row group rg of 32 rows); a warp reads one whole 128-byte
+          // row per step (conflict-free under the swizzle); bf16 operands go straight into the FMA
+          const int tp = et & 31, rg = et >> 5;
+          if (sl * 64 + 2 * tp < p.bn) {
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            const __nv_bfloat16 one = one_of<__nv_bfloat16>();
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              const int row = rg * 32 + rr;
+              if (row < rows_valid && (m0 + row) < p.M) {
+                uint32_t w2;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(buf + (uint32_t)(row * 128 + (((tp >> 2) ^ (row & 7)) << 4) + (tp & 3) * 4)));
+                const __nv_bfloat16 lo = __ushort_as_bfloat16((unsigned short)(w2 & 0xFFFFu)), hi = __ushort_as_bfloat16((unsigned short)(w2 >> 16));
+                s0 = mfma<__nv_bfloat16>(lo, one, s0); q0 = mfma<__nv_bfloat16>(lo, lo, q0);
+                s1 = mfma<__nv_bfloat16>(hi, one, s1); q1 = mfma<__nv_bfloat16>(hi, hi, q1);
+              }
+            }
+            atomicAdd(&s_sum[sl * 64 + 2 * tp], s0); atomicAdd(&s_sq[sl * 64 + 2 * tp], q0);
+            atomicAdd(&s_sum[sl * 64 + 2 * tp + 1], s1); atomicAdd(&s_sq[sl * 64 + 2 * tp + 1], q1);
+          }
+        }
       }
       if (stats && p.rows_per_sample == 0) {
-        const int t = et;
-        for (int j = t; j < p.bn; j += 128) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // every thread's shared-memory partials are in
+        for (int j = et; j < p.bn; j += 128) {
           if (n0 + j < p.N) {
             atomicAdd(p.col_sum + n0 + j, s_sum[j]);
             atomicAdd(p.col_sqsum + n0 + j, s_sq[j]);
@@ -374,12 +397,20 @@ static int tc_launch(const CUtensorMap& a1, const CUtensorMap& b1, const CUtenso
   CUtensorMap dmap;
   int rcd = make_map_2d(&dmap, p.D, p.M, p.N, p.ldd, p.rows_per_tile);
   if (rcd) return rcd;
-  const int out_bytes = ((p.bn + 63) / 64) * TC_BM * 128;
+  const int out_bytes = 2 * TC_BM * 128;                  // two 64-column slab buffers
   const int a_bytes = TC_BM * TC_BK * 2, b_bytes = p.bn * TC_BK * 2;
   const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
   p.m_tiles = m_tiles;
-  p.stages = TC_STAGES;
-  while (p.stages > 2 && p.stages * stage_bytes + out_bytes > 104 * 1024) --p.stages;     // two CTAs per SM when possible
+  // two CTAs per SM (two epilogue teams, two MMA issuers) when at least 3 stages fit next to each other and the two pairs of
+  // accumulator buffers fit the 512 TMEM columns; else one CTA with as many stages as the ring supports
+  int per_sm = 2;
+  p.stages = (104 * 1024 - out_bytes) / stage_bytes;
+  if (p.stages < 3 || 2 * p.bn > 256) {
+    per_sm = 1;
+    p.stages = (200 * 1024 - out_bytes) / stage_bytes;
+  }
+  if (p.stages > TC_STAGES) p.stages = TC_STAGES;
+  if (p.stages < 2) p.stages = 2;
   const int smem = p.stages * stage_bytes + out_bytes + 1024;
   static PerDevFlag configured_d;
   if (bool& configured = configured_d.get(); !configured) {
@@ -388,7 +419,7 @@ static int tc_launch(const CUtensorMap& a1, const CUtensorMap& b1, const CUtenso
     configured = true;
   }
   const int total = m_tiles * ((p.N + p.bn - 1) / p.bn);
-  int grid = 2 * num_sms();
+  int grid = per_sm * num_sms();                          // resident CTAs only: a second wave would start from a cold pipeline
   if (grid > total) grid = total;
   COTB200_PROF_B(what, alg_bytes);
   tc_gemm_kernel<<<grid, TC_THREADS, smem, st>>>(a1, b1, a2, b2, dmap, p);

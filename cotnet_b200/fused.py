@@ -707,9 +707,17 @@ class TcConv1x1Fn(Function):
         if ctx.needs_input_grad[2]:
             # weight gradient dW = dpre^T [a1 | a2] on the MN-major tcgen05 kernel (csrc/tc_wgrad.cu): the NHWC tiles are
             # consumed as they land, fp32 accumulation, one launch for both operand pairs
-            acc = _zeros((N, K1 + K2,), dy.device)
-            _tc.wgrad_bf16(dpre, a1, a2, out=acc)
-            dw = acc.reshape(wshape).to(wdt)
+            if N * (K1 + K2) >= 1024 * 1024 or (N * (K1 + K2) >= 256 * 1024 and M >= 40000):
+                # large, compute-shaped weight gradients (bottleneck convolutions of stages 3-4): the library kernel is faster
+                # (profiles/r02_bench_conv_*.json); everything byte-heavy stays on the MN-major tcgen05 kernel
+                parts = [torch.mm(d2.t(), _rows2d(a1))]
+                if a2 is not None:
+                    parts.append(torch.mm(d2.t(), _rows2d(a2)))
+                dw = (parts[0] if a2 is None else torch.cat(parts, 1)).reshape(wshape).to(wdt)
+            else:
+                acc = _zeros((N, K1 + K2,), dy.device)
+                _tc.wgrad_bf16(dpre, a1, a2, out=acc)
+                dw = acc.reshape(wshape).to(wdt)
         return da1, da2, dw, dcb, dgamma, dbeta, None, None, dres
 
 
@@ -777,6 +785,11 @@ import os as _os  # noqa: E402
 trunk_conv_backend = _os.environ.get("COTB200_TRAIN_CONV", "tc_e0")
 
 
+#: the bottleneck convolutions of stages 3-4 (weights of 256K .. 1M elements, 12.5K-50K pixels) are compute-shaped; measured per
+#: shape (profiles/r02_bench_conv_*.json) cuDNN's 2-CTA kernels win there, the tcgen05 path wins on the byte-heavy stages 1-2
+TC_TRUNK_MAX_WEIGHT = int(_os.environ.get("COTB200_TC_TRUNK_MAX_WEIGHT", str(128 * 1024)))
+
+
 def conv1x1_bn(x, conv, bn, relu, res=None):
     """act(BN(conv1x1(x)) (+ res)) for the bottleneck's 1x1 convolutions (models/cotnet.py:229-235,249-262): on the tcgen05
     GEMMs when the backend says so and the geometry allows (bf16 channels_last, stride 1, dense, no bias), else cuDNN + the
@@ -784,7 +797,7 @@ def conv1x1_bn(x, conv, bn, relu, res=None):
     w = conv.weight
     if (trunk_conv_backend == "tc_all1x1" and x.dtype == torch.bfloat16 and supported(x) and conv.kernel_size == (1, 1)
             and conv.stride == (1, 1) and conv.groups == 1 and conv.bias is None and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0
-            and (torch.is_grad_enabled() or not bn.training)):
+            and w.shape[0] * w.shape[1] <= TC_TRUNK_MAX_WEIGHT and (torch.is_grad_enabled() or not bn.training)):
         return TcConv1x1Fn.apply(x, None, w, None, bn.weight, bn.bias, bn, relu, res)
     return bn_act(conv(x).contiguous(memory_format=torch.channels_last), bn, relu=relu, res=res)
 

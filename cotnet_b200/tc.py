@@ -69,8 +69,14 @@ def wgrad_bf16(dy, a1, a2=None, out=None):
     K = K1 + K2
     if out is None:
         out = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
-    assert out.shape == (N, K) and out.dtype == torch.float32 and out.stride(1) == 1
+    assert out.shape == (N, K) and out.dtype == torch.float32 and out.stride(1) == 1 and out.data_ptr() % 16 == 0
     lib = _lib.load()
+    if a2 is not None and K1 % 64:
+        # the two-source form takes 64-channel boxes from a1 then a2: an a1 that does not end on a box boundary (CoXt, C = 96 ...)
+        # runs as two single-source launches into the two column ranges of `out`
+        wgrad_bf16(dy, a1, None, out=out[:, :K1])
+        wgrad_bf16(dy, a2, None, out=out[:, K1:])
+        return out
     # orientation: rows of the MMA tile (128 per CTA) from dy or from the input -- whichever needs fewer tiles
     t0 = ((N + 127) // 128) * ((K + 255) // 256)
     t1 = ((K + 127) // 128) * ((N + 255) // 256)

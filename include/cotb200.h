@@ -230,8 +230,9 @@ int cotb200_pool3s2_bwd(int dtype, int mode, int N, int H, int W, int C, const v
  *   Replaces the 1x1 nn.Conv2d launches of the block (cuDNN in the reference): embed.0 on cat[x,k] without the
  *   concat (models/cotnet.py:52,81), embed.3 (:55), conv1x1.0 (:60) -- rows are NHWC pixels.
  *   epi(acc)[m,n] = relu?( acc*scale[n] + shift[n] )  (scale/shift NULL = 1/0: folded eval-mode BatchNorm or bias);
- *   col_sum/col_sqsum (both or neither): += sum_m acc[m,n], sum_m acc[m,n]^2 of the RAW accumulator
- *   (training-mode BatchNorm batch statistics, models/cotnet.py:45,53,61).
+ *   col_sum/col_sqsum (both or neither): += sum_m D[m,n], sum_m D[m,n]^2 of the STORED bf16 output (with scale/shift NULL
+ *   and relu 0 that is the raw product: the training-mode BatchNorm batch statistics of the convolution output,
+ *   models/cotnet.py:45,53,61 -- taken from the staged output tile, exactly the values the normalisation reads back).
  *   Requirements: N, K1, K2, ldd multiples of 8; operands 16-byte aligned. */
 int cotb200_gemm_bf16(int M, int N, int K1, const void* A1, long long lda1, const void* B1, long long ldb1,
                       int K2, const void* A2, long long lda2, const void* B2, long long ldb2,
