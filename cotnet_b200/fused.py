@@ -569,6 +569,41 @@ def group_norm9_from_colsums(l, gn: torch.nn.GroupNorm, gc, csum, csq, lbias_in_
     return out
 
 
+def cot_eval_tail_fused(v, l2d, csum, csq, lbias_p, gamma_p, beta_p, eps, gc, bn_ss, k, se):
+    """Inference tail of the CoT block from the logits GEMM on: coefficient kernel (GroupNorm statistics -> per-(sample, column)
+    affine), the fused LocalConv kernel (GroupNorm affine + aggregation + bn + SiLU + pooled (y + k)), the SE kernel, and the
+    recombination -- 4 launches for models/cotnet.py:85-104.  v, k: channels_last [B,C,H,W]; l2d: [B*H*W, 9C/8] tap-major logits
+    (bias included) with per-sample column sums csum / csq of the pre-bias accumulator.  Returns None when the fused kernel cannot
+    take the geometry (the caller then uses the separate kernels)."""
+    B, C, H, W = v.shape
+    wc = C // 8
+    lib, st, dt = _lib.load(), _lib.stream_ptr(v), _lib.dtype_code(v)
+    coef = torch.empty(B, 9 * wc, 2, dtype=torch.float32, device=v.device)
+    _lib.check(lib.cotb200_gn9_coef_from_colsums(B, H * W, wc, gc, csum.data_ptr(), csq.data_ptr(), lbias_p.data_ptr(), gamma_p.data_ptr(),
+                                                 beta_p.data_ptr(), float(eps), coef.data_ptr(), st), "gn9_coef_from_colsums")
+    d = _lib.AggDesc()
+    d.n, d.c, d.h, d.w = B, C, H, W
+    d.heads, d.wc = 1, wc
+    d.kh = d.kw = 3
+    d.sh = d.sw = d.ph = d.pw = d.dh = d.dw = 1
+    d.ho, d.wo = H, W
+    d.dtype, d.layout, d.gc, d.fold = dt, _lib.NHWC_TAP, gc, 1
+    y = torch.empty_like(v, memory_format=torch.channels_last)
+    psum = torch.zeros(B, C, dtype=torch.float32, device=v.device)
+    rc = lib.cotb200_cot_agg_eval(d, v.data_ptr(), l2d.data_ptr(), coef.data_ptr(), bn_ss[0].data_ptr(), bn_ss[1].data_ptr(), k.data_ptr(),
+                                  y.data_ptr(), psum.data_ptr(), st)
+    if rc == -7:                                   # COTB200_EUNSUPPORTED
+        return None
+    _lib.check(rc, "cot_agg_eval")
+    w0, b0, s1, t1, w3, b3 = _se_eval_params(se)
+    a = torch.empty(B, C, 2, dtype=torch.float32, device=v.device)
+    _lib.check(lib.cotb200_se_eval(B, C, w0.shape[0], psum.data_ptr(), 1.0 / (H * W), w0.data_ptr(), _lib.ptr(b0), s1.data_ptr(),
+                                   t1.data_ptr(), w3.data_ptr(), _lib.ptr(b3), a.data_ptr(), st), "se_eval")
+    out = torch.empty_like(v, memory_format=torch.channels_last)
+    _lib.check(lib.cotb200_mix2(dt, B, H * W, C, y.data_ptr(), k.data_ptr(), a.data_ptr(), out.data_ptr(), st), "mix2")
+    return out
+
+
 def cot_tail(u, k, bn: torch.nn.BatchNorm2d, se: torch.nn.Module):
     if (not torch.is_grad_enabled() and not bn.training and not se[1].training and k is not None and se[1].running_mean is not None
             and bn.running_mean is not None and isinstance(se[2], torch.nn.ReLU)):
