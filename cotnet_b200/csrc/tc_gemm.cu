@@ -100,7 +100,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
   uint8_t* out_tile = smem + (size_t)p.stages * stage_bytes;      // [bn/64 slabs][128 rows][128 B], 128B-swizzled
   __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_tfull[2], s_tempty[2];
   __shared__ uint32_t s_tmem;
-  __shared__ float s_sum[256], s_sq[256];
+  __shared__ float s_sum[4][256], s_sq[4][256];            // per row-group partials of the tile's column statistics
   __shared__ __align__(16) float s_scale[256], s_shift[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -122,7 +122,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 256; i += TC_THREADS) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+  for (int i = threadIdx.x; i < 4 * 256; i += TC_THREADS) { (&s_sum[0][0])[i] = 0.f; (&s_sq[0][0])[i] = 0.f; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -133,7 +133,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     if (lane == 0) {
       int kbc = 0;                                      // k-block counter, continuous across tiles
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int tile_m = tile % p.m_tiles, n0 = (tile / p.m_tiles) * p.bn;
+        const int tile_m = tile / n_tiles, n0 = (tile % n_tiles) * p.bn;      // N tiles of one row tile are neighbours: its A tile stays in L2
         int b0, h0, rows_valid; long long m0;
         tc_tile_origin(p, tile_m, b0, h0, m0, rows_valid);
         for (int kb = 0; kb < nkb; ++kb, ++kbc) {
@@ -207,7 +207,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     int ti = 0, last_n0 = -1;
     uint32_t slab_ctr = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-      const int tile_m = tile % p.m_tiles, n0 = (tile / p.m_tiles) * p.bn;
+      const int tile_m = tile / n_tiles, n0 = (tile % n_tiles) * p.bn;
       int b0, h0, rows_valid; long long m0;
       tc_tile_origin(p, tile_m, b0, h0, m0, rows_valid);
       const int acc = ti & 1;
@@ -305,19 +305,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
           if (sl * 64 + 2 * tp < p.bn) {
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
             const __nv_bfloat16 one = one_of<__nv_bfloat16>();
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
+            const int nrow = min(32, min(rows_valid, (int)min((long long)TC_BM, p.M - m0)) - rg * 32);      // valid rows of this row group
+            uint32_t w2[32];
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {               // all loads first (independent), then the arithmetic
               const int row = rg * 32 + rr;
-              if (row < rows_valid && (m0 + row) < p.M) {
-                uint32_t w2;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(buf + (uint32_t)(row * 128 + (((tp >> 2) ^ (row & 7)) << 4) + (tp & 3) * 4)));
-                const __nv_bfloat16 lo = __ushort_as_bfloat16((unsigned short)(w2 & 0xFFFFu)), hi = __ushort_as_bfloat16((unsigned short)(w2 >> 16));
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2[rr]) : "r"(buf + (uint32_t)(row * 128 + (((tp >> 2) ^ (row & 7)) << 4) + (tp & 3) * 4)));
+            }
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              if (rr < nrow) {
+                const __nv_bfloat16 lo = __ushort_as_bfloat16((unsigned short)(w2[rr] & 0xFFFFu)), hi = __ushort_as_bfloat16((unsigned short)(w2[rr] >> 16));
                 s0 = mfma<__nv_bfloat16>(lo, one, s0); q0 = mfma<__nv_bfloat16>(lo, lo, q0);
                 s1 = mfma<__nv_bfloat16>(hi, one, s1); q1 = mfma<__nv_bfloat16>(hi, hi, q1);
               }
             }
-            atomicAdd(&s_sum[sl * 64 + 2 * tp], s0); atomicAdd(&s_sq[sl * 64 + 2 * tp], q0);
-            atomicAdd(&s_sum[sl * 64 + 2 * tp + 1], s1); atomicAdd(&s_sq[sl * 64 + 2 * tp + 1], q1);
+            // one owner per (row group, column): plain stores, no atomics; every column of the tile is written once per tile
+            s_sum[rg][sl * 64 + 2 * tp] = s0; s_sq[rg][sl * 64 + 2 * tp] = q0;
+            s_sum[rg][sl * 64 + 2 * tp + 1] = s1; s_sq[rg][sl * 64 + 2 * tp + 1] = q1;
           }
         }
       }
@@ -325,10 +330,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         asm volatile("bar.sync 1, 128;" ::: "memory");      // every thread's shared-memory partials are in
         for (int j = et; j < p.bn; j += 128) {
           if (n0 + j < p.N) {
-            atomicAdd(p.col_sum + n0 + j, s_sum[j]);
-            atomicAdd(p.col_sqsum + n0 + j, s_sq[j]);
+            atomicAdd(p.col_sum + n0 + j, (s_sum[0][j] + s_sum[1][j]) + (s_sum[2][j] + s_sum[3][j]));
+            atomicAdd(p.col_sqsum + n0 + j, (s_sq[0][j] + s_sq[1][j]) + (s_sq[2][j] + s_sq[3][j]));
           }
-          s_sum[j] = 0.f; s_sq[j] = 0.f;
         }
       }
     }
@@ -405,7 +409,7 @@ static int tc_launch(const CUtensorMap& a1, const CUtensorMap& b1, const CUtenso
   // accumulator buffers fit the 512 TMEM columns; else one CTA with as many stages as the ring supports
   int per_sm = 2;
   p.stages = (104 * 1024 - out_bytes) / stage_bytes;
-  if (p.stages < 3 || 2 * p.bn > 256) {
+  if (p.stages < 2 || 2 * p.bn > 256) {
     per_sm = 1;
     p.stages = (200 * 1024 - out_bytes) / stage_bytes;
   }
@@ -426,7 +430,19 @@ static int tc_launch(const CUtensorMap& a1, const CUtensorMap& b1, const CUtenso
   return check_launch(what);
 }
 
-static int pick_bn(int N) {
+static int pick_bn_wide(int N);
+static int pick_bn(int N, int K = 1 << 30) {
+  // short contractions (K <= 128) with a wide output are epilogue-bound: TMEM drains at 64 B/clk per SM, so a 256-column tile
+  // needs > 1 us just to leave TMEM while its operands arrived in a fraction of that.  Two CTAs per SM with 128-column tiles
+  // run two epilogues side by side (the re-read A tile is small and comes from L2).
+  if (K <= 128 && N > 128) {
+    const int parts = (N + 127) / 128;
+    const int bn = (((N + parts - 1) / parts) + 63) & ~63;
+    return bn > 128 ? 128 : bn;
+  }
+  return pick_bn_wide(N);
+}
+static int pick_bn_wide(int N) {
   // One N tile when N fits a single UMMA (<= 256): bn = N rounded up to 16, columns beyond N are clipped by the TMA store.
   // Several N tiles: bn must be a multiple of 64 so that every 64-column store slab lies inside its own tile.
   if (N <= 256) return (N + 15) & ~15;
@@ -450,7 +466,7 @@ extern "C" int cotb200_gemm_bf16(int M, int N, int K1, const void* A1, long long
   if ((col_sum == nullptr) != (col_sqsum == nullptr)) { set_error("gemm_bf16: col_sum and col_sqsum go together"); return COTB200_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
   TcParams p{};
-  p.M = M; p.N = N; p.rows_per_tile = TC_BM; p.bn = pick_bn(N); p.mode = 0;
+  p.M = M; p.N = N; p.rows_per_tile = TC_BM; p.bn = pick_bn(N, K1 + K2); p.mode = 0;
   p.kb1 = (K1 + TC_BK - 1) / TC_BK; p.kb2 = (K2 + TC_BK - 1) / TC_BK;
   p.relu = relu; p.ldd = ldd; p.D = (__nv_bfloat16*)D; p.scale = scale; p.shift = shift; p.col_sum = col_sum; p.col_sqsum = col_sqsum;
   CUtensorMap a1, b1, a2, b2;
