@@ -42,16 +42,16 @@ def _keep_format(out, like):
 
 def _dense_from_grouped(w, groups):
     """[N, K/groups, kh, kw] weight of a grouped convolution -> the block-diagonal dense weight [N, K, kh, kw] of the same
-    convolution (exact zeros outside the blocks).  Differentiable: the gradient of the grouped parameter is the blocks of the
-    dense weight gradient."""
+    convolution (exact zeros outside the blocks).  Differentiable (one index_put; its backward is one gather): the gradient of
+    the grouped parameter is the blocks of the dense weight gradient."""
     if groups == 1:
         return w
     N, kg = w.shape[0], w.shape[1]
-    ng = N // groups
-    out = w.new_zeros((N, kg * groups) + tuple(w.shape[2:]))
-    for g in range(groups):
-        out[g * ng:(g + 1) * ng, g * kg:(g + 1) * kg] = w[g * ng:(g + 1) * ng]
-    return out
+    ng, rest = N // groups, tuple(w.shape[2:])
+    dense = w.new_zeros((groups, ng, groups, kg) + rest)
+    idx = torch.arange(groups, device=w.device)
+    dense[idx, :, idx] = w.reshape((groups, ng, kg) + rest)             # (idx, :, idx) -> [groups, ng, kg, ...]
+    return dense.reshape((N, groups * kg) + rest)
 
 
 def _coxt_embed0_dense(w, groups):
@@ -60,13 +60,13 @@ def _coxt_embed0_dense(w, groups):
     weights with  embed.0(qk) == x @ Wx^T + k @ Wk^T  -- the operand pairs of the concat-free GEMM."""
     N, kg = w.shape[0], w.shape[1]                 # kg = 2C / groups
     ng, ch = N // groups, kg // 2
-    w2 = w.reshape(N, kg)
-    wx = w.new_zeros((N, ch * groups))
-    wk = w.new_zeros((N, ch * groups))
-    for g in range(groups):
-        wx[g * ng:(g + 1) * ng, g * ch:(g + 1) * ch] = w2[g * ng:(g + 1) * ng, 0::2]
-        wk[g * ng:(g + 1) * ng, g * ch:(g + 1) * ch] = w2[g * ng:(g + 1) * ng, 1::2]
-    return wx, wk
+    w2 = w.reshape(groups, ng, ch, 2)
+    idx = torch.arange(groups, device=w.device)
+    wx = w.new_zeros((groups, ng, groups, ch))
+    wk = w.new_zeros((groups, ng, groups, ch))
+    wx[idx, :, idx] = w2[..., 0]
+    wk[idx, :, idx] = w2[..., 1]
+    return wx.reshape(N, groups * ch), wk.reshape(N, groups * ch)
 
 
 class CotLayer(nn.Module):
