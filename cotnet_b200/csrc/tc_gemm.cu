@@ -418,7 +418,7 @@ static int tc_launch(const CUtensorMap& a1, const CUtensorMap& b1, const CUtenso
   const int smem = p.stages * stage_bytes + out_bytes + 1024;
   static PerDevFlag configured_d;
   if (bool& configured = configured_d.get(); !configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
