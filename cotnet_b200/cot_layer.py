@@ -199,7 +199,7 @@ class CotLayer(nn.Module):
             # affine applied inside the LocalConv kernel, which also does bn + SiLU and the pooled descriptor
             l, cs, cq = tc.gemm_bf16_samplestats(e, p["we2p"], H * W, shift=p["be2p"])
             v = tc.gemm_bf16(x, p["wv"], scale=p["v_ss"][0], shift=p["v_ss"][1])
-            out = fused.cot_eval_tail_fused(v.view(B, H, W, C).permute(0, 3, 1, 2), l, cs, cq, p["be2p"], p["gnw_p"], p["gnb_p"],
+            out = fused.cot_eval_tail_fused(v.view(B, H, W, C).permute(0, 3, 1, 2), l, cs, cq, None, p["gnw_p"], p["gnb_p"],
                                             float(self.embed[4].eps), gc, p["bn_ss"], k, self.se)
             if out is not None:
                 return out
@@ -207,7 +207,7 @@ class CotLayer(nn.Module):
             l, cs, cq = tc.gemm_bf16_samplestats(e, p["we2"], H * W, shift=p["be2"])
             v = tc.gemm_bf16(x, p["wv"], scale=p["v_ss"][0], shift=p["v_ss"][1])
             J = l.shape[1]
-            w = fused.group_norm9_from_colsums(l.view(B, H, W, J).permute(0, 3, 1, 2), self.embed[4], gc, cs, cq, p["be2"])
+            w = fused.group_norm9_from_colsums(l.view(B, H, W, J).permute(0, 3, 1, 2), self.embed[4], gc, cs, cq, None)
         else:
             l = tc.gemm_bf16(e, p["we2"], shift=p["be2"])
             v = tc.gemm_bf16(x, p["wv"], scale=p["v_ss"][0], shift=p["v_ss"][1])

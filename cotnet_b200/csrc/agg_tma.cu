@@ -339,6 +339,13 @@ agg3_eval_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         for (int j = ct; j < p.J; j += nct) s_coef[j] = __ldg(q.coef + (long long)n * p.J + j);
         last_n = n;
       }
+      // k of this thread's pixels: issued now, consumed in the epilogue -- the global-load latency hides behind the TMA wait,
+      // the prologue and the tap loop (loading it at the point of use exposed ~1 us per item)
+      const T* kt = kg + n * p.y_sn + (long long)h0 * p.W * p.y_sp;
+      Pack<T, VEC> kpre[MAXI];
+#pragma unroll
+      for (int kk = 0; kk < MAXI; ++kk)
+        if (i_hl[kk] >= 0 && h0 + i_hl[kk] < p.H) kpre[kk] = ld_pack<T, VEC>(kt + i_ob[kk]);
       mbar_wait(smem_u32(&s_full[s]), ph);
       const uint32_t xs = smem_base + (uint32_t)(s * p.stage_bytes);
       const uint32_t ws = xs + (uint32_t)(p.slabs * p.slab_bytes);
@@ -358,7 +365,6 @@ agg3_eval_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
       }
       asm volatile("bar.sync 2, %0;" ::"r"(nct) : "memory");
       T* yt = y + n * p.y_sn + (long long)h0 * p.W * p.y_sp;
-      const T* kt = kg + n * p.y_sn + (long long)h0 * p.W * p.y_sp;
       float pacc[VEC];
 #pragma unroll
       for (int i = 0; i < VEC; ++i) pacc[i] = 0.f;
@@ -378,7 +384,7 @@ agg3_eval_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
 #pragma unroll
           for (int i = 0; i < VEC; ++i) acc[i] = mfma<T>(wv.v[i], xv.v[i], acc[i]);
         }
-        const Pack<T, VEC> kv = ld_pack<T, VEC>(kt + i_ob[kk]);
+        const Pack<T, VEC> kv = kpre[kk];
         Pack<T, VEC> o;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {

@@ -251,7 +251,7 @@ extern "C" int cotb200_u8_to_nhwc(int dtype, int N, int C, int H, int W, const v
 // The eager form is ~10 launches of GEMV-sized ops per CoT layer; here one kernel, SE_S samples per CTA so that the two
 // weight matrices are read once per SE_S samples.  fp32 throughout ([B, C] inputs are tiny).
 namespace cotb200 {
-static constexpr int SE_S = 8;
+static constexpr int SE_S = 2;      // samples per CTA: B/2 CTAs fill the machine (8 per CTA left 32 CTAs with long serial loops: 128 us)
 __global__ void __launch_bounds__(256)
 se_eval_kernel(const float* __restrict__ psum, float inv_hw, const float* __restrict__ W0, const float* __restrict__ b0,
                const float* __restrict__ s1, const float* __restrict__ t1, const float* __restrict__ W3, const float* __restrict__ b3,

@@ -238,29 +238,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if (stats && p.rows_per_sample > 0) {
-            // per-sample column sums (GroupNorm over the 9 taps x H x W of one sample, models/cotnet.py:56): a warp's 32 rows
-            // touch at most two samples (rows_per_sample >= 32 is checked on the host); one butterfly per sample, straight to global
-            const long long row0 = m0 + quad * 32;
-            const int s_lo = (int)(row0 / p.rows_per_sample);
-            const int rb = (int)min((long long)32, (long long)(s_lo + 1) * p.rows_per_sample - row0);   // first row of sample s_lo + 1
-            const bool col_ok = n0 + c * 32 + lane < p.N;
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-              if (half == 1 && rb >= 32) break;                                  // warp-uniform
-              float a[32], b[32];
-              const bool mine = row_ok && ((lane < rb) == (half == 0));
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { a[j] = mine ? v[j] : 0.f; b[j] = a[j] * a[j]; }
-              const float cs = warp_colsum32(a);
-              const float cq = warp_colsum32(b);
-              const long long srow = (long long)(s_lo + half) * p.N + n0 + c * 32 + lane;
-              if (col_ok && (row0 + (half ? rb : 0)) < p.M) {
-                atomicAdd(p.col_sum + srow, cs);
-                atomicAdd(p.col_sqsum + srow, cq);
-              }
-            }
-          }
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             const int col = c * 32 + j8 * 8;               // column inside the N tile
@@ -297,6 +274,46 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                          ::"l"(&mapD), "r"(buf), "r"(n0 + sl * 64), "r"((int)m0) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (stats && p.rows_per_sample > 0) {
+          // PER-SAMPLE column sums of the staged slab (GroupNorm over the 9 taps x H x W of one sample, models/cotnet.py:56): a row
+          // group of 32 rows touches at most two samples (rows_per_sample >= 32 is checked on the host); two partial sets per
+          // thread, straight to the [sample, column] tables
+          const int tp = et & 31, rg = et >> 5;
+          if (sl * 64 + 2 * tp < p.bn && n0 + sl * 64 + 2 * tp < p.N) {
+            const long long row0 = m0 + rg * 32;
+            const int s_lo = (int)(row0 / p.rows_per_sample);
+            const int rb = (int)min((long long)32, (long long)(s_lo + 1) * p.rows_per_sample - row0);   // rows [0, rb) belong to sample s_lo
+            const int nrow = min(32, min(rows_valid, (int)min((long long)TC_BM, p.M - m0)) - rg * 32);
+            const __nv_bfloat16 one = one_of<__nv_bfloat16>();
+            float sa[2] = {0.f, 0.f}, qa[2] = {0.f, 0.f}, sb[2] = {0.f, 0.f}, qb[2] = {0.f, 0.f};
+            uint32_t w2[32];
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              const int row = rg * 32 + rr;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2[rr]) : "r"(buf + (uint32_t)(row * 128 + (((tp >> 2) ^ (row & 7)) << 4) + (tp & 3) * 4)));
+            }
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              if (rr < nrow) {
+                const __nv_bfloat16 lo = __ushort_as_bfloat16((unsigned short)(w2[rr] & 0xFFFFu)), hi = __ushort_as_bfloat16((unsigned short)(w2[rr] >> 16));
+                const int h = rr < rb ? 0 : 1;
+                if (h == 0) { sa[0] = mfma<__nv_bfloat16>(lo, one, sa[0]); qa[0] = mfma<__nv_bfloat16>(lo, lo, qa[0]);
+                              sb[0] = mfma<__nv_bfloat16>(hi, one, sb[0]); qb[0] = mfma<__nv_bfloat16>(hi, hi, qb[0]); }
+                else        { sa[1] = mfma<__nv_bfloat16>(lo, one, sa[1]); qa[1] = mfma<__nv_bfloat16>(lo, lo, qa[1]);
+                              sb[1] = mfma<__nv_bfloat16>(hi, one, sb[1]); qb[1] = mfma<__nv_bfloat16>(hi, hi, qb[1]); }
+              }
+            }
+            const int col = n0 + sl * 64 + 2 * tp;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if ((h == 0 && nrow > 0) || (h == 1 && nrow > rb)) {
+                const long long srow = (long long)(s_lo + h) * p.N + col;
+                atomicAdd(p.col_sum + srow, sa[h]); atomicAdd(p.col_sqsum + srow, qa[h]);
+                if (col + 1 < p.N) { atomicAdd(p.col_sum + srow + 1, sb[h]); atomicAdd(p.col_sqsum + srow + 1, qb[h]); }
+              }
+            }
+          }
         }
         if (stats && p.rows_per_sample == 0) {
           // column sums of the staged slab: thread = (column pair tp, row group rg of 32 rows); a warp reads one whole 128-byte

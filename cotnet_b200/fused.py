@@ -555,7 +555,8 @@ def _cot_tail_eval(u, k, bn, se):
 def group_norm9_from_colsums(l, gn: torch.nn.GroupNorm, gc, csum, csq, lbias_in_stats):
     """Inference GroupNorm(9 taps) whose statistics come from the logits GEMM's epilogue (per-sample column sums of the raw
     accumulator, cotb200_gemm_bf16_samplestats): one tiny kernel turns them into mean / rstd, then the apply kernel.  `l` already
-    contains the embed.3 bias; `lbias_in_stats` is that bias (it was NOT in the accumulator the sums were taken from)."""
+    contains the embed.3 bias and so do the sums (they are taken from the stored logits): `lbias_in_stats` is None unless the
+    sums come from somewhere that has not seen the bias."""
     B, J, H, W = l.shape
     wc = J // 9
     lib, st, dt = _lib.load(), _lib.stream_ptr(l), _lib.dtype_code(l)
@@ -579,7 +580,7 @@ def cot_eval_tail_fused(v, l2d, csum, csq, lbias_p, gamma_p, beta_p, eps, gc, bn
     wc = C // 8
     lib, st, dt = _lib.load(), _lib.stream_ptr(v), _lib.dtype_code(v)
     coef = torch.empty(B, 9 * wc, 2, dtype=torch.float32, device=v.device)
-    _lib.check(lib.cotb200_gn9_coef_from_colsums(B, H * W, wc, gc, csum.data_ptr(), csq.data_ptr(), lbias_p.data_ptr(), gamma_p.data_ptr(),
+    _lib.check(lib.cotb200_gn9_coef_from_colsums(B, H * W, wc, gc, csum.data_ptr(), csq.data_ptr(), _lib.ptr(lbias_p), gamma_p.data_ptr(),
                                                  beta_p.data_ptr(), float(eps), coef.data_ptr(), st), "gn9_coef_from_colsums")
     d = _lib.AggDesc()
     d.n, d.c, d.h, d.w = B, C, H, W

@@ -256,14 +256,16 @@ int cotb200_gemm_bf16(int M, int N, int K1, const void* A1, long long lda1, cons
                       float* col_sum, float* col_sqsum, void* stream);
 
 /* cotb200_gemm_bf16_samplestats: the single-product GEMM above whose statistics epilogue accumulates PER SAMPLE:
- *   samp_sum / samp_sqsum [M / rows_per_sample, N] += column sums / sums of squares of the RAW accumulator over the
- *   rows_per_sample consecutive rows (= H*W pixels) of each sample.  With cotb200_gn9_from_colsums this gives the GroupNorm
- *   statistics of the attention logits (models/cotnet.py:55-56) without a pass over them.  rows_per_sample >= 32, M % it == 0. */
+ *   samp_sum / samp_sqsum [M / rows_per_sample, N] += column sums / sums of squares of the STORED output (scale / shift
+ *   applied, bf16-rounded) over the rows_per_sample consecutive rows (= H*W pixels) of each sample.  With
+ *   cotb200_gn9_from_colsums (bias = NULL: it is already in the stored logits) this gives the GroupNorm statistics of the
+ *   attention logits (models/cotnet.py:55-56) without a pass over them.  rows_per_sample >= 32, M % it == 0. */
 int cotb200_gemm_bf16_samplestats(int M, int N, int K1, const void* A1, long long lda1, const void* B1, long long ldb1,
                                   void* D, long long ldd, const float* scale, const float* shift, int relu,
                                   int rows_per_sample, float* samp_sum, float* samp_sqsum, void* stream);
-/* mean[b,g], rstd[b,g] of GroupNorm(wc groups of 9 taps) from per-sample column sums csum / csq [B, 9*wc] of the logits
- * BEFORE the bias (bias [9*wc] or NULL is accounted for analytically); column order given by gc like cotb200_gn9_apply. */
+/* mean[b,g], rstd[b,g] of GroupNorm(wc groups of 9 taps) from per-sample column sums csum / csq [B, 9*wc] of the logits.
+ * bias [9*wc]: a bias that is NOT yet contained in the summed values is accounted for analytically (NULL when the sums were
+ * taken over the final logits); column order given by gc like cotb200_gn9_apply. */
 int cotb200_gn9_from_colsums(int B, int HW, int wc, int gc, const float* csum, const float* csq, const float* bias,
                              float eps, float* mean, float* rstd, void* stream);
 /* Same statistics, returned as the per-(sample, column) affine of the normalisation: coef[b, j] = (rstd*gamma_j,

@@ -91,6 +91,49 @@ def main():
         print(json.dumps(rec), flush=True)
         del x, w, dy, y, dx, dw, xo, wo, yo, xb, wb, db, yb
         torch.cuda.empty_cache()
+    # ---- the mix op and the three cupy_layers variants at the shapes their cubins were built for
+    def t2(fn):
+        def g():
+            flush.zero_()
+            fn()
+        return timeit(g, a.iters) - timeit(lambda: flush.zero_(), a.iters)
+
+    e, x, w1, w2, dy = rk.make_inputs("mix_s1_b32", "float", op="mix")
+    rec = {"tag": "mix_s1_b32", "op": "aggregation_zeropad_mix", "shape": [e["N"], e["C"], e["H"], e["W"]]}
+    y = torch.empty(e["N"], 2 * e["C"], e["H"], e["W"], device="cuda")
+    ef = rk.entry("aggregation_zeropad_mix_forward_kernel", "mix_s1_b32", "float")
+    rec["ref_fp32_fwd_us"] = t2(lambda: rk.launch(ef, x, w1, w2, y))
+    rec["ref_fp32_bwd_us"] = t2(lambda: rk.mix_backward("mix_s1_b32", dy, x, w1, w2))
+    xo, w1o, w2o = [t_.clone().requires_grad_(True) for t_ in (x, w1, w2)]
+    rec["ours_fp32_fwd_us"] = t2(lambda: cotnet_b200.aggregation_zeropad_mix(x, w1, w2, 3, 5, 1, 1, 2, 1))
+    yo = cotnet_b200.aggregation_zeropad_mix(xo, w1o, w2o, 3, 5, 1, 1, 2, 1)
+    rec["ours_fp32_bwd_us"] = t2(lambda: torch.autograd.grad(yo, (xo, w1o, w2o), dy, retain_graph=True))
+    rec["speedup_fwd"] = rec["ref_fp32_fwd_us"] / rec["ours_fp32_fwd_us"]
+    rec["speedup_bwd"] = rec["ref_fp32_bwd_us"] / rec["ours_fp32_bwd_us"]
+    rows.append({k: (round(v, 3) if isinstance(v, float) else v) for k, v in rec.items()})
+    print(json.dumps(rows[-1]), flush=True)
+    for op, tag, fwd, bwd, ours in (
+            ("refpad", "refpad_s2_b8", rk.refpad_forward, rk.refpad_backward,
+             lambda x_, w_, *r: cotnet_b200.aggregation_refpad(x_, w_, 3, 1, 1, 1)),
+            ("dilate", "dilate_s2_b8", rk.dilate_forward, rk.dilate_backward,
+             lambda x_, w_, dil: cotnet_b200.aggregation_zeropad_dilate(x_, w_, dil, 3, 1)),
+            ("merge", "merge_s1_b8", rk.merge_forward, rk.merge_backward,
+             lambda x_, w_, e_: cotnet_b200.aggregation_zeropad_mix_merge(x_, w_, e_["heads"], e_["wc"], 3, 5, 1, 1, 2, 1))):
+        inp = rk.make_variant_inputs(tag, "float", op)
+        e, x, w = inp[0], inp[1], inp[2]
+        dy = inp[-1]
+        extra = (inp[3],) if op == "dilate" else ((e,) if op == "merge" else ())
+        rec = {"tag": tag, "op": op}
+        rec["ref_fp32_fwd_us"] = t2(lambda: fwd(tag, x, w, *(extra if op == "dilate" else ())))
+        rec["ref_fp32_bwd_us"] = t2(lambda: bwd(tag, dy, x, w, *(extra if op == "dilate" else ())))
+        xo, wo = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        rec["ours_fp32_fwd_us"] = t2(lambda: ours(x, w, *extra))
+        yo = ours(xo, wo, *extra)
+        rec["ours_fp32_bwd_us"] = t2(lambda: torch.autograd.grad(yo, (xo, wo), dy, retain_graph=True))
+        rec["speedup_fwd"] = rec["ref_fp32_fwd_us"] / rec["ours_fp32_fwd_us"]
+        rec["speedup_bwd"] = rec["ref_fp32_bwd_us"] / rec["ours_fp32_bwd_us"]
+        rows.append({k: (round(v, 3) if isinstance(v, float) else v) for k, v in rec.items()})
+        print(json.dumps(rows[-1]), flush=True)
     if a.json:
         json.dump(rows, open(a.json, "w"), indent=1)
 
