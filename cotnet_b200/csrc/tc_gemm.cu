@@ -100,7 +100,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
   uint8_t* out_tile = smem + (size_t)p.stages * stage_bytes;      // [bn/64 slabs][128 rows][128 B], 128B-swizzled
   __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_tfull[2], s_tempty[2];
   __shared__ uint32_t s_tmem;
-  __shared__ float s_sum[4][256], s_sq[4][256];            // per row-group partials of the tile's column statistics
+  // per row-group partials of the tile's column statistics: [4][256] floats each, in DYNAMIC shared memory behind the two slab
+  // buffers and only when statistics are requested (static tables would cost every launch its second resident CTA)
+  float (*s_sum)[256] = reinterpret_cast<float (*)[256]>(out_tile + 2 * TC_BM * 128);
+  float (*s_sq)[256] = s_sum + 4;
   __shared__ __align__(16) float s_scale[256], s_shift[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -122,7 +125,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 4 * 256; i += TC_THREADS) { (&s_sum[0][0])[i] = 0.f; (&s_sq[0][0])[i] = 0.f; }
+  if (p.col_sum != nullptr && p.rows_per_sample == 0)
+    for (int i = threadIdx.x; i < 4 * 256; i += TC_THREADS) { (&s_sum[0][0])[i] = 0.f; (&s_sq[0][0])[i] = 0.f; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -418,7 +422,7 @@ static int tc_launch(const CUtensorMap& a1, const CUtensorMap& b1, const CUtenso
   CUtensorMap dmap;
   int rcd = make_map_2d(&dmap, p.D, p.M, p.N, p.ldd, p.rows_per_tile);
   if (rcd) return rcd;
-  const int out_bytes = 2 * TC_BM * 128;                  // two 64-column slab buffers
+  const int out_bytes = 2 * TC_BM * 128 + ((p.col_sum && p.rows_per_sample == 0) ? 2 * 4 * 256 * 4 : 0);   // two slab buffers (+ statistics partials)
   const int a_bytes = TC_BM * TC_BK * 2, b_bytes = p.bn * TC_BK * 2;
   const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
   p.m_tiles = m_tiles;
