@@ -336,7 +336,8 @@ agg3_eval_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
       const int par = it & 1;
       if (n != last_n) {                                        // (a, c) of this sample -> shared memory
         asm volatile("bar.sync 2, %0;" ::"r"(nct) : "memory");  // nobody still reads the previous sample's table
-        for (int j = ct; j < p.J; j += nct) s_coef[j] = __ldg(q.coef + (long long)n * p.J + j);
+        // stored element-major, [VEC][JP]: the prologue's lanes walk jp, so lane-consecutive float2 reads are conflict-free
+        for (int j = ct; j < p.J; j += nct) s_coef[(j % VEC) * JP + j / VEC] = __ldg(q.coef + (long long)n * p.J + j);
         last_n = n;
       }
       // k of this thread's pixels: issued now, consumed in the epilogue -- the global-load latency hides behind the TMA wait,
@@ -357,7 +358,7 @@ agg3_eval_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         Pack<T, VEC> lv = lds_pack<T, VEC>(addr);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-          const float2 ac = s_coef[jp * VEC + i];
+          const float2 ac = s_coef[i * JP + jp];
           lv.v[i] = Elem<T>::from(fmaf(to_acc(lv.v[i]), ac.x, ac.y));
         }
         const uint4 u = *reinterpret_cast<const uint4*>(&lv);
@@ -386,9 +387,15 @@ agg3_eval_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         }
         const Pack<T, VEC> kv = kpre[kk];
         Pack<T, VEC> o;
+        float bsc[VEC], bsh[VEC];                               // folded BatchNorm of the channel packet: 128-bit shared loads
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4) {
+          *reinterpret_cast<float4*>(&bsc[i]) = *reinterpret_cast<const float4*>(&s_ss[0][i_c0[kk] + i]);
+          *reinterpret_cast<float4*>(&bsh[i]) = *reinterpret_cast<const float4*>(&s_ss[1][i_c0[kk] + i]);
+        }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-          const float z = fmaf(acc[i], s_ss[0][i_c0[kk] + i], s_ss[1][i_c0[kk] + i]);
+          const float z = fmaf(acc[i], bsc[i], bsh[i]);
           float sg;
           if constexpr (sizeof(T) == 2) { float th; asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * z)); sg = fmaf(0.5f, th, 0.5f); }
           else sg = __fdividef(1.f, 1.f + __expf(-z));

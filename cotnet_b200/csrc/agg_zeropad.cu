@@ -190,7 +190,7 @@ __global__ void agg_dw_generic(const T* __restrict__ dy, const T* __restrict__ x
 template <typename T, int K>
 __global__ void __launch_bounds__(256)
 agg_fwd_nchw_fast(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ y, int N, int C, int H, int W,
-                  int wc, int rep, long long y_sn, int total) {
+                  int wc, int rep, long long y_sn, long long w_sn, int total) {
   constexpr int R = K / 2, K2 = K * K;
   const int HW = H * W;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -199,7 +199,7 @@ agg_fwd_nchw_fast(const T* __restrict__ x, const T* __restrict__ w, T* __restric
     const int n = idx / (HW * wc);
     const int h = p / W, wq = p - h * W;
     float wt[K2];
-    const T* wp = w + ((long long)(n * wc + gch) * K2) * HW + p;
+    const T* wp = w + n * w_sn + ((long long)gch * K2) * HW + p;
 #pragma unroll
     for (int t = 0; t < K2; ++t) {
       const int dh = t / K - R, dw = t % K - R;
@@ -276,7 +276,7 @@ agg_mix_fwd_nchw_fast(const T* __restrict__ x, const T* __restrict__ w1, const T
 template <typename T, int K, bool DX, bool DW, bool ACC_DX>
 __global__ void __launch_bounds__(256)
 agg_bwd_nchw_fast(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ dx,
-                  T* __restrict__ dw, int N, int C, int H, int W, int wc, int rep, long long dy_sn, int total) {
+                  T* __restrict__ dw, int N, int C, int H, int W, int wc, int rep, long long dy_sn, long long w_sn, int total) {
   constexpr int R = K / 2, K2 = K * K;
   const int HW = H * W;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -286,7 +286,7 @@ agg_bwd_nchw_fast(const T* __restrict__ dy, const T* __restrict__ x, const T* __
     const int h = p / W, wq = p - h * W;
     float ws[K2];   // DX: w at the shifted (output) positions p - off_t
     float gw[K2];   // DW accumulators
-    const T* wp = w + ((long long)(n * wc + gch) * K2) * HW + p;
+    const T* wp = w + n * w_sn + ((long long)gch * K2) * HW + p;
 #pragma unroll
     for (int t = 0; t < K2; ++t) {
       const int dh = t / K - R, dw_ = t % K - R;
@@ -326,7 +326,7 @@ agg_bwd_nchw_fast(const T* __restrict__ dy, const T* __restrict__ x, const T* __
       xp += (long long)wc * HW; dp += (long long)wc * HW; dxp += (long long)wc * HW;
     }
     if (DW) {
-      T* dwp = dw + ((long long)(n * wc + gch) * K2) * HW + p;
+      T* dwp = dw + n * w_sn + ((long long)gch * K2) * HW + p;
 #pragma unroll
       for (int t = 0; t < K2; ++t) dwp[(long long)t * HW] = Elem<T>::from(gw[t]);
     }
@@ -581,9 +581,9 @@ static int fwd_impl(const Geo& g, const T* x, const T* w, T* y, cudaStream_t st)
     if (agg_tma_fwd<T>(nhwc2_args(g), x, w, y, st, &rc2)) return rc2;     // persistent TMA-pipelined kernel (TAP layout)
     if (nhwc2_fwd<T>(nhwc2_args(g), x, w, y, st, &rc2)) return rc2;
   }
-  if (g.layout == COTB200_NCHW && nofold(g) && fits32(g) && is_same3(g, 3)) {
+  if (g.layout == COTB200_NCHW && nofold(g) && fits32(g) && is_same3(g, 3) && g.w_sn == (long long)g.wc * 9 * g.H * g.W) {
     int rc2 = 0;
-    if (g.x_sn == (long long)g.C * g.H * g.W && g.w_sn == (long long)g.wc * 9 * g.H * g.W &&
+    if (g.x_sn == (long long)g.C * g.H * g.W &&
         nchw_tma_launch<T>(0, g.N, g.C, g.H, g.W, g.wc, g.x_sn, 0, g.y_sn, x, w, y, st, &rc2)) return rc2;
     if (nchw2_fwd<T>(g.N, g.C, g.H, g.W, g.wc, g.y_sn, x, w, y, st, &rc2)) return rc2;
   }
@@ -592,8 +592,8 @@ static int fwd_impl(const Geo& g, const T* x, const T* w, T* y, cudaStream_t st)
       const int total = g.N * g.wc * g.H * g.W;
       const int grid = grid_for(total, 256);
       COTB200_PROF_B(g.KH == 3 ? "agg_fwd_nchw_k3" : "agg_fwd_nchw_k5", ((double)g.N * g.C * g.H * g.W + (double)g.N * g.heads * g.wc * g.K2 * g.HO * g.WO + (double)g.N * g.heads * g.C * g.HO * g.WO) * sizeof(T));
-      if (g.KH == 3) agg_fwd_nchw_fast<T, 3><<<grid, 256, 0, st>>>(x, w, y, g.N, g.C, g.H, g.W, g.wc, g.rep, g.y_sn, total);
-      else agg_fwd_nchw_fast<T, 5><<<grid, 256, 0, st>>>(x, w, y, g.N, g.C, g.H, g.W, g.wc, g.rep, g.y_sn, total);
+      if (g.KH == 3) agg_fwd_nchw_fast<T, 3><<<grid, 256, 0, st>>>(x, w, y, g.N, g.C, g.H, g.W, g.wc, g.rep, g.y_sn, g.w_sn, total);
+      else agg_fwd_nchw_fast<T, 5><<<grid, 256, 0, st>>>(x, w, y, g.N, g.C, g.H, g.W, g.wc, g.rep, g.y_sn, g.w_sn, total);
       return check_launch("agg_fwd_nchw_fast");
     }
   }
@@ -628,7 +628,7 @@ static int fwd_impl(const Geo& g, const T* x, const T* w, T* y, cudaStream_t st)
 template <typename T>
 static int bwd_impl(const Geo& g, const T* dy, const T* x, const T* w, T* dx, T* dw, bool acc_dx, cudaStream_t st) {
   if (!dx && !dw) return 0;
-  if (g.layout == COTB200_NCHW && nofold(g) && fits32(g) && is_same3(g, 3) && !acc_dx) {
+  if (g.layout == COTB200_NCHW && nofold(g) && fits32(g) && is_same3(g, 3) && !acc_dx && g.w_sn == (long long)g.wc * 9 * g.H * g.W) {
     int rc2 = 0;
     if (g.x_sn == (long long)g.C * g.H * g.W && g.w_sn == (long long)g.wc * 9 * g.H * g.W) {
       // TMA-pipelined kernels, one per gradient; if only one of the two is eligible the register kernel does the other
@@ -648,7 +648,7 @@ static int bwd_impl(const Geo& g, const T* dy, const T* x, const T* w, T* dx, T*
       COTB200_PROF_B(dx && dw ? "agg_bwd_nchw_dxdw" : (dx ? "agg_bwd_nchw_dx" : "agg_bwd_nchw_dw"), (dx && dw ? 1.0 : 0.0) * ((double)g.N * g.C * g.H * g.W + (double)g.N * g.wc * g.K2 * g.HO * g.WO) * sizeof(T) + ((double)g.N * g.C * g.H * g.W + (double)g.N * g.heads * g.wc * g.K2 * g.HO * g.WO + (double)g.N * g.heads * g.C * g.HO * g.WO) * sizeof(T));
 #define COTB200_LAUNCH_BWD(K, DX, DW, ACC)                                                                          \
   agg_bwd_nchw_fast<T, K, DX, DW, ACC><<<grid, 256, 0, st>>>(dy, x, w, dx, dw, g.N, g.C, g.H, g.W, g.wc, g.rep,      \
-                                                            g.y_sn, total)
+                                                            g.y_sn, g.w_sn, total)
       if (g.KH == 3) {
         if (dx && dw) { if (acc_dx) COTB200_LAUNCH_BWD(3, true, true, true); else COTB200_LAUNCH_BWD(3, true, true, false); }
         else if (dx) { if (acc_dx) COTB200_LAUNCH_BWD(3, true, false, true); else COTB200_LAUNCH_BWD(3, true, false, false); }
@@ -803,6 +803,13 @@ extern "C" int cotb200_agg_zeropad_mix_bwd(const cotb200_agg_desc* d, int k2h, i
   cudaStream_t st = (cudaStream_t)stream;
   const long long half = (long long)g1.heads * g1.C * g1.HO * g1.WO;
   COTB200_DISPATCH_DTYPE(d->dtype, {
+    if (sizeof(T) >= 4 && is_same3(g1, 3) && is_same3(g2, 5) && fits32(g2)) {
+      // fp32 / fp64 storage: the second kernel can accumulate into dX exactly, so both halves run on the register-resident
+      // fused dX + dW kernels (the generic path below is kept for 16-bit storage, where dX must be summed before rounding)
+      rc = bwd_impl<T>(g1, (const T*)dy, (const T*)x, (const T*)w1, (T*)dx, (T*)dw1, false, st);
+      if (rc) return rc;
+      return bwd_impl<T>(g2, (const T*)dy + half, (const T*)x, (const T*)w2, (T*)dx, (T*)dw2, dx != nullptr, st);
+    }
     if (dx) {   // both halves of dX in one fp32-accumulating pass
       const long long total = (long long)g1.N * g1.C * g1.H * g1.W;
       COTB200_PROF("agg_mix_dx");
@@ -840,13 +847,11 @@ extern "C" int cotb200_agg_zeropad_mix_merge_fwd(const cotb200_agg_desc* d, int 
   merge_strides(g1, g2, off2);
   const long long half = (long long)g1.heads * g1.C * g1.HO * g1.WO;
   const long long total = (long long)g1.N * half;
+  (void)total;
   COTB200_DISPATCH_DTYPE(d->dtype, {
-    COTB200_PROF("agg_mix_merge_fwd");
-    agg_fwd_generic<T><<<grid_for(total, 256, 16), 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, g1, total);
-    rc = check_launch("agg_mix_merge_fwd");
+    rc = fwd_impl<T>(g1, (const T*)x, (const T*)w, (T*)y, st);                  // register-resident kernels when 3x3 / 5x5 same-pad, heads 1
     if (rc) return rc;
-    agg_fwd_generic<T><<<grid_for(total, 256, 16), 256, 0, st>>>((const T*)x, (const T*)w + off2, (T*)y + half, g2, total);
-    return check_launch("agg_mix_merge_fwd");
+    return fwd_impl<T>(g2, (const T*)x, (const T*)w + off2, (T*)y + half, st);
   });
   return 0;
 }
@@ -862,6 +867,11 @@ extern "C" int cotb200_agg_zeropad_mix_merge_bwd(const cotb200_agg_desc* d, int 
   merge_strides(g1, g2, off2);
   const long long half = (long long)g1.heads * g1.C * g1.HO * g1.WO;
   COTB200_DISPATCH_DTYPE(d->dtype, {
+    if (sizeof(T) >= 4 && is_same3(g1, 3) && is_same3(g2, 5) && fits32(g2)) {
+      rc = bwd_impl<T>(g1, (const T*)dy, (const T*)x, (const T*)w, (T*)dx, (T*)dw, false, st);
+      if (rc) return rc;
+      return bwd_impl<T>(g2, (const T*)dy + half, (const T*)x, (const T*)w + off2, (T*)dx, dw ? (T*)dw + off2 : (T*)nullptr, dx != nullptr, st);
+    }
     if (dx) {
       const long long total = (long long)g1.N * g1.C * g1.H * g1.W;
       COTB200_PROF("agg_mix_merge_dx");
