@@ -212,6 +212,84 @@ __global__ void dilate_dw_kernel(const T* __restrict__ dy, const T* __restrict__
   }
 }
 
+// Register-resident forwards (the common small-footprint cases): one thread per (n, head, weight channel, output pixel) keeps
+// the K*K weights and the K*K input offsets in registers and walks the C / wc input channels that share them, so a weight is
+// read once instead of C / wc times and the index arithmetic is paid once per pixel (32-bit throughout; host checks the sizes).
+template <typename T, int K>
+__global__ void __launch_bounds__(256)
+refpad_fwd_fast(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ y, VGeo g, int total) {
+  using Acc = typename Elem<T>::Acc;
+  constexpr int K2 = K * K;
+  const int plane = g.HO * g.WO, iplane = g.H * g.W;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int p = idx % plane;
+    int r = idx / plane;
+    const int gch = r % g.wc; r /= g.wc;
+    const int head = r % g.heads;
+    const int n = r / g.heads;
+    const int ho = p / g.WO, wo = p - ho * g.WO;
+    Acc wt[K2];
+    int off[K2];
+    const T* wp = w + ((long long)((n * g.heads + head) * g.wc + gch) * K2) * plane + p;
+#pragma unroll
+    for (int kh = 0; kh < K; ++kh) {
+      const int hi = reflect_idx(-g.PH + ho * g.SH + kh * g.DH, g.H);
+#pragma unroll
+      for (int kw = 0; kw < K; ++kw) {
+        const int wi = reflect_idx(-g.PW + wo * g.SW + kw * g.DW, g.W);
+        wt[kh * K + kw] = to_acc(wp[(long long)(kh * K + kw) * plane]);
+        off[kh * K + kw] = hi * g.W + wi;
+      }
+    }
+    const T* xp = x + (long long)(n * g.C + gch) * iplane;
+    T* yp = y + (long long)((n * g.heads + head) * g.C + gch) * plane + p;
+    for (int rr = 0; rr < g.rep; ++rr) {
+      Acc acc = 0;
+#pragma unroll
+      for (int t = 0; t < K2; ++t) acc += wt[t] * to_acc(xp[off[t]]);
+      *yp = Elem<T>::from(acc);
+      xp += (long long)g.wc * iplane;
+      yp += (long long)g.wc * plane;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dilate_fwd_fast(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ dil, T* __restrict__ y, VGeo g, int total) {
+  using Acc = typename Elem<T>::Acc;
+  const int plane = g.H * g.W;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int p = idx % plane;
+    int r = idx / plane;
+    const int gch = r % g.wc; r /= g.wc;
+    const int head = r % g.heads;
+    const int n = r / g.heads;
+    const int h = p / g.W, wq = p - h * g.W;
+    const int d = (int)to_acc(dil[gch]);
+    Acc wt[9];
+    int off[9];
+    const T* wp = w + ((long long)((n * g.heads + head) * g.wc + gch) * 9) * plane + p;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int hi = h + (t / 3 - 1) * d, wi = wq + (t % 3 - 1) * d;
+      const bool ok = hi >= 0 && hi < g.H && wi >= 0 && wi < g.W;
+      wt[t] = ok ? to_acc(wp[(long long)t * plane]) : Acc(0);
+      off[t] = ok ? hi * g.W + wi : -1;                            // an out-of-range tap is skipped (never multiplied)
+    }
+    const T* xp = x + (long long)(n * g.C + gch) * plane;
+    T* yp = y + (long long)((n * g.heads + head) * g.C + gch) * plane + p;
+    for (int rr = 0; rr < g.rep; ++rr) {
+      Acc acc = 0;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) if (off[t] >= 0) acc += wt[t] * to_acc(xp[off[t]]);
+      *yp = Elem<T>::from(acc);
+      xp += (long long)g.wc * plane;
+      yp += (long long)g.wc * plane;
+    }
+  }
+}
+
 static int vgrid(long long total) {
   long long need = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
@@ -256,7 +334,15 @@ extern "C" int cotb200_agg_refpad_fwd(const cotb200_agg_desc* d, const void* x, 
   const long long total = (long long)g.N * g.heads * g.C * g.HO * g.WO;
   COTB200_DISPATCH_DTYPE(d->dtype, {
     COTB200_PROF_B("agg_refpad_fwd", ((double)g.N * g.C * g.H * g.W + (double)g.N * g.heads * (g.wc * g.K2 + g.C) * g.HO * g.WO) * sizeof(T));
-    refpad_fwd_kernel<T><<<vgrid(total), 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, g, total);
+    const long long items = total / g.rep;
+    const bool small = total < (1LL << 31) && (long long)g.N * g.heads * g.wc * g.K2 * g.HO * g.WO < (1LL << 31) && g.H * g.W < (1 << 24);
+    if (small && g.KH == g.KW && (g.KH == 3 || g.KH == 5 || g.KH == 7)) {
+      if (g.KH == 3) refpad_fwd_fast<T, 3><<<vgrid(items), 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, g, (int)items);
+      else if (g.KH == 5) refpad_fwd_fast<T, 5><<<vgrid(items), 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, g, (int)items);
+      else refpad_fwd_fast<T, 7><<<vgrid(items), 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, g, (int)items);
+    } else {
+      refpad_fwd_kernel<T><<<vgrid(total), 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, g, total);
+    }
     return check_launch("agg_refpad_fwd");
   });
   return 0;
@@ -298,7 +384,10 @@ extern "C" int cotb200_agg_zeropad_dilate_fwd(const cotb200_agg_desc* d, const v
   const long long total = (long long)g.N * g.heads * g.C * g.H * g.W;
   COTB200_DISPATCH_DTYPE(d->dtype, {
     COTB200_PROF_B("agg_dilate_fwd", ((double)g.N * g.H * g.W) * ((double)g.C + g.heads * (g.wc * 9.0 + g.C)) * sizeof(T));
-    dilate_fwd_kernel<T><<<vgrid(total), 256, 0, st>>>((const T*)x, (const T*)w, (const T*)dilation, (T*)y, g, total);
+    if (total < (1LL << 31) && (long long)g.N * g.heads * g.wc * 9 * g.H * g.W < (1LL << 31))
+      dilate_fwd_fast<T><<<vgrid(total / g.rep), 256, 0, st>>>((const T*)x, (const T*)w, (const T*)dilation, (T*)y, g, (int)(total / g.rep));
+    else
+      dilate_fwd_kernel<T><<<vgrid(total), 256, 0, st>>>((const T*)x, (const T*)w, (const T*)dilation, (T*)y, g, total);
     return check_launch("agg_zeropad_dilate_fwd");
   });
   return 0;
