@@ -126,7 +126,12 @@ class CoTResNet(nn.Module):
 
     def forward_features(self, x):
         if fused.supported(x):
-            x = fused.max_pool3x3s2(fused.bn_act(self._stem_conv(x).contiguous(memory_format=torch.channels_last), self.bn1, relu=True))
+            if self.stem_pad == 0 and x.dtype == torch.bfloat16:
+                # conv1 + bn1 + ReLU: 7x7/s2 stem on the 4-tap tcgen05 implicit GEMM, BatchNorm statistics from its epilogue
+                # (fused.stem_conv_bn falls back to cuDNN + the fused BatchNorm kernels for geometries it does not take)
+                x = fused.max_pool3x3s2(fused.stem_conv_bn(x, self.conv1, self.bn1, relu=True))
+            else:
+                x = fused.max_pool3x3s2(fused.bn_act(self._stem_conv(x).contiguous(memory_format=torch.channels_last), self.bn1, relu=True))
         else:
             x = self.maxpool(self.act1(self.bn1(self.conv1(x))))
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))

@@ -248,86 +248,107 @@ extern "C" int cotb200_u8_to_nhwc(int dtype, int N, int C, int H, int W, const v
 // ------------------------------------------------------------------------------------------------ SE MLP of the CoT tail (eval)
 // a[b, c, 0:2] = softmax_r( W3[2c+r, :] . relu(s1 * (W0 . p[b] + b0) + t1) + b3[2c+r] ),  p[b] = psum[b] * inv_hw
 // (models/cotnet.py:69-77,92-101 with the BatchNorm of `se` folded: s1 = gamma * rstd, t1 = beta - mean * s1).
-// The eager form is ~10 launches of GEMV-sized ops per CoT layer; here one kernel, SE_S samples per CTA so that the two
-// weight matrices are read once per SE_S samples.  fp32 throughout ([B, C] inputs are tiny).
+// The eager form is ~10 launches of GEMV-sized ops per CoT layer.  Two tiny GEMMs [B, C] x [C, A] and [B, A] x [A, 2C]: the only
+// thing that matters is memory-level parallelism, so each is one launch of (16 samples x 32 outputs) tiles whose operands are
+// staged in shared memory with independent 16-byte loads (one latency round per 256-wide K chunk) -- the first version (one CTA
+// per 2 samples walking whole weight rows with dependent loads) took 63 us per layer at C = 512 (profiles/r02_prof_cotnet50_eval_callH.md).
+// fp32 throughout.
 namespace cotb200 {
-static constexpr int SE_S = 2;      // samples per CTA: B/2 CTAs fill the machine (8 per CTA left 32 CTAs with long serial loops: 128 us)
+static constexpr int SE_TS = 16;     // samples per tile
+static constexpr int SE_TJ = 32;     // outputs per tile (16 pairs)
+static constexpr int SE_KC = 256;    // K chunk staged per round
+static constexpr int SE_LD = SE_KC + 1;
+
+// EPI 0: out[s, j] = relu(s1[j] * (acc + b[j]) + t1[j])            (fc1 + folded BatchNorm + ReLU), in = psum * in_scale
+// EPI 1: out[s, c, 0:2] = softmax(acc[2c] + b[2c], acc[2c+1] + b[2c+1])   (fc2 + radix-2 softmax)
+template <int EPI>
 __global__ void __launch_bounds__(256)
-se_eval_kernel(const float* __restrict__ psum, float inv_hw, const float* __restrict__ W0, const float* __restrict__ b0,
-               const float* __restrict__ s1, const float* __restrict__ t1, const float* __restrict__ W3, const float* __restrict__ b3,
-               float* __restrict__ a, int B, int C, int A) {
-  extern __shared__ float se_sm[];                 // p [SE_S][C] | z [SE_S][A]
-  float* p = se_sm;
-  float* z = se_sm + SE_S * C;
-  const int b0i = blockIdx.x * SE_S;
-  const int ns = min(SE_S, B - b0i);
-  for (int i = threadIdx.x; i < SE_S * C; i += 256) {
-    const int s = i / C, c = i - s * C;
-    p[i] = s < ns ? psum[(long long)(b0i + s) * C + c] * inv_hw : 0.f;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < A; j += 8) {               // one warp per hidden unit: coalesced row of W0
-    float acc[SE_S];
-#pragma unroll
-    for (int s = 0; s < SE_S; ++s) acc[s] = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float w = __ldg(W0 + (long long)j * C + c);
-#pragma unroll
-      for (int s = 0; s < SE_S; ++s) acc[s] = fmaf(w, p[s * C + c], acc[s]);
-    }
-#pragma unroll
-    for (int s = 0; s < SE_S; ++s) {
-      float v = acc[s];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) z[s * A + j] = fmaxf(fmaf(v + (b0 ? __ldg(b0 + j) : 0.f), __ldg(s1 + j), __ldg(t1 + j)), 0.f);
-    }
-  }
-  __syncthreads();
-  for (int c = warp; c < C; c += 8) {               // one warp per channel: the two logits 2c, 2c+1
-    float a0[SE_S], a1[SE_S];
-#pragma unroll
-    for (int s = 0; s < SE_S; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
-    for (int j = lane; j < A; j += 32) {
-      const float w0 = __ldg(W3 + (long long)(2 * c) * A + j), w1 = __ldg(W3 + (long long)(2 * c + 1) * A + j);
-#pragma unroll
-      for (int s = 0; s < SE_S; ++s) { a0[s] = fmaf(w0, z[s * A + j], a0[s]); a1[s] = fmaf(w1, z[s * A + j], a1[s]); }
-    }
-#pragma unroll
-    for (int s = 0; s < SE_S; ++s) {
-      float u = a0[s], v = a1[s];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) { u += __shfl_xor_sync(0xffffffffu, u, o); v += __shfl_xor_sync(0xffffffffu, v, o); }
-      if (lane == 0 && s < ns) {
-        u += b3 ? __ldg(b3 + 2 * c) : 0.f; v += b3 ? __ldg(b3 + 2 * c + 1) : 0.f;
-        const float m = fmaxf(u, v), eu = __expf(u - m), ev = __expf(v - m), inv = 1.f / (eu + ev);
-        a[((long long)(b0i + s) * C + c) * 2] = eu * inv;
-        a[((long long)(b0i + s) * C + c) * 2 + 1] = ev * inv;
+se_fc_kernel(const float* __restrict__ in, float in_scale, const float* __restrict__ Wt, const float* __restrict__ b,
+             const float* __restrict__ s1, const float* __restrict__ t1, float* __restrict__ out, int B, int K, int J) {
+  extern __shared__ float se_sm[];                 // in tile [SE_TS][SE_LD] | W tile [SE_TJ][SE_LD]
+  float* is = se_sm;
+  float* ws = se_sm + SE_TS * SE_LD;
+  const int s0 = blockIdx.x * SE_TS, j0 = blockIdx.y * SE_TJ;
+  const int t = threadIdx.x;
+  const int s = t >> 4, pp = t & 15;               // sample of the tile, output pair
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int k0 = 0; k0 < K; k0 += SE_KC) {
+    const int kc = min(SE_KC, K - k0);
+    if (k0) __syncthreads();
+    // stage: rows of kc floats; 16-byte global loads when the row start allows (K % 4 == 0: always for C % 8 == 0)
+    const bool v4 = (K & 3) == 0 && (kc & 3) == 0;
+    if (v4) {
+      const int q = kc >> 2;
+      for (int i = t; i < (SE_TS + SE_TJ) * q; i += 256) {
+        const int r = i / q, c4 = (i - r * q) << 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* dst;
+        if (r < SE_TS) {
+          if (s0 + r < B) v = __ldg(reinterpret_cast<const float4*>(in + (long long)(s0 + r) * K + k0 + c4));
+          v.x *= in_scale; v.y *= in_scale; v.z *= in_scale; v.w *= in_scale;
+          dst = is + r * SE_LD + c4;
+        } else {
+          const int jr = r - SE_TS;
+          if (j0 + jr < J) v = __ldg(reinterpret_cast<const float4*>(Wt + (long long)(j0 + jr) * K + k0 + c4));
+          dst = ws + jr * SE_LD + c4;
+        }
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+      }
+    } else {
+      for (int i = t; i < (SE_TS + SE_TJ) * kc; i += 256) {
+        const int r = i / kc, c = i - r * kc;
+        if (r < SE_TS) is[r * SE_LD + c] = s0 + r < B ? __ldg(in + (long long)(s0 + r) * K + k0 + c) * in_scale : 0.f;
+        else ws[(r - SE_TS) * SE_LD + c] = j0 + r - SE_TS < J ? __ldg(Wt + (long long)(j0 + r - SE_TS) * K + k0 + c) : 0.f;
       }
     }
+    __syncthreads();
+    const float* ip = is + s * SE_LD;
+    const float* w0 = ws + (2 * pp) * SE_LD;
+    const float* w1 = w0 + SE_LD;
+#pragma unroll 8
+    for (int k = 0; k < kc; ++k) {
+      const float a = ip[k];
+      acc0 = fmaf(a, w0[k], acc0);
+      acc1 = fmaf(a, w1[k], acc1);
+    }
+  }
+  const int j = j0 + 2 * pp;
+  if (s0 + s >= B || j >= J) return;
+  if (EPI == 0) {
+    out[(long long)(s0 + s) * J + j] = fmaxf(fmaf(acc0 + (b ? __ldg(b + j) : 0.f), __ldg(s1 + j), __ldg(t1 + j)), 0.f);
+    if (j + 1 < J) out[(long long)(s0 + s) * J + j + 1] = fmaxf(fmaf(acc1 + (b ? __ldg(b + j + 1) : 0.f), __ldg(s1 + j + 1), __ldg(t1 + j + 1)), 0.f);
+  } else {
+    const float u = acc0 + (b ? __ldg(b + j) : 0.f), v = acc1 + (b ? __ldg(b + j + 1) : 0.f);
+    const float m = fmaxf(u, v), eu = __expf(u - m), ev = __expf(v - m), inv = 1.f / (eu + ev);
+    out[(long long)(s0 + s) * J + j] = eu * inv;             // [B, C, 2] with J = 2C: (c, r) at 2c + r
+    out[(long long)(s0 + s) * J + j + 1] = ev * inv;
   }
 }
 }  // namespace cotb200
 
+extern "C" long long cotb200_se_eval_scratch_bytes(int B, int A) { return (long long)B * A * 4; }
+
 extern "C" int cotb200_se_eval(int B, int C, int A, const float* psum, float inv_hw, const float* W0, const float* b0,
-                               const float* s1, const float* t1, const float* W3, const float* b3, float* a, void* stream) {
-  if (!psum || !W0 || !s1 || !t1 || !W3 || !a) { set_error("se_eval: NULL pointer"); return COTB200_ENULL; }
+                               const float* s1, const float* t1, const float* W3, const float* b3, float* a, float* z_scratch,
+                               void* stream) {
+  if (!psum || !W0 || !s1 || !t1 || !W3 || !a || !z_scratch) { set_error("se_eval: NULL pointer"); return COTB200_ENULL; }
   if (B <= 0 || C <= 0 || A <= 0) { set_error("se_eval: non-positive dims"); return COTB200_EINVAL; }
-  const size_t smem = (size_t)SE_S * (C + A) * sizeof(float);
-  if (smem > 200 * 1024) { set_error("se_eval: C=%d A=%d too large for the shared-memory staging", C, A); return COTB200_ETOOBIG; }
   cudaStream_t st = (cudaStream_t)stream;
-  if (smem > 48 * 1024) {
-    static PerDevFlag cfgd;
-    if (bool& cfg = cfgd.get(); !cfg) {
-      cudaError_t e = cudaFuncSetAttribute(se_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-      cfg = true;
-    }
+  const int smem = (SE_TS + SE_TJ) * SE_LD * (int)sizeof(float);      // 49.3 KB
+  static PerDevFlag cfgd;
+  if (bool& cfg = cfgd.get(); !cfg) {
+    cudaError_t e = cudaFuncSetAttribute(se_fc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(se_fc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    cfg = true;
   }
   COTB200_PROF("se_eval");
-  se_eval_kernel<<<(B + SE_S - 1) / SE_S, 256, smem, st>>>(psum, inv_hw, W0, b0, s1, t1, W3, b3, a, B, C, A);
-  return check_launch("se_eval");
+  dim3 g1((B + SE_TS - 1) / SE_TS, (A + SE_TJ - 1) / SE_TJ), g2((B + SE_TS - 1) / SE_TS, (2 * C + SE_TJ - 1) / SE_TJ);
+  se_fc_kernel<0><<<g1, 256, smem, st>>>(psum, inv_hw, W0, b0, s1, t1, z_scratch, B, C, A);
+  int rc = check_launch("se_eval fc1");
+  if (rc) return rc;
+  se_fc_kernel<1><<<g2, 256, smem, st>>>(z_scratch, 1.f, W3, b3, nullptr, nullptr, a, B, A, 2 * C);
+  return check_launch("se_eval fc2");
 }
 
 // ------------------------------------------------------------------------------------------------ radix-2 recombination of stored y

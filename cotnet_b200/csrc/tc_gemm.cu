@@ -6,6 +6,12 @@
 //   conv mode  : 3x3 / pad 1 / stride 1 grouped convolution as an im2col-FREE implicit GEMM: for each tap the A
 //                tile is a 4-D TMA box {64 ch, W, hbox, bbox} of the NHWC input fetched at the tap's (dh,dw) offset;
 //                TMA's out-of-bounds zero fill IS the zero padding (key_embed.0, models/cotnet.py:44).
+//   stem mode  : 7x7 / stride 2 / pad 3 convolution of a 3-channel image (models/resnet.py:552) as a 4-tap implicit GEMM over
+//                the space-to-depth copy of the input made by stem_s2d_kernel (csrc/stem.cu): P[b, i, 2 + j, (di,dj,c)] =
+//                x[b, 2i+di, 2j+dj, c], 16 channels per cell.  An output pixel's receptive field is 4 s2d rows x 4 cells x 16
+//                channels; one TMA box {64 elements, tile width, 1, 1} of a tensor map whose pixel stride (32 B) is SMALLER than
+//                its inner extent (128 B) fetches the overlapping 4-cell windows of a whole output row segment straight into the
+//                K-major A tile -- im2col done by the TMA address generator.
 //   epilogue   : per-column scale/shift (folded BatchNorm or bias), optional ReLU, bf16 store; optional per-column
 //                sum / sum-of-squares of the raw accumulator (training-mode BatchNorm statistics) reduced with a
 //                butterfly transpose-reduce in registers, one global atomic per column per CTA.
@@ -31,10 +37,11 @@ struct TcParams {
   int M, N;                 // valid rows (pixels) / output channels
   int rows_per_tile;        // D rows per CTA (128 plain; rows of the pixel box in conv mode)
   int bn;                   // N tile (multiple of 16, <= 256)
-  int mode;                 // 0 plain, 1 conv3x3
+  int mode;                 // 0 plain, 1 conv3x3, 2 stem (row-window conv)
   int kb1, kb2;             // plain: 64-wide k-blocks of operand pair 1 / 2
   int H, W, B, hbox, bbox;  // conv geometry
   int kc;                   // conv: 64-channel chunks per tap (= bn / 64)
+  int wtiles;               // stem: tiles per output row (tile width = rows_per_tile)
   int relu;
   int m_tiles;              // number of row tiles (persistent CTAs loop over m_tiles * n_tiles)
   int stages;               // smem ring depth actually used (<= TC_STAGES): short K loops take less smem -> more CTAs/SM
@@ -71,11 +78,18 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
 //   epilogue warps drain buffer i while the MMAs of tile i+1 fill the other one.
 // (The first version launched one CTA per tile: ncu showed ~5 us of fixed per-CTA cost -- barrier init, TMEM alloc,
 //  a cold TMA round trip -- dominating tiles with 1-2 k-blocks; profiles/r01_tma_tc_ncu.md.)
-__device__ __forceinline__ void tc_tile_origin(const TcParams& p, int tile_m, int& b0, int& h0, long long& m0, int& rows_valid) {
-  b0 = 0; h0 = 0;
+__device__ __forceinline__ void tc_tile_origin(const TcParams& p, int tile_m, int& b0, int& h0, int& w0, long long& m0, int& rows_valid) {
+  b0 = 0; h0 = 0; w0 = 0;
   if (p.mode == 0) {
     m0 = (long long)tile_m * TC_BM;
     rows_valid = (int)min((long long)TC_BM, (long long)p.M - m0);
+  } else if (p.mode == 2) {                       // stem: tile = (sample, output row, segment of the row); H, W = OUTPUT dims
+    const int per_b = p.H * p.wtiles;
+    b0 = tile_m / per_b;
+    const int rem = tile_m - b0 * per_b;
+    h0 = rem / p.wtiles; w0 = (rem - h0 * p.wtiles) * p.rows_per_tile;
+    m0 = ((long long)b0 * p.H + h0) * p.W + w0;
+    rows_valid = p.rows_per_tile;
   } else if (p.bbox == 1) {
     const int tps = (p.H + p.hbox - 1) / p.hbox;
     b0 = tile_m / tps; h0 = (tile_m % tps) * p.hbox;
@@ -107,7 +121,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
   __shared__ __align__(16) float s_scale[256], s_shift[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = p.mode == 0 ? p.kb1 + p.kb2 : 9 * p.kc;
+  const int nkb = p.mode == 1 ? 9 * p.kc : p.kb1 + p.kb2;
   const int n_tiles = (p.N + p.bn - 1) / p.bn;
   const int total_tiles = p.m_tiles * n_tiles;
 
@@ -138,8 +152,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       int kbc = 0;                                      // k-block counter, continuous across tiles
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int tile_m = tile / n_tiles, n0 = (tile % n_tiles) * p.bn;      // N tiles of one row tile are neighbours: its A tile stays in L2
-        int b0, h0, rows_valid; long long m0;
-        tc_tile_origin(p, tile_m, b0, h0, m0, rows_valid);
+        int b0, h0, w0, rows_valid; long long m0;
+        tc_tile_origin(p, tile_m, b0, h0, w0, m0, rows_valid);
         for (int kb = 0; kb < nkb; ++kb, ++kbc) {
           const int s = kbc % p.stages;
           const uint32_t ph = (kbc / p.stages) & 1;
@@ -156,6 +170,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
               tma_load_2d(sa, &mapA2, full, (kb - p.kb1) * TC_BK, (int)m0);
               tma_load_2d(sb, &mapB2, full, (kb - p.kb1) * TC_BK, n0);
             }
+          } else if (p.mode == 2) {
+            // A: the 4-cell windows of output pixels w0 .. w0 + tile width of s2d row h0 - 2 + kb (rows outside the image: zero fill)
+            tma_load_4d(sa, &mapA1, full, 0, w0, h0 - 2 + kb, b0);
+            tma_load_2d(sb, &mapB1, full, kb * TC_BK, n0);
           } else {
             const int tap = kb / p.kc, cc = kb % p.kc;
             const int dh = tap / 3 - 1, dw = tap % 3 - 1;
@@ -212,8 +230,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     uint32_t slab_ctr = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int tile_m = tile / n_tiles, n0 = (tile % n_tiles) * p.bn;
-      int b0, h0, rows_valid; long long m0;
-      tc_tile_origin(p, tile_m, b0, h0, m0, rows_valid);
+      int b0, h0, w0, rows_valid; long long m0;
+      tc_tile_origin(p, tile_m, b0, h0, w0, m0, rows_valid);
       const int acc = ti & 1;
       const uint32_t use = (uint32_t)(ti >> 1);
       const bool row_ok = r < rows_valid && (m0 + r) < p.M;
@@ -556,4 +574,92 @@ extern "C" int cotb200_conv3x3_bf16(int B, int H, int W, int C, const void* X, l
   if ((rc = make_map_nhwc(&a1, X, B, H, W, C, ldx, p.hbox, p.bbox))) return rc;
   if ((rc = make_map_2d(&b1, Wp, C, 9LL * bn, 9LL * bn, bn))) return rc;
   return tc_launch(a1, b1, a1, b1, p, m_tiles, st, "tc_conv3x3", 2.0 * (2.0 * (double)B * H * W * C + 9.0 * (double)C * bn));
+}
+
+// ---------------------------------------------------------------------------------------------- stem: 7x7 / s2 / p3, 3 -> N
+namespace cotb200 {
+
+// Space-to-depth copy of the 3-channel NHWC image for the stem GEMM:
+//   P[b, i, jp, (di*2+dj)*3 + c] = x[b, 2i+di, 2(jp-2)+dj, c]   for 2 <= jp < Wh+2, zero for the two pad cells either side and for
+//   channels 12..15.  One thread per cell: three 4-byte loads per image row (the 6 bf16 of two neighbouring pixels are contiguous
+//   and 4-byte aligned because W is even), two 16-byte stores.
+__global__ void __launch_bounds__(256)
+stem_s2d_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ P, int B, int H, int W) {
+  const int Hh = H >> 1, Wh = W >> 1, Wp = Wh + 4;
+  const long long total = (long long)B * Hh * Wp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int jp = (int)(idx % Wp);
+    const long long bi = idx / Wp;
+    const int i = (int)(bi % Hh), b = (int)(bi / Hh);
+    uint32_t o[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    const int j = jp - 2;
+    if (j >= 0 && j < Wh) {
+      const uint32_t* r0 = reinterpret_cast<const uint32_t*>(x + (((long long)b * H + 2 * i) * W + 2 * j) * 3);
+      const uint32_t* r1 = reinterpret_cast<const uint32_t*>(x + (((long long)b * H + 2 * i + 1) * W + 2 * j) * 3);
+      o[0] = __ldg(r0); o[1] = __ldg(r0 + 1); o[2] = __ldg(r0 + 2);
+      o[3] = __ldg(r1); o[4] = __ldg(r1 + 1); o[5] = __ldg(r1 + 2);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(P + idx * 16);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], 0u, 0u);
+  }
+}
+
+// s2d image [B, Hh, Wh+4, 16] seen as the matrix of overlapping 4-cell windows: {64 elements (window), Wh+1 window starts (32 B
+// apart), Hh rows, B}; box {64, tw, 1, 1}.  Rows outside [0, Hh) are zero-filled by the TMA = the vertical padding.
+static int make_map_stem(CUtensorMap* m, const void* base, int B, int Hh, int Wh, int tw) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return COTB200_EINVAL; }
+  const long long Wp = Wh + 4;
+  cuuint64_t dims[4] = {64, (cuuint64_t)(Wh + 1), (cuuint64_t)Hh, (cuuint64_t)B};
+  cuuint64_t strides[3] = {32, (cuuint64_t)Wp * 32, (cuuint64_t)Wp * 32 * Hh};
+  cuuint32_t box[4] = {64, (cuuint32_t)tw, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(stem windows) failed: %d", (int)r); return COTB200_EUNSUPPORTED; }
+  return 0;
+}
+
+}  // namespace cotb200
+
+extern "C" long long cotb200_stem7x7s2_scratch_bytes(int B, int H, int W) {
+  return (long long)B * (H / 2) * (W / 2 + 4) * 16 * 2;
+}
+
+// 7x7 / stride 2 / pad 3 convolution of a 3-channel NHWC bf16 image, see include/cotb200.h
+extern "C" int cotb200_stem7x7s2_bf16(int B, int H, int W, const void* X, const void* Wm, int N, void* D, long long ldd,
+                                      const float* scale, const float* shift, int relu, float* col_sum, float* col_sqsum,
+                                      void* scratch, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || N <= 0) { set_error("stem7x7s2_bf16: bad dims"); return COTB200_EINVAL; }
+  if (!X || !Wm || !D || !scratch) { set_error("stem7x7s2_bf16: NULL operand"); return COTB200_ENULL; }
+  if ((H & 1) || (W & 1)) { set_error("stem7x7s2_bf16: H=%d, W=%d must be even", H, W); return COTB200_EUNSUPPORTED; }
+  if ((N & 7) || N > 256 || (ldd & 7)) { set_error("stem7x7s2_bf16: N=%d must be a multiple of 8, <= 256", N); return COTB200_EUNSUPPORTED; }
+  if ((col_sum == nullptr) != (col_sqsum == nullptr)) { set_error("stem7x7s2_bf16: col_sum and col_sqsum go together"); return COTB200_EINVAL; }
+  if ((reinterpret_cast<uintptr_t>(X) & 3) || (reinterpret_cast<uintptr_t>(scratch) & 15)) { set_error("stem7x7s2_bf16: misaligned operand"); return COTB200_EALIGN; }
+  const int Hh = H / 2, Wh = W / 2;
+  int wtiles = (Wh + TC_BM - 1) / TC_BM;
+  while (Wh % wtiles) ++wtiles;                    // equal segments of an output row
+  const int tw = Wh / wtiles;
+  if (tw < 8) { set_error("stem7x7s2_bf16: W=%d not supported by the row tiling", W); return COTB200_EUNSUPPORTED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap a1, b1;
+  int rc;
+  if ((rc = make_map_stem(&a1, scratch, B, Hh, Wh, tw))) return rc;
+  TcParams p{};
+  p.M = B * Hh * Wh; p.N = N; p.bn = pick_bn_wide(N); p.mode = 2; p.kb1 = 4; p.kb2 = 0;
+  p.H = Hh; p.W = Wh; p.B = B; p.wtiles = wtiles; p.rows_per_tile = tw;
+  p.relu = relu; p.ldd = ldd; p.D = (__nv_bfloat16*)D; p.scale = scale; p.shift = shift; p.col_sum = col_sum; p.col_sqsum = col_sqsum;
+  if ((rc = make_map_2d(&b1, Wm, N, 256, 256, p.bn))) return rc;
+  {
+    const long long cells = (long long)B * Hh * (Wh + 4);
+    long long g = (cells + 255) / 256;
+    const int grid = (int)(g < (long long)num_sms() * 16 ? g : (long long)num_sms() * 16);
+    COTB200_PROF_B("stem_s2d", (double)B * H * W * 3 * 2 + (double)cells * 32);
+    stem_s2d_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)X, (__nv_bfloat16*)scratch, B, H, W);
+    if ((rc = check_launch("stem_s2d"))) return rc;
+  }
+  return tc_launch(a1, b1, a1, b1, p, B * Hh * wtiles, st, "tc_stem7x7",
+                   (double)B * Hh * (Wh + 4) * 32 + 2.0 * (double)p.M * N + 2.0 * N * 256);
 }

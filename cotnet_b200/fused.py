@@ -544,8 +544,9 @@ def _cot_tail_eval(u, k, bn, se):
                "tail_pool")
     w0, b0, s1, t1, w3, b3 = _se_eval_params(se)
     a = torch.empty(B, C, 2, dtype=torch.float32, device=u.device)
+    zs = torch.empty(B, w0.shape[0], dtype=torch.float32, device=u.device)
     _lib.check(lib.cotb200_se_eval(B, C, w0.shape[0], psum.data_ptr(), 1.0 / (H * W), w0.data_ptr(), _lib.ptr(b0), s1.data_ptr(),
-                                   t1.data_ptr(), w3.data_ptr(), _lib.ptr(b3), a.data_ptr(), st), "se_eval")
+                                   t1.data_ptr(), w3.data_ptr(), _lib.ptr(b3), a.data_ptr(), zs.data_ptr(), st), "se_eval")
     out = torch.empty_like(u, memory_format=torch.channels_last)
     _lib.check(lib.cotb200_tail_combine(dt, B, H * W, C, u.data_ptr(), k.data_ptr(), ss[0].data_ptr(), ss[1].data_ptr(), a.data_ptr(),
                                         out.data_ptr(), st), "tail_combine")
@@ -598,8 +599,9 @@ def cot_eval_tail_fused(v, l2d, csum, csq, lbias_p, gamma_p, beta_p, eps, gc, bn
     _lib.check(rc, "cot_agg_eval")
     w0, b0, s1, t1, w3, b3 = _se_eval_params(se)
     a = torch.empty(B, C, 2, dtype=torch.float32, device=v.device)
+    zs = torch.empty(B, w0.shape[0], dtype=torch.float32, device=v.device)
     _lib.check(lib.cotb200_se_eval(B, C, w0.shape[0], psum.data_ptr(), 1.0 / (H * W), w0.data_ptr(), _lib.ptr(b0), s1.data_ptr(),
-                                   t1.data_ptr(), w3.data_ptr(), _lib.ptr(b3), a.data_ptr(), st), "se_eval")
+                                   t1.data_ptr(), w3.data_ptr(), _lib.ptr(b3), a.data_ptr(), zs.data_ptr(), st), "se_eval")
     out = torch.empty_like(v, memory_format=torch.channels_last)
     _lib.check(lib.cotb200_mix2(dt, B, H * W, C, y.data_ptr(), k.data_ptr(), a.data_ptr(), out.data_ptr(), st), "mix2")
     return out
@@ -812,6 +814,81 @@ class TcConv3x3Fn(Function):
             # weight gradient: cuDNN grouped wgrad through torch
             dw = torch.nn.grad.conv2d_weight(x, weight.shape, dpre, stride=1, padding=1, dilation=1, groups=groups).to(weight.dtype)
         return dx, dw, sums[1].to(bndt), sums[0].to(bndt), None, None, None
+
+
+class StemConvBNFn(Function):
+    """act1(bn1(conv1(x))) of the trunk (models/resnet.py:552-554,601-603): 7x7 / stride 2 / pad 3, 3 -> N channels, on the 4-tap
+    tcgen05 implicit GEMM (cotb200_stem7x7s2_bf16) with the BatchNorm statistics in its epilogue.  x: channels_last bf16.
+    Backward: fused BatchNorm backward kernels; the weight gradient of the 3-channel convolution stays on cuDNN (the image
+    needs no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bn_w, bn_b, bn, relu):
+        B, _, H, W = x.shape
+        N = weight.shape[0]
+        lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.BF16
+        xd = x.detach()
+        wm = _tc.prepare_stem_weight(weight)
+        out = torch.empty((B, N, H // 2, W // 2), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+        pre = scale = mean = rstd = None
+        batch = bn.training or bn.running_mean is None
+        if batch:
+            sums = _zeros((2, N,), x.device)
+            pre = torch.empty_like(out, memory_format=torch.channels_last)
+            if _tc.stem7x7s2_bf16(xd, wm, stats=(sums[0], sums[1]), out=pre) is None:
+                raise RuntimeError("cotb200 stem7x7s2: geometry not supported")
+            ss = _bn_apply_batch(pre, None, sums, bn, bn_w, bn_b, relu, out, lib, st, dt)
+            scale, shift, mean, rstd = ss[0], ss[1], ss[2], ss[3]
+        else:
+            scale, shift, mean, rstd = _bn_eval_fold(bn, bn_w, bn_b)
+            if _tc.stem7x7s2_bf16(xd, wm, scale=scale, shift=shift, relu=relu, out=out) is None:
+                raise RuntimeError("cotb200 stem7x7s2: geometry not supported")
+            if any(ctx.needs_input_grad):
+                pre = _tc.stem7x7s2_bf16(xd, wm)
+        ctx.save_for_backward(xd, weight.detach(), pre, out if relu else None, scale, mean, rstd)
+        ctx.cfg = (relu, batch, bn_w.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, pre, y, scale, mean, rstd = ctx.saved_tensors
+        relu, batch, bndt = ctx.cfg
+        B, N, Ho, Wo = dy.shape
+        M = B * Ho * Wo
+        lib, st, dt = _lib.load(), _lib.stream_ptr(dy), _lib.BF16
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        sums = torch.zeros(2, N, dtype=torch.float32, device=dy.device)          # escapes as dgamma/dbeta
+        _lib.check(lib.cotb200_bn_bwd_sums(dt, B, Ho * Wo, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
+                                           None, mean.data_ptr(), rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(),
+                                           sums[1].data_ptr(), st), "bn_bwd_sums")
+        dpre = torch.empty_like(dy, memory_format=torch.channels_last)
+        _lib.check(lib.cotb200_bn_bwd_apply(dt, B, Ho * Wo, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
+                                            None, mean.data_ptr(), rstd.data_ptr(), _lib.ptr(sums[0]) if batch else None,
+                                            _lib.ptr(sums[1]) if batch else None, 1.0 / M, 1 if relu else 0,
+                                            dpre.data_ptr(), None, st), "bn_bwd_apply")
+        dx = dw = None
+        wq = weight.to(dpre.dtype)
+        if ctx.needs_input_grad[0]:
+            dx = torch.nn.grad.conv2d_input(x.shape, wq, dpre, stride=2, padding=3)
+        if ctx.needs_input_grad[1]:
+            dw = torch.nn.grad.conv2d_weight(x, weight.shape, dpre, stride=2, padding=3).to(weight.dtype)
+        return dx, dw, sums[1].to(bndt), sums[0].to(bndt), None, None
+
+
+#: the trunk's 7x7 stem convolution on the tcgen05 implicit GEMM (0 = cuDNN, the round-1 path)
+stem_tc = _os.environ.get("COTB200_STEM_TC", "1") != "0"
+
+
+def stem_conv_bn(x, conv, bn, relu=True):
+    """act(bn(conv(x))) for the 7x7/s2 stem.  tcgen05 path for channels_last bf16 3-channel images of even size (and an image
+    row of at most 256 output pixels per tile segment); anything else: cuDNN + the fused BatchNorm kernels."""
+    w = conv.weight
+    if (stem_tc and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] == 3 and tuple(w.shape[1:]) == (3, 7, 7)
+            and conv.stride == (2, 2) and conv.padding == (3, 3) and conv.dilation == (1, 1) and conv.bias is None
+            and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and w.shape[0] % 8 == 0 and w.shape[0] <= 256
+            and x.is_contiguous(memory_format=torch.channels_last)):
+        return StemConvBNFn.apply(x, w, bn.weight, bn.bias, bn, relu)
+    return bn_act(conv(x).contiguous(memory_format=torch.channels_last), bn, relu=relu)
 
 
 #: which 1x1 convolutions of the ENCLOSING bottleneck (conv1 / conv3 / stride-1 downsample) run on the tcgen05 kernels in

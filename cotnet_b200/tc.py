@@ -128,3 +128,35 @@ def conv3x3_bf16(x, wp, bn, scale=None, shift=None, relu=False, stats=None, out=
                                           _lib.ptr(shift), 1 if relu else 0, _lib.ptr(cs), _lib.ptr(cq), _lib.stream_ptr(x))
     _lib.check(rc, "conv3x3_bf16")
     return out
+
+
+def prepare_stem_weight(weight):
+    """[N, 3, 7, 7] -> Wm [N, 256] bf16 for cotb200_stem7x7s2_bf16: Wm[n, a*64 + a2*16 + (di*2+dj)*3 + c] =
+    weight[n, c, 2a+di-1, 2a2+dj-1] (zero where an index is -1, and for the 4 pad channels of every cell)."""
+    N = weight.shape[0]
+    assert tuple(weight.shape[1:]) == (3, 7, 7)
+    wp = torch.zeros(N, 3, 8, 8, dtype=torch.float32, device=weight.device)
+    wp[:, :, 1:, 1:] = weight.detach().float()                       # index u = kh + 1 = 2a + di
+    w6 = wp.view(N, 3, 4, 2, 4, 2).permute(0, 2, 4, 3, 5, 1)         # [n, a, a2, di, dj, c]
+    wm = torch.zeros(N, 4, 4, 16, dtype=torch.float32, device=weight.device)
+    wm[..., :12] = w6.reshape(N, 4, 4, 12)
+    return wm.reshape(N, 256).to(torch.bfloat16).contiguous()
+
+
+def stem7x7s2_bf16(x, wm, scale=None, shift=None, relu=False, stats=None, out=None):
+    """x: channels_last bf16 [B,3,H,W] -> channels_last bf16 [B,N,H/2,W/2] = conv 7x7 / stride 2 / pad 3 with the prepared weight
+    wm (prepare_stem_weight).  Returns None when the library cannot take the geometry (COTB200_EUNSUPPORTED)."""
+    assert x.dim() == 4 and x.shape[1] == 3 and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+    B, _, H, W = x.shape
+    N = wm.shape[0]
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((B, N, H // 2, W // 2), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    scratch = torch.empty(int(lib.cotb200_stem7x7s2_scratch_bytes(B, H, W)), dtype=torch.uint8, device=x.device)
+    cs, cq = (stats if stats is not None else (None, None))
+    rc = lib.cotb200_stem7x7s2_bf16(B, H, W, x.data_ptr(), wm.data_ptr(), N, out.data_ptr(), N, _lib.ptr(scale), _lib.ptr(shift),
+                                    1 if relu else 0, _lib.ptr(cs), _lib.ptr(cq), scratch.data_ptr(), _lib.stream_ptr(x))
+    if rc == -7:
+        return None
+    _lib.check(rc, "stem7x7s2_bf16")
+    return out

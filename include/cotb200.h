@@ -164,12 +164,15 @@ int cotb200_tail_bwd_dz_sums(int dtype, int B, int HW, int C, const void* dout, 
 int cotb200_tail_bwd_apply(int dtype, int B, int HW, int C, const void* dout, const void* u, const float* scale,
                            const float* shift, const float* mu, const float* rstd, const float* a, const float* dpn,
                            const float* c1, const float* c2, float inv_n, float pscale, void* du, void* dk, void* stream);
-/* The SE MLP of the split attention in EVAL mode, one launch (models/cotnet.py:69-77,92-101):
+/* The SE MLP of the split attention in EVAL mode (models/cotnet.py:69-77,92-101), two tiled launches (fc1, fc2 + softmax):
  *   a[b,c,0:2] = softmax_r( W3[2c+r,:] . relu(s1*(W0 . (psum[b]*inv_hw) + b0) + t1) + b3[2c+r] )
  * with the BatchNorm of `se` folded into s1 / t1.  psum [B,C] is what cotb200_tail_pool accumulates; a [B,C,2] is what
- * cotb200_tail_combine takes.  All fp32; W0 [A,C], W3 [2C,A] row-major; b0 / b3 may be NULL. */
+ * cotb200_tail_combine takes.  All fp32; W0 [A,C], W3 [2C,A] row-major; b0 / b3 may be NULL; z_scratch: B*A floats
+ * (cotb200_se_eval_scratch_bytes) for the hidden activations between the two launches. */
+long long cotb200_se_eval_scratch_bytes(int B, int A);
 int cotb200_se_eval(int B, int C, int A, const float* psum, float inv_hw, const float* W0, const float* b0,
-                    const float* s1, const float* t1, const float* W3, const float* b3, float* a, void* stream);
+                    const float* s1, const float* t1, const float* W3, const float* b3, float* a, float* z_scratch,
+                    void* stream);
 /* BatchNorm2d (+ReLU) (+residual add) on NHWC tensors: y = act(x*scale + shift (+ res)).  With cotb200_col_stats this
  * replaces nn.BatchNorm2d / nn.ReLU pairs of the block (models/cotnet.py:45-46,53-54,61-62) and of the enclosing
  * bottleneck (models/cotnet.py:231-235,:249-262) in 2 forward + 2 backward HBM passes.  relu: 0/1; res may be NULL. */
@@ -282,6 +285,19 @@ int cotb200_gn9_coef_from_colsums(int B, int HW, int wc, int gc, const float* cs
 int cotb200_conv3x3_bf16(int B, int H, int W, int C, const void* X, long long ldx, const void* Wp, int bn,
                          void* D, long long ldd, const float* scale, const float* shift, int relu,
                          float* col_sum, float* col_sqsum, void* stream);
+
+/* cotb200_stem7x7s2_bf16: the stem convolution conv1 = nn.Conv2d(3, N, 7, stride=2, padding=3, bias=False)
+ *   (models/resnet.py:552, called at :601; cuDNN in the reference) on an NHWC bf16 image X[B,H,W,3] (dense, H and W even) as a
+ *   4-tap implicit tcgen05 GEMM: a space-to-depth copy of the image (scratch, cotb200_stem7x7s2_scratch_bytes bytes, 16-byte
+ *   aligned) turns the 7x7/s2 window into 4 rows x 4 cells x 16 channels, and one TMA box per row fetches the overlapping
+ *   windows of a whole output-row segment as the K-major A tile (K = 4 x 64).  D[B*(H/2)*(W/2), N] bf16 (row pitch ldd).
+ *   Wm [N, 256] bf16: Wm[n, a*64 + a2*16 + (di*2+dj)*3 + c] = weight[n, c, 2a+di-1, 2a2+dj-1] (0 where an index is -1 and
+ *   for the 4 pad channels).  Same epilogue as cotb200_gemm_bf16 (scale/shift/ReLU, optional BatchNorm column statistics).
+ *   Returns COTB200_EUNSUPPORTED when the geometry / driver cannot take it (the caller then keeps its cuDNN convolution). */
+long long cotb200_stem7x7s2_scratch_bytes(int B, int H, int W);
+int cotb200_stem7x7s2_bf16(int B, int H, int W, const void* X, const void* Wm, int N, void* D, long long ldd,
+                           const float* scale, const float* shift, int relu, float* col_sum, float* col_sqsum,
+                           void* scratch, void* stream);
 
 /* cotb200_wgrad_bf16: weight gradient of a 1x1 convolution,  OUT += A[M,R]^T [B1[M,C1] | B2[M,C2]]  (contraction over the M
  *   pixels; A = dY, B = the convolution input(s); bf16 operands, fp32 accumulation in TMEM, fp32 OUT).  Replaces cuDNN's wgrad

@@ -151,3 +151,42 @@ def test_tap_chunk_and_positions():
             # each chunk of 8 groups occupies the same 72 positions in both orders (what csrc/gn72.cu relies on)
             assert pos // 72 == (g * 9 + t) // 72
     assert len(seen) == 9 * wc
+
+
+def test_stem_space_to_depth_weight_packing():
+    """conv 7x7 / stride 2 / pad 3 on 3 channels == 4 row-taps x (4 cells x 16 channels) contraction over the space-to-depth image,
+    with the weight packed by cotnet_b200.tc.prepare_stem_weight -- the arithmetic of cotb200_stem7x7s2_bf16 (csrc/tc_gemm.cu
+    stem mode) restated in torch fp64 (models/resnet.py:552)."""
+    from cotnet_b200 import tc
+    torch.manual_seed(3)
+    B, H, W, N = 2, 12, 20, 8
+    x = torch.randn(B, 3, H, W, dtype=torch.float64)
+    w = torch.randn(N, 3, 7, 7, dtype=torch.float64)
+    want = torch.nn.functional.conv2d(x, w, None, 2, 3)
+    Hh, Wh = H // 2, W // 2
+    # P[b, i, jp, (di*2+dj)*3 + c] = x[b, c, 2i+di, 2(jp-2)+dj], two zero cells either side, channels 12..15 zero
+    P = torch.zeros(B, Hh, Wh + 4, 16, dtype=torch.float64)
+    xs = x.view(B, 3, Hh, 2, Wh, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, Hh, Wh, 12)      # [b, i, j, (di, dj, c)]
+    P[:, :, 2:Wh + 2, :12] = xs
+    wm = tc.prepare_stem_weight(w.float()).double()        # bf16-rounded values
+    wq = torch.zeros_like(w)
+    # undo the packing to know which (rounded) weight the kernel multiplies with
+    wm4 = wm.view(N, 4, 4, 16)[..., :12].reshape(N, 4, 4, 2, 2, 3)
+    for a in range(4):
+        for a2 in range(4):
+            for di in range(2):
+                for dj in range(2):
+                    kh, kw = 2 * a + di - 1, 2 * a2 + dj - 1
+                    if kh >= 0 and kw >= 0:
+                        wq[:, :, kh, kw] = wm4[:, a, a2, di, dj, :]
+    assert (wq - w).abs().max() <= 2 ** -8 * w.abs().max()          # only bf16 rounding
+    want_q = torch.nn.functional.conv2d(x, wq, None, 2, 3)
+    # implicit GEMM: out[b, oh, ow, n] = sum_a  window(P[b, oh-2+a, ow .. ow+3, :]) . wm[n, a*64 : (a+1)*64]
+    Pp = torch.nn.functional.pad(P, (0, 0, 0, 0, 2, 2))              # rows oh-2+a in [-2, Hh+1] -> zero rows (TMA out-of-bounds fill)
+    out = torch.zeros(B, Hh, Wh, N, dtype=torch.float64)
+    for a in range(4):
+        rows = Pp[:, a:a + Hh]                                      # [B, Hh, Wh+4, 16]
+        win = torch.stack([rows[:, :, k:k + Wh] for k in range(4)], dim=3).reshape(B, Hh, Wh, 64)
+        out += win @ wm[:, a * 64:(a + 1) * 64].t()
+    assert (out.permute(0, 3, 1, 2) - want_q).abs().max() < 1e-9
+    assert (out.permute(0, 3, 1, 2) - want).abs().max() < 0.2

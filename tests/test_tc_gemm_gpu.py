@@ -246,3 +246,54 @@ def test_tc_conv3x3_fn_autograd(training):
     _close(y, yr, 3e-2)
     for a, b in zip(grads, grads_r):
         _rel_l2(a, b)
+
+
+@pytest.mark.parametrize("B,H,W,N", [(2, 224, 224, 64), (3, 64, 96, 64), (1, 32, 480, 32)])
+def test_stem7x7s2_vs_conv2d(B, H, W, N):
+    """conv1 of the trunk (models/resnet.py:552) on the 4-tap tcgen05 implicit GEMM against fp32 torch math on the same bf16 operands;
+    raw output + BatchNorm column statistics, and the eval epilogue (folded scale / shift + ReLU)."""
+    g = torch.Generator(device="cuda").manual_seed(B + H + W)
+    x = torch.randn(B, 3, H, W, generator=g, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(N, 3, 7, 7, generator=g, device="cuda") / 12).bfloat16()
+    want = F.conv2d(x.float(), w.float(), None, 2, 3)
+    tc = _tc()
+    wm = tc.prepare_stem_weight(w)
+    cs, cq = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+    d = tc.stem7x7s2_bf16(x, wm, stats=(cs, cq))
+    assert d is not None, "stem geometry refused"
+    assert d.shape == want.shape and d.is_contiguous(memory_format=torch.channels_last)
+    _close(d, want)
+    assert torch.allclose(cs, d.float().sum((0, 2, 3)), atol=2e-2, rtol=1e-4)
+    assert torch.allclose(cq, (d.float() ** 2).sum((0, 2, 3)), atol=2e-2, rtol=1e-4)
+    scale = torch.rand(N, generator=g, device="cuda") + 0.5
+    shift = torch.randn(N, generator=g, device="cuda")
+    d2 = tc.stem7x7s2_bf16(x, wm, scale=scale, shift=shift, relu=True)
+    _close(d2, torch.relu(want * scale[None, :, None, None] + shift[None, :, None, None]))
+
+
+def test_stem_conv_bn_autograd_vs_cudnn_path():
+    """fused.stem_conv_bn (tcgen05 stem + statistics epilogue + fused BatchNorm) against the cuDNN convolution + the same fused
+    BatchNorm kernels: outputs, BatchNorm buffers and parameter gradients."""
+    import copy
+    from cotnet_b200 import fused
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(4, 3, 96, 128, generator=g, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    conv = torch.nn.Conv2d(3, 64, 7, 2, 3, bias=False).cuda().to(torch.bfloat16)
+    bn = torch.nn.BatchNorm2d(64).cuda().train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.2)
+    conv2, bn2 = copy.deepcopy(conv), copy.deepcopy(bn)
+    cot = torch.randn(4, 64, 48, 64, generator=g, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    y1 = fused.stem_conv_bn(x, conv, bn, relu=True)
+    y2 = fused.bn_act(conv2(x).contiguous(memory_format=torch.channels_last), bn2, relu=True)
+    _close(y1, y2, 2e-2)
+    assert torch.allclose(bn.running_mean, bn2.running_mean, atol=1e-3) and torch.allclose(bn.running_var, bn2.running_var, atol=1e-3, rtol=1e-2)
+    g1 = torch.autograd.grad(y1, (conv.weight, bn.weight, bn.bias), cot)
+    g2 = torch.autograd.grad(y2, (conv2.weight, bn2.weight, bn2.bias), cot)
+    for a, b in zip(g1, g2):
+        rel = ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-6)).item()
+        assert rel <= 3e-2, rel
+    # eval mode: BatchNorm folded into the GEMM epilogue
+    bn.eval(); bn2.eval()
+    with torch.no_grad():
+        _close(fused.stem_conv_bn(x, conv, bn, relu=True), fused.bn_act(conv2(x).contiguous(memory_format=torch.channels_last), bn2, relu=True), 2e-2)
