@@ -488,6 +488,9 @@ template <typename T> int nhwc2_dw(const Nhwc2Args&, const T*, const T*, T*, cud
 // TMA-pipelined NCHW kernels (agg_nchw_tma.cu): mode 0 fwd / 1 dX / 2 dW
 template <typename T> int nchw_tma_launch(int, int, int, int, int, int, long long, long long, long long, const T*, const T*, T*,
                                           cudaStream_t, int*);
+// small-plane NCHW kernels (agg_nchw_plane.cu): mode 0 fwd / 1 dX / 2 dW / 3 dX + dW
+template <typename T> int nchw_plane_launch(int, int, int, int, int, int, long long, long long, long long, const T*, const T*, const T*, T*, T*,
+                                            cudaStream_t, int*);
 // second-generation NCHW kernels (agg_nchw2.cu)
 template <typename T> int nchw2_fwd(int, int, int, int, int, long long, const T*, const T*, T*, cudaStream_t, int*);
 template <typename T> int nchw2_bwd(int, int, int, int, int, long long, const T*, const T*, const T*, T*, T*, cudaStream_t, int*);
@@ -583,6 +586,7 @@ static int fwd_impl(const Geo& g, const T* x, const T* w, T* y, cudaStream_t st)
   }
   if (g.layout == COTB200_NCHW && nofold(g) && fits32(g) && is_same3(g, 3) && g.w_sn == (long long)g.wc * 9 * g.H * g.W) {
     int rc2 = 0;
+    if (g.H * g.W <= 256 && nchw_plane_launch<T>(0, g.N, g.C, g.H, g.W, g.wc, g.x_sn, g.y_sn, g.w_sn, x, (const T*)nullptr, w, y, (T*)nullptr, st, &rc2)) return rc2;
     if (g.x_sn == (long long)g.C * g.H * g.W &&
         nchw_tma_launch<T>(0, g.N, g.C, g.H, g.W, g.wc, g.x_sn, 0, g.y_sn, x, w, y, st, &rc2)) return rc2;
     if (nchw2_fwd<T>(g.N, g.C, g.H, g.W, g.wc, g.y_sn, x, w, y, st, &rc2)) return rc2;
@@ -630,6 +634,8 @@ static int bwd_impl(const Geo& g, const T* dy, const T* x, const T* w, T* dx, T*
   if (!dx && !dw) return 0;
   if (g.layout == COTB200_NCHW && nofold(g) && fits32(g) && is_same3(g, 3) && !acc_dx && g.w_sn == (long long)g.wc * 9 * g.H * g.W) {
     int rc2 = 0;
+    if (g.H * g.W <= 256 && nchw_plane_launch<T>(dx && dw ? 3 : (dx ? 1 : 2), g.N, g.C, g.H, g.W, g.wc, g.x_sn, g.y_sn, g.w_sn, dy, x, w,
+                                                 dx, dw, st, &rc2)) return rc2;
     if (g.x_sn == (long long)g.C * g.H * g.W && g.w_sn == (long long)g.wc * 9 * g.H * g.W) {
       // TMA-pipelined kernels, one per gradient; if only one of the two is eligible the register kernel does the other
       int done_dx = !dx, done_dw = !dw;

@@ -4,7 +4,8 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-( timeout 600 python -m pytest tests/test_tc_gemm_gpu.py tests/test_fused_gpu.py tests/test_cot_layer_gpu.py -m gpu -q --maxfail=30 2>&1 | tail -60 ) > gpurun_out/i_tests.log 2>&1
+( timeout 900 python -m pytest tests/test_tc_gemm_gpu.py tests/test_fused_gpu.py tests/test_cot_layer_gpu.py tests/test_agg_gpu.py tests/test_ref_kernels_gpu.py -m gpu -q --maxfail=30 2>&1 | tail -60 ) > gpurun_out/i_tests.log 2>&1
+( timeout 400 python tools/bench_ref_kernels.py --iters 10 --json gpurun_out/i_bench_ref_kernels.json ) > gpurun_out/i_bench_ref_kernels.log 2>&1
 ( timeout 400 python -m pytest tests/test_trainer_gpu.py -m gpu -q -k "bench_path or plain_pytorch_loop" 2>&1 | tail -30 ) > gpurun_out/i_tests_trainer.log 2>&1
 cp gpurun_out/parity_measured.json gpurun_out/i_parity_default.json 2>/dev/null
 ( COTB200_TRAIN_CONV=cudnn timeout 300 python -m pytest tests/test_trainer_gpu.py -m gpu -q -k "bench_path and cotnext" 2>&1 | tail -8 ) > gpurun_out/i_tests_cotnext_cudnn.log 2>&1
@@ -38,4 +39,5 @@ for n in ("default","cudnn"):
         print(n, "ERR", e)
 PY
 head -14 gpurun_out/i_prof_cotnet50_eval.md | cut -c1-140
+tail -6 gpurun_out/i_bench_ref_kernels.log | cut -c1-500
 head -14 gpurun_out/i_prof_cotnet50_eval_nofuse.md | cut -c1-140
