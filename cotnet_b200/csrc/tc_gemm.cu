@@ -490,6 +490,278 @@ static int pick_bn_wide(int N) {
   return bn > 256 ? 256 : bn;
 }
 
+// ---------------------------------------------------------------------------------------------- 3x3 conv, haloed-tile kernel
+// conv mode of tc_gemm_kernel fetches one pixel box PER TAP: every input pixel travels L2 -> shared memory nine times and the
+// kernel is L2-bound (120 us at [256,64,56,56] against a 32 us HBM roof, profiles/r01_tc_ncu_v3.md).  Here a CTA loads ONE haloed
+// tile {64 ch, W+2, R+2} of the NHWC input per work item (TMA out-of-bounds fill = zero padding on all four sides) and the nine
+// taps are nine UMMA A-descriptors INTO THAT TILE: with the output pixels enumerated in padded coordinates q = r*(W+2) + c, the A
+// rows of tap (dh, dw) are the smem rows q + (dh+1)*(W+2) + (dw+1) -- a contiguous row range, i.e. the same K-major SW128
+// descriptor with a start address moved by a whole number of 128-byte rows (the 128B swizzle is a function of the absolute shared
+// memory address, which is how TMA wrote the tile).  Outputs with c >= W are garbage columns that are never stored.
+//   * weights of the CTA's 64 output channels (9 taps x 64 x 64, 72 KB) stay resident in shared memory: CTAs are bound to one
+//     N tile, work items of that N tile are strided over the CTAs bound to it;
+//   * accumulators: MB <= 2 M-blocks of 128 padded pixels x 64 columns, double-buffered in TMEM across work items;
+//   * epilogue: TMEM -> scale/shift/ReLU -> bf16 -> compacted (garbage columns dropped) 128B-swizzled image of the R x W output
+//     pixels -> ONE TMA store; BatchNorm column statistics from the staged image, accumulated in registers over ALL work items of
+//     the CTA (its N tile never changes) and flushed with one atomic per column per CTA.
+// Geometry: bn = 64 (kc = 1), R | H, R*(W+2) <= 256.  Everything else stays on conv mode of tc_gemm_kernel.
+struct HcParams {
+  int B, H, W, C, R, MB, Wp, n_tiles, bands, items;   // items = B * bands work items per N tile
+  int a_stage_bytes, stages, box_bytes, relu, base_off;
+  const float* scale; const float* shift; float* col_sum; float* col_sqsum;
+};
+
+static constexpr int HC_WBYTES = 9 * 64 * 128;          // resident weights of one N tile
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_rows(uint32_t saddr, int base_off) {
+  uint64_t d = umma_desc_sw128(saddr);
+  if (base_off) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
+                       const __grid_constant__ CUtensorMap mapD, const HcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_s = smem;                                               // [9][64 rows][128 B] SW128
+  uint8_t* a_s = smem + HC_WBYTES;                                    // stages x haloed tile
+  uint8_t* o_s = a_s + (size_t)p.stages * p.a_stage_bytes;           // [R*W rows][128 B] SW128 compacted output image
+  __shared__ __align__(8) uint64_t s_full[4], s_empty[4], s_wfull, s_tfull[2], s_tempty[2];
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) float s_scale[64], s_shift[64];
+  __shared__ float s_part[2][4][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = blockIdx.x % p.n_tiles, n0 = nt * 64;
+  const int first = blockIdx.x / p.n_tiles, step = gridDim.x / p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
+    mbar_init(smem_u32(&s_wfull), 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&s_tfull[a]), 1); mbar_init(smem_u32(&s_tempty[a]), 4); }
+    mbar_init_fence();
+  }
+  const uint32_t ncols = p.MB == 1 ? 128u : 256u;                     // two buffers x MB x 64 columns
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x < 64) {
+    s_scale[threadIdx.x] = p.scale ? __ldg(p.scale + n0 + threadIdx.x) : 1.f;
+    s_shift[threadIdx.x] = p.shift ? __ldg(p.shift + n0 + threadIdx.x) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t wf = smem_u32(&s_wfull);
+      mbar_expect_tx(wf, HC_WBYTES);
+      for (int t = 0; t < 9; ++t) tma_load_2d(smem_u32(w_s + t * 8192), &mapW, wf, t * 64, n0);
+      int it = 0;
+      for (int m = first; m < p.items; m += step, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        const int b = m / p.bands, h0 = (m - b * p.bands) * p.R;
+        mbar_wait(smem_u32(&s_empty[s]), ph ^ 1);
+        const uint32_t full = smem_u32(&s_full[s]);
+        mbar_expect_tx(full, (uint32_t)p.box_bytes);
+        tma_load_4d(smem_u32(a_s + (size_t)s * p.a_stage_bytes), &mapX, full, n0, -1, h0 - 1, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(64);
+      mbar_wait(smem_u32(&s_wfull), 0);
+      tc_fence_after();
+      const uint32_t wb = smem_u32(w_s);
+      int it = 0;
+      for (int m = first; m < p.items; m += step, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        const int acc = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(smem_u32(&s_tempty[acc]), (use & 1) ^ 1);
+        tc_fence_after();
+        mbar_wait(smem_u32(&s_full[s]), ph);
+        tc_fence_after();
+        const uint32_t ab = smem_u32(a_s + (size_t)s * p.a_stage_bytes);
+        for (int mb = 0; mb < p.MB; ++mb) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)((acc * p.MB + mb) * 64);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int row = mb * 128 + (t / 3) * p.Wp + (t % 3);          // first smem row of this tap's A operand
+            const uint64_t da = umma_desc_sw128_rows(ab + (uint32_t)row * 128u, p.base_off);
+            const uint64_t db = umma_desc_sw128(wb + (uint32_t)t * 8192u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (t | k) != 0);
+          }
+        }
+        umma_commit(smem_u32(&s_empty[s]));
+        umma_commit(smem_u32(&s_tfull[acc]));
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;
+    const int et = threadIdx.x - 64;
+    const bool stats = p.col_sum != nullptr;
+    const uint32_t ob = smem_u32(o_s);
+    const int RW = p.R * p.W;
+    const int tp = et & 31, rg = et >> 5;
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;                     // statistics of columns 2tp, 2tp+1 over rows rg, rg+4, ...
+    int it = 0;
+    for (int m = first; m < p.items; m += step, ++it) {
+      const int acc = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      const int b = m / p.bands, h0 = (m - b * p.bands) * p.R;
+      mbar_wait(smem_u32(&s_tfull[acc]), use & 1);
+      __syncwarp();
+      tc_fence_after();
+      // the previous item's store must have finished READING the staging image
+      if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int mb = 0; mb < p.MB; ++mb) {
+        const int q = mb * 128 + quad * 32 + lane;                   // padded output pixel
+        const int ro = q / p.Wp, co = q - ro * p.Wp;
+        const bool ok = ro < p.R && co < p.W;
+        const int prow = ro * p.W + co;                              // row of the compacted image
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * p.MB + mb) * 64 + c * 32), raw);
+          if (ok) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const int col = c * 32 + j8 * 8;
+              const float4 sc0 = *reinterpret_cast<const float4*>(&s_scale[col]), sc1 = *reinterpret_cast<const float4*>(&s_scale[col + 4]);
+              const float4 sh0 = *reinterpret_cast<const float4*>(&s_shift[col]), sh1 = *reinterpret_cast<const float4*>(&s_shift[col + 4]);
+              const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+              const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float lo = fmaf(__uint_as_float(raw[j8 * 8 + 2 * e]), scv[2 * e], shv[2 * e]);
+                float hi = fmaf(__uint_as_float(raw[j8 * 8 + 2 * e + 1]), scv[2 * e + 1], shv[2 * e + 1]);
+                if (p.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              const int chunk = c * 4 + j8;
+              const uint32_t dst = ob + (uint32_t)(prow * 128 + ((chunk ^ (prow & 7)) << 4));
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+            }
+          }
+        }
+      }
+      // accumulator buffer drained
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_tempty[acc]));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        const int m0 = (b * p.H + h0) * p.W;
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(&mapD), "r"(ob), "r"(n0), "r"(m0) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (stats) {
+        const __nv_bfloat16 one = one_of<__nv_bfloat16>();
+        for (int r0 = rg; r0 < RW; r0 += 32) {                       // 8 rows per batch: loads first, then the arithmetic
+          uint32_t w2[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int row = r0 + 4 * u;
+            w2[u] = 0u;
+            if (row < RW) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2[u]) : "r"(ob + (uint32_t)(row * 128 + (((tp >> 2) ^ (row & 7)) << 4) + (tp & 3) * 4)));
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const __nv_bfloat16 lo = __ushort_as_bfloat16((unsigned short)(w2[u] & 0xFFFFu)), hi = __ushort_as_bfloat16((unsigned short)(w2[u] >> 16));
+            s0 = mfma<__nv_bfloat16>(lo, one, s0); q0 = mfma<__nv_bfloat16>(lo, lo, q0);
+            s1 = mfma<__nv_bfloat16>(hi, one, s1); q1 = mfma<__nv_bfloat16>(hi, hi, q1);
+          }
+        }
+      }
+    }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (stats) {
+      s_part[0][rg][2 * tp] = s0; s_part[0][rg][2 * tp + 1] = s1;
+      s_part[1][rg][2 * tp] = q0; s_part[1][rg][2 * tp + 1] = q1;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < 64) {
+        atomicAdd(p.col_sum + n0 + et, (s_part[0][0][et] + s_part[0][1][et]) + (s_part[0][2][et] + s_part[0][3][et]));
+        atomicAdd(p.col_sqsum + n0 + et, (s_part[1][0][et] + s_part[1][1][et]) + (s_part[1][2][et] + s_part[1][3][et]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
+// returns 1 when the haloed-tile kernel took the convolution (*rc = status), 0 when conv mode of tc_gemm_kernel should run
+static int conv3x3_halo_launch(int B, int H, int W, int C, const void* X, long long ldx, const void* Wp, int bn, void* D, long long ldd,
+                               const float* scale, const float* shift, int relu, float* col_sum, float* col_sqsum, cudaStream_t st, int* rc) {
+  static int mode = -2;                       // COTB200_CONV_HALO: 0 = off, 1 (default) = on, 2 = on with descriptor base offsets
+  if (mode == -2) { const char* e = getenv("COTB200_CONV_HALO"); mode = e ? atoi(e) : 1; }
+  if (mode <= 0 || bn != 64 || C % 64 || W + 2 > 256 || ldx != C || ldd != C) return 0;
+  const int Wpad = W + 2;
+  int R = 0;
+  for (int r = 1; r <= H; ++r) if (H % r == 0 && r * Wpad <= 256 && r * W <= 256) R = r;
+  if (R == 0) return 0;
+  HcParams p{};
+  p.B = B; p.H = H; p.W = W; p.C = C; p.R = R; p.Wp = Wpad; p.MB = (R * Wpad + 127) / 128;
+  p.n_tiles = C / 64; p.bands = H / R; p.items = B * p.bands;
+  if (p.n_tiles > num_sms()) return 0;
+  const int a_rows = max((R + 2) * Wpad, p.MB * 128 + 2 * Wpad + 2);
+  p.a_stage_bytes = (a_rows * 128 + 1023) & ~1023;
+  p.box_bytes = (R + 2) * Wpad * 128;
+  const int out_bytes = (R * W * 128 + 1023) & ~1023;
+  p.stages = (220 * 1024 - HC_WBYTES - out_bytes) / p.a_stage_bytes;
+  if (p.stages > 4) p.stages = 4;
+  if (p.stages < 2) return 0;
+  p.relu = relu; p.base_off = mode == 2 ? 1 : 0;
+  p.scale = scale; p.shift = shift; p.col_sum = col_sum; p.col_sqsum = col_sqsum;
+  CUtensorMap mx, mw, md;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return 0;
+  {
+    if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(D) & 15)) return 0;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+    cuuint32_t box[4] = {64, (cuuint32_t)Wpad, (cuuint32_t)(R + 2), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(X), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 0;
+  }
+  if (make_map_2d(&mw, Wp, C, 9LL * 64, 9LL * 64, 64)) return 0;
+  if (make_map_2d(&md, D, (long long)B * H * W, C, ldd, R * W)) return 0;
+  const int smem = HC_WBYTES + p.stages * p.a_stage_bytes + out_bytes + 1024;
+  static PerDevFlag configured_d;
+  if (bool& configured = configured_d.get(); !configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv halo): %s", cudaGetErrorString(e)); *rc = (int)e; return 1; }
+    configured = true;
+  }
+  int grid = (num_sms() / p.n_tiles) * p.n_tiles;
+  if (grid > p.items * p.n_tiles) grid = p.items * p.n_tiles;
+  COTB200_PROF_B("tc_conv3x3_halo", 2.0 * (2.0 * (double)B * H * W * C + 9.0 * (double)C * 64));
+  tc_conv3x3_halo_kernel<<<grid, TC_THREADS, smem, st>>>(mx, mw, md, p);
+  *rc = check_launch("tc_conv3x3_halo");
+  return 1;
+}
+
 }  // namespace cotb200
 
 using namespace cotb200;
@@ -553,6 +825,10 @@ extern "C" int cotb200_conv3x3_bf16(int B, int H, int W, int C, const void* X, l
   if (W > 128) { set_error("conv3x3_bf16: W=%d > 128 not supported by the pixel-box tiling", W); return COTB200_EINVAL; }
   if ((col_sum == nullptr) != (col_sqsum == nullptr)) { set_error("conv3x3_bf16: col_sum and col_sqsum go together"); return COTB200_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    int hrc = 0;
+    if (conv3x3_halo_launch(B, H, W, C, X, ldx, Wp, bn, D, ldd, scale, shift, relu, col_sum, col_sqsum, st, &hrc)) return hrc;
+  }
   TcParams p{};
   p.M = B * H * W; p.N = C; p.bn = bn; p.mode = 1; p.kc = bn / 64;
   p.H = H; p.W = W; p.B = B;

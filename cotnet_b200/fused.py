@@ -636,6 +636,7 @@ def split_attn_tail(u, bn0: torch.nn.BatchNorm2d, fc1, bn1, fc2):
 #   weight grad  : 1x1: the MN-major tcgen05 kernel (tc_wgrad.cu); the grouped 3x3 still goes through cuDNN
 # ====================================================================================================================
 from . import tc as _tc  # noqa: E402
+import os as _os  # noqa: E402
 
 
 def _rows2d(t):
@@ -894,7 +895,6 @@ def stem_conv_bn(x, conv, bn, relu=True):
 #: which 1x1 convolutions of the ENCLOSING bottleneck (conv1 / conv3 / stride-1 downsample) run on the tcgen05 kernels in
 #: training: "tc_all1x1" = all of them (forward with the BatchNorm statistics in the epilogue, data and weight gradients),
 #: anything else = cuDNN + the fused BatchNorm kernels.  Same environment variable as CotLayer.train_conv_backend.
-import os as _os  # noqa: E402
 trunk_conv_backend = _os.environ.get("COTB200_TRAIN_CONV", "tc_e0")
 
 

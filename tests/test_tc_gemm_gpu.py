@@ -64,7 +64,7 @@ def test_gemm_channels_last_rows():
 
 
 @pytest.mark.parametrize("C,groups,H,B", [(64, 4, 56, 2), (128, 4, 28, 3), (256, 4, 14, 3), (512, 4, 7, 5), (64, 4, 8, 2),
-                                          (64, 1, 10, 2)])
+                                          (64, 1, 10, 2), (128, 4, 40, 2), (64, 4, 80, 1), (192, 1, 12, 2)])
 def test_conv3x3(C, groups, H, B):
     tc = _tc()
     g = torch.Generator(device="cuda").manual_seed(C + H)

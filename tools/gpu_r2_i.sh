@@ -5,6 +5,8 @@ cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 ( timeout 900 python -m pytest tests/test_tc_gemm_gpu.py tests/test_fused_gpu.py tests/test_cot_layer_gpu.py tests/test_agg_gpu.py tests/test_ref_kernels_gpu.py -m gpu -q --maxfail=30 2>&1 | tail -60 ) > gpurun_out/i_tests.log 2>&1
+( COTB200_CONV_HALO=2 timeout 300 python -m pytest tests/test_tc_gemm_gpu.py -m gpu -q -k conv3x3 2>&1 | tail -15 ) > gpurun_out/i_tests_halo_baseoff.log 2>&1
+( COTB200_CONV_HALO=0 timeout 300 python -m pytest tests/test_tc_gemm_gpu.py -m gpu -q -k conv3x3 2>&1 | tail -5 ) > gpurun_out/i_tests_halo_off.log 2>&1
 ( timeout 400 python tools/bench_ref_kernels.py --iters 10 --json gpurun_out/i_bench_ref_kernels.json ) > gpurun_out/i_bench_ref_kernels.log 2>&1
 ( timeout 400 python -m pytest tests/test_trainer_gpu.py -m gpu -q -k "bench_path or plain_pytorch_loop" 2>&1 | tail -30 ) > gpurun_out/i_tests_trainer.log 2>&1
 cp gpurun_out/parity_measured.json gpurun_out/i_parity_default.json 2>/dev/null
@@ -20,7 +22,8 @@ COTB200_EVAL_FUSED_AGG=0 b eval_nofuse
 ( timeout 300 python tools/profile_step.py --model cotnet50 --batch 256 --out gpurun_out/i_prof_cotnet50_train.md ) > gpurun_out/i_prof_train.log 2>&1
 ( timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/i_targets python tools/ncu_targets.py --what eval,gemm ) > gpurun_out/i_ncu.log 2>&1
 ls -la gpurun_out/i_targets.ncu-rep
-tail -12 gpurun_out/i_tests.log | cut -c1-250
+tail -25 gpurun_out/i_tests.log | cut -c1-250
+echo '--- halo base offset variant'; tail -6 gpurun_out/i_tests_halo_baseoff.log | cut -c1-250; tail -2 gpurun_out/i_tests_halo_off.log
 tail -8 gpurun_out/i_tests_trainer.log | cut -c1-250
 tail -4 gpurun_out/i_tests_cotnext_cudnn.log | cut -c1-250
 python - <<'PY'
