@@ -109,9 +109,18 @@ class CotLayer(nn.Module):
         # x has three consumers and k two: their gradients (two of them channel slices of the concat's) are summed by
         # one kernel each (fused.fan_out) instead of autograd's pairwise strided adds
         xk, xc, xv = fused.fan_out(x, 3)
-        k = fused.bn_act(self.key_embed[0](xk).contiguous(memory_format=cl), self.key_embed[1], relu=True)
+        be = self.train_conv_backend
+        if be.endswith("+k") and fused.tc_supported(x, self.dim) and self.key_embed[0].weight.dtype == x.dtype:
+            # key_embed on the haloed-tile tcgen05 convolution: forward with the BatchNorm statistics in the epilogue, data gradient by
+            # the same kernel (flipped / transposed weights); the grouped weight gradient stays on cuDNN
+            ke = self.key_embed
+            k = fused.TcConv3x3Fn.apply(xk, ke[0].weight, ke[1].weight, ke[1].bias, ke[1], ke[0].groups, True)
+            be = be[:-2]
+        else:
+            be = be[:-2] if be.endswith("+k") else be
+            k = fused.bn_act(self.key_embed[0](xk).contiguous(memory_format=cl), self.key_embed[1], relu=True)
         kc, kt = fused.fan_out(k, 2)
-        hybrid = (self.train_conv_backend in ("tc_e0", "tc_1x1", "tc_e0e3", "tc_all1x1") and fused.tc_supported(x, self.dim)
+        hybrid = (be in ("tc_e0", "tc_1x1", "tc_e0e3", "tc_all1x1") and fused.tc_supported(x, self.dim)
                   and k.dtype == x.dtype)
         if hybrid:      # embed.0 as ONE tcgen05 GEMM over the operand pairs (x, W_x), (k, W_k): no concat, statistics in the epilogue
             em = self.embed
@@ -119,11 +128,11 @@ class CotLayer(nn.Module):
         else:
             e = fused.bn_act(self.embed[0](torch.cat([xc, kc], dim=1)).contiguous(memory_format=cl), self.embed[1], relu=True)
         # embed.3 runs bias-free; its bias is added (and differentiated) inside the GroupNorm kernels
-        if hybrid and self.train_conv_backend in ("tc_e0e3", "tc_all1x1"):
+        if hybrid and be in ("tc_e0e3", "tc_all1x1"):
             l = fused.TcConv1x1Fn.apply(e, None, self.embed[3].weight, None, None, None, None, False, None)
         else:
             l = F.conv2d(e, self.embed[3].weight, None)
-        if hybrid and self.train_conv_backend in ("tc_1x1", "tc_all1x1"):
+        if hybrid and be in ("tc_1x1", "tc_all1x1"):
             cv = self.conv1x1
             v = fused.TcConv1x1Fn.apply(xv, None, cv[0].weight, None, cv[1].weight, cv[1].bias, cv[1], False, None)
         else:
@@ -195,15 +204,19 @@ class CotLayer(nn.Module):
         e = tc.gemm_bf16(x, p["we1x"], k, p["we1k"], scale=p["e_ss"][0], shift=p["e_ss"][1], relu=True)
         gc = fused.tap_chunk(C // 8)
         if self.eval_fused_agg and gc == 8 and H * W >= 32 and C <= 512 and p["ref"] is not None:
-            # logits in tap-major order + their per-sample column sums from ONE GEMM; GroupNorm becomes a per-(sample, column)
-            # affine applied inside the LocalConv kernel, which also does bn + SiLU and the pooled descriptor
+            # (opt-in, COTB200_EVAL_FUSED_AGG=1) logits in tap-major order + their per-sample column sums from ONE GEMM; GroupNorm
+            # becomes a per-(sample, column) affine applied inside the LocalConv kernel, which also does bn + SiLU and the pooled
+            # descriptor.  Fewer launches and HBM passes, but measured SLOWER than the separate kernels (profiles/r02_ncu_targets_callI.md:
+            # the in-place weight-tile prologue makes the kernel shared-memory-latency bound, 349 us against 125 us at stage 1).
             l, cs, cq = tc.gemm_bf16_samplestats(e, p["we2p"], H * W, shift=p["be2p"])
             v = tc.gemm_bf16(x, p["wv"], scale=p["v_ss"][0], shift=p["v_ss"][1])
             out = fused.cot_eval_tail_fused(v.view(B, H, W, C).permute(0, 3, 1, 2), l, cs, cq, None, p["gnw_p"], p["gnb_p"],
                                             float(self.embed[4].eps), gc, p["bn_ss"], k, self.se)
             if out is not None:
                 return out
-        if H * W >= 32:     # GroupNorm statistics from the logits GEMM's own epilogue: no statistics pass over l
+        if self.eval_samplestats and H * W >= 32:
+            # (opt-in) GroupNorm statistics from the logits GEMM's own epilogue: saves the statistics pass over l, but the per-sample
+            # epilogue costs more than gn72_stats does (104 vs 40 + 40 us at stage 1, same profile)
             l, cs, cq = tc.gemm_bf16_samplestats(e, p["we2"], H * W, shift=p["be2"])
             v = tc.gemm_bf16(x, p["wv"], scale=p["v_ss"][0], shift=p["v_ss"][1])
             J = l.shape[1]
@@ -238,8 +251,11 @@ class CotLayer(nn.Module):
     #: cudnn 42.80 ms, tc_e0 41.29 ms, tc_1x1 42.37 ms, tc 46.38 ms  ->  tc_e0 is the default (bf16 channels_last, dim % 64 == 0;
     #: anything else silently uses cuDNN for embed.0 as well).
     train_conv_backend = os.environ.get("COTB200_TRAIN_CONV", "tc_e0")
-    #: inference: GroupNorm-apply, LocalConv, bn + SiLU and the pooling in ONE kernel (cotb200_cot_agg_eval); 0 = separate kernels
-    eval_fused_agg = os.environ.get("COTB200_EVAL_FUSED_AGG", "1") != "0"
+    #: inference: GroupNorm-apply, LocalConv, bn + SiLU and the pooling in ONE kernel (cotb200_cot_agg_eval); default 0 = separate
+    #: kernels, which measure faster (11.65 -> 9.70 ms CoTNet-50 bs256 eval forward, profiles/r02_prof_cotnet50_eval_callI*.md)
+    eval_fused_agg = os.environ.get("COTB200_EVAL_FUSED_AGG", "0") != "0"
+    #: inference: GroupNorm statistics from the logits GEMM epilogue (cotb200_gemm_bf16_samplestats) instead of gn9_stats
+    eval_samplestats = os.environ.get("COTB200_EVAL_SAMPLESTATS", "0") != "0"
 
     def forward(self, x):
         B, C, H, W = x.shape

@@ -11,6 +11,7 @@
 //     registers across the rep channels; dW is 9 register accumulators per thread, no reduction (one owner per (pixel, tap));
 //   * 7x7 planes: floor(256 / 49) = 5 items per CTA so the CTA stays full.
 // One pass over every tensor: (2C + 9wc) elements per pixel forward, (3C + 9wc) + (C + 9wc) backward (dy, x, w in; dx, dw out).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace cotb200 {
@@ -29,22 +30,30 @@ agg3_plane_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __r
   float* bs = pl_sm + (size_t)ipc * rep * PP;         // [ipc][rep][PP] (dW only)
   const int tid = threadIdx.x;
   const int nsm = ipc * rep * PP * (DW ? 2 : 1);
+  __shared__ unsigned short s_hoff[256];              // pixel -> offset inside a haloed plane (the only division of the staging)
   for (int i = tid; i < nsm; i += 256) pl_sm[i] = 0.f;
+  if (tid < HW) { const int ph = tid / W; s_hoff[tid] = (unsigned short)((ph + 1) * Wp + (tid - ph * W) + 1); }
   __syncthreads();
   const int item0 = blockIdx.x * ipc;
-  // ---- stage the planes (fp32, haloed)
-  const int per_item = rep * HW;
-  for (int e = tid; e < ipc * per_item; e += 256) {
-    const int il = e / per_item, r = e - il * per_item;
-    const int item = item0 + il;
-    if (item >= items) break;
-    const int j = r / HW, p = r - j * HW;
-    const int n = item / wc, g = item - n * wc;
-    const int ph = p / W, pw = p - ph * W;
-    const int so = (il * rep + j) * PP + (ph + 1) * Wp + pw + 1;
-    const long long go = (long long)(g + j * wc) * HW + p;
-    as[so] = (float)to_acc(__ldg(a + n * a_sn + go));
-    if (DW) bs[so] = (float)to_acc(__ldg(b + n * b_sn + go));
+  // ---- stage the planes (fp32, haloed): warp w takes planes w, w + 8, ...; lanes walk the pixels of the plane (coalesced)
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nplanes = ipc * rep;
+    for (int pl = warp; pl < nplanes; pl += 8) {
+      const int il = pl / rep, j = pl - il * rep;
+      const int item = item0 + il;
+      if (item >= items) break;
+      const int n = item / wc, g = item - n * wc;
+      const T* ag = a + n * a_sn + (long long)(g + j * wc) * HW;
+      const T* bg = DW ? b + n * b_sn + (long long)(g + j * wc) * HW : nullptr;
+      float* ad = as + (size_t)pl * PP;
+      float* bd = bs + (size_t)pl * PP;
+      for (int p = lane; p < HW; p += 32) {
+        const int so = s_hoff[p];
+        ad[so] = (float)to_acc(__ldg(ag + p));
+        if (DW) bd[so] = (float)to_acc(__ldg(bg + p));
+      }
+    }
   }
   // ---- this thread's pixel and its 9 weights (global loads in flight across the barrier)
   const int il = tid / HW, p = tid - il * HW;
@@ -106,11 +115,14 @@ template <typename T>
 int nchw_plane_launch(int mode, int N, int C, int H, int W, int wc, long long x_sn, long long y_sn, long long w_sn, const T* a, const T* b,
                       const T* w, T* o1, T* o2, cudaStream_t st, int* rc) {
   if constexpr (std::is_same<T, double>::value) { return 0; } else {
-    static int disabled = -1;
-    if (disabled < 0) { const char* e = getenv("COTB200_AGG_PLANE"); disabled = (e && e[0] == '0') ? 1 : 0; }
-    if (disabled) return 0;
+    // COTB200_AGG_PLANE: 0 = off, 1 (default) = where it measured faster than the tiled kernels AND the reference's own kernels
+    // (backward on planes of >= 100 pixels: profiles/r02_bench_ref_kernels_callI.json), 2 = every small plane, forward included
+    static int level = -1;
+    if (level < 0) { const char* e = getenv("COTB200_AGG_PLANE"); level = e ? atoi(e) : 1; }
+    if (level <= 0) return 0;
     const int HW = H * W;
     if (HW > 256 || HW < 16 || C % wc) return 0;
+    if (level == 1 && (mode == 0 || HW < 100)) return 0;
     const int rep = C / wc;
     int ipc = 256 / HW;
     const int PP = (H + 2) * (W + 2);

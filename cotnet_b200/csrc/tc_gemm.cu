@@ -251,15 +251,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         // the store that read this buffer two slabs ago must have finished READING it (at most the latest group may be pending)
         if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll 1
+        // both 32-column halves of the slab are requested from TMEM before the single wait: one exposed TMEM round trip per slab
+        // instead of two (the epilogue is a latency chain: profiles/r02_ncu_targets_callI.md, wide-N tiles at 0.55-0.7 of the roof)
+        uint32_t rawA[32], rawB[32];
+        const bool hasB = (sl * 2 + 1) * 32 < p.bn;
+        tmem_ld32_issue(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn + sl * 64), rawA);
+        if (hasB) tmem_ld32_issue(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn + sl * 64 + 32), rawB);
+        tmem_ld_wait();
+#pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
+          if (cc == 1 && !hasB) break;
           const int c = sl * 2 + cc;
-          if (c * 32 >= p.bn) break;
-          uint32_t raw[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn + c * 32), raw);
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cc == 0 ? rawA[j] : rawB[j]);
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             const int col = c * 32 + j8 * 8;               // column inside the N tile
@@ -632,11 +637,13 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_co
         const int ro = q / p.Wp, co = q - ro * p.Wp;
         const bool ok = ro < p.R && co < p.W;
         const int prow = ro * p.W + co;                              // row of the compacted image
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * p.MB + mb) * 64 + c * 32), raw);
-          if (ok) {
+        uint32_t rawA[32], rawB[32];                                   // both halves of the 64 columns in flight, one wait
+        tmem_ld32_issue(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * p.MB + mb) * 64), rawA);
+        tmem_ld32_issue(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * p.MB + mb) * 64 + 32), rawB);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
               const int col = c * 32 + j8 * 8;
@@ -647,8 +654,10 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_co
               uint32_t pk[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float lo = fmaf(__uint_as_float(raw[j8 * 8 + 2 * e]), scv[2 * e], shv[2 * e]);
-                float hi = fmaf(__uint_as_float(raw[j8 * 8 + 2 * e + 1]), scv[2 * e + 1], shv[2 * e + 1]);
+                const uint32_t r0 = c == 0 ? rawA[j8 * 8 + 2 * e] : rawB[j8 * 8 + 2 * e];
+                const uint32_t r1 = c == 0 ? rawA[j8 * 8 + 2 * e + 1] : rawB[j8 * 8 + 2 * e + 1];
+                float lo = fmaf(__uint_as_float(r0), scv[2 * e], shv[2 * e]);
+                float hi = fmaf(__uint_as_float(r1), scv[2 * e + 1], shv[2 * e + 1]);
                 if (p.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
                 __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
                 pk[e] = *reinterpret_cast<uint32_t*>(&h2);
@@ -717,8 +726,10 @@ static int conv3x3_halo_launch(int B, int H, int W, int C, const void* X, long l
   if (mode == -2) { const char* e = getenv("COTB200_CONV_HALO"); mode = e ? atoi(e) : 1; }
   if (mode <= 0 || bn != 64 || C % 64 || W + 2 > 256 || ldx != C || ldd != C) return 0;
   const int Wpad = W + 2;
+  static int maxpx = -1;                      // COTB200_HALO_MAXPX: padded output pixels per work item (128 -> one M block, more ring stages)
+  if (maxpx < 0) { const char* e = getenv("COTB200_HALO_MAXPX"); maxpx = e ? atoi(e) : 256; if (maxpx < 128) maxpx = 128; if (maxpx > 256) maxpx = 256; }
   int R = 0;
-  for (int r = 1; r <= H; ++r) if (H % r == 0 && r * Wpad <= 256 && r * W <= 256) R = r;
+  for (int r = 1; r <= H; ++r) if (H % r == 0 && r * Wpad <= maxpx && r * W <= 256) R = r;
   if (R == 0) return 0;
   HcParams p{};
   p.B = B; p.H = H; p.W = W; p.C = C; p.R = R; p.Wp = Wpad; p.MB = (R * Wpad + 127) / 128;
