@@ -83,6 +83,7 @@ SYMBOLS = {
     "cotb200_stem7x7s2_scratch_bytes": (ctypes.c_longlong, [ctypes.c_int] * 3),
     "cotb200_stem7x7s2_bf16": (ctypes.c_int, [ctypes.c_int] * 3 + [_VP, _VP, ctypes.c_int, _VP, ctypes.c_longlong, _VP, _VP, ctypes.c_int,
                                               _VP, _VP, _VP, _VP]),
+    "cotb200_stem7x7s2_wgrad_bf16": (ctypes.c_int, [ctypes.c_int] * 3 + [_VP, ctypes.c_longlong, ctypes.c_int, _VP, _VP, _VP]),
     "cotb200_wgrad_bf16": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _VP, ctypes.c_longlong, ctypes.c_int, _VP, ctypes.c_longlong,
                                           ctypes.c_int, _VP, ctypes.c_longlong, _VP, ctypes.c_longlong, ctypes.c_int, _VP]),
     "cotb200_se_eval_scratch_bytes": (ctypes.c_longlong, [ctypes.c_int] * 2),

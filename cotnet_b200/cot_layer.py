@@ -110,7 +110,8 @@ class CotLayer(nn.Module):
         # one kernel each (fused.fan_out) instead of autograd's pairwise strided adds
         xk, xc, xv = fused.fan_out(x, 3)
         be = self.train_conv_backend
-        if be.endswith("+k") and fused.tc_supported(x, self.dim) and self.key_embed[0].weight.dtype == x.dtype:
+        if (be.endswith("+k") and self.dim <= self.tc_key_max_dim and fused.tc_supported(x, self.dim)
+                and self.key_embed[0].weight.dtype == x.dtype):
             # key_embed on the haloed-tile tcgen05 convolution: forward with the BatchNorm statistics in the epilogue, data gradient by
             # the same kernel (flipped / transposed weights); the grouped weight gradient stays on cuDNN
             ke = self.key_embed
@@ -251,6 +252,9 @@ class CotLayer(nn.Module):
     #: cudnn 42.80 ms, tc_e0 41.29 ms, tc_1x1 42.37 ms, tc 46.38 ms  ->  tc_e0 is the default (bf16 channels_last, dim % 64 == 0;
     #: anything else silently uses cuDNN for embed.0 as well).
     train_conv_backend = os.environ.get("COTB200_TRAIN_CONV", "tc_e0")
+    #: "+k" suffix of the backend: key_embed on the haloed-tile tcgen05 convolution for dim <= this (stages 1-2: there it beats
+    #: cuDNN's grouped kernels 94 vs 159 us and 57 vs 74-82 us per call, profiles/r02_bench_halo_callJ.json; at 14x14 / 7x7 cuDNN wins)
+    tc_key_max_dim = int(os.environ.get("COTB200_TC_KEY_MAX_DIM", "128"))
     #: inference: GroupNorm-apply, LocalConv, bn + SiLU and the pooling in ONE kernel (cotb200_cot_agg_eval); default 0 = separate
     #: kernels, which measure faster (11.65 -> 9.70 ms CoTNet-50 bs256 eval forward, profiles/r02_prof_cotnet50_eval_callI*.md)
     eval_fused_agg = os.environ.get("COTB200_EVAL_FUSED_AGG", "0") != "0"

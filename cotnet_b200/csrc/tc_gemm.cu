@@ -185,8 +185,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, warp-uniform; one elected lane issues) =====================
+    {
       const uint32_t idesc = umma_idesc(p.bn);
       int kbc = 0, ti = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
@@ -202,14 +202,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the 128 B swizzle atom: start-address field += 2
-            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              // advance 16 bf16 = 32 B inside the 128 B swizzle atom: start-address field += 2
+              umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
+            umma_commit(smem_u32(&s_empty[s]));           // frees the smem stage when the MMAs above retire
           }
-          umma_commit(smem_u32(&s_empty[s]));           // frees the smem stage when the MMAs above retire
+          __syncwarp();
         }
-        umma_commit(smem_u32(&s_tfull[acc]));            // accumulator of this tile complete
+        if (elect_one()) umma_commit(smem_u32(&s_tfull[acc]));            // accumulator of this tile complete
+        __syncwarp();
       }
     }
   } else {
@@ -580,8 +584,8 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, warp-uniform; one elected lane issues) =====================
+    {
       const uint32_t idesc = umma_idesc(64);
       mbar_wait(smem_u32(&s_wfull), 0);
       tc_fence_after();
@@ -597,19 +601,22 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_co
         mbar_wait(smem_u32(&s_full[s]), ph);
         tc_fence_after();
         const uint32_t ab = smem_u32(a_s + (size_t)s * p.a_stage_bytes);
-        for (int mb = 0; mb < p.MB; ++mb) {
-          const uint32_t tmem_d = tmem_base + (uint32_t)((acc * p.MB + mb) * 64);
+        if (elect_one()) {
+          for (int mb = 0; mb < p.MB; ++mb) {
+            const uint32_t tmem_d = tmem_base + (uint32_t)((acc * p.MB + mb) * 64);
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int row = mb * 128 + (t / 3) * p.Wp + (t % 3);          // first smem row of this tap's A operand
-            const uint64_t da = umma_desc_sw128_rows(ab + (uint32_t)row * 128u, p.base_off);
-            const uint64_t db = umma_desc_sw128(wb + (uint32_t)t * 8192u);
+            for (int t = 0; t < 9; ++t) {
+              const int row = mb * 128 + (t / 3) * p.Wp + (t % 3);          // first smem row of this tap's A operand
+              const uint64_t da = umma_desc_sw128_rows(ab + (uint32_t)row * 128u, p.base_off);
+              const uint64_t db = umma_desc_sw128(wb + (uint32_t)t * 8192u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (t | k) != 0);
+              for (int k = 0; k < 4; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (t | k) != 0);
+            }
           }
+          umma_commit(smem_u32(&s_empty[s]));
+          umma_commit(smem_u32(&s_tfull[acc]));
         }
-        umma_commit(smem_u32(&s_empty[s]));
-        umma_commit(smem_u32(&s_tfull[acc]));
+        __syncwarp();
       }
     }
   } else {

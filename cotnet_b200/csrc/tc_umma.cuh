@@ -10,6 +10,16 @@ namespace cotb200 {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a CONVERGED warp (the lowest): the MMA-issuer warp runs its loop warp-uniformly (descriptors and addresses stay in
+// uniform registers) and only the tcgen05.mma / tcgen05.commit instructions themselves are predicated on the elected lane.  With the
+// whole loop inside `if (lane == 0)` the compiler has to move every descriptor through R2UR + an ELECT waterfall per MMA (~15 SASS
+// instructions, ~100 cycles of issue latency each): kernels with many small MMAs per tile were issue-bound (profiles/r02_ncu_targets_callI.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO unused (=1), version 1.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);

@@ -36,6 +36,10 @@ struct WgParams {
   int kb_total;              // ceil(M / 64)
   int transpose;             // 0: OUT[r * ldo + c]   1: OUT[c * ldo + r]
   int lbo, sbo;              // UMMA descriptor offsets (bytes) -- see wg_desc_offsets()
+  int px;                    // pixels per pipeline stage (multiple of 16): 64, or one output row of the stem convolution
+  int stages;                // ring depth (<= WG_STAGES)
+  int stem_ho;               // > 0: B = the stem's window matrices (4-D map, csrc/tc_gemm.cu stem mode); pixel block kb = (sample kb / stem_ho,
+                             //      output row kb % stem_ho), column block j = s2d row tap a
   long long ldo;
   float* out;
 };
@@ -49,8 +53,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   __shared__ uint32_t s_tmem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nbb = p.bc / 64;                                   // B boxes per stage
-  const int a_bytes = 2 * WG_BOX_BYTES;
-  const int stage_bytes = a_bytes + nbb * WG_BOX_BYTES;
+  const int box_bytes = 128 * p.px;                            // one {64 ch, px pixels} bf16 box
+  const int a_bytes = 2 * box_bytes;
+  const int stage_bytes = a_bytes + nbb * box_bytes;
   // tile decode
   int t = blockIdx.x;
   const int split = t % p.splits; t /= p.splits;
@@ -82,39 +87,48 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (warp == 0) {
       if (lane == 0) {
         for (int i = 0; i < nkb; ++i) {
-          const int s = i % WG_STAGES;
-          const uint32_t ph = (i / WG_STAGES) & 1;
+          const int s = i % p.stages;
+          const uint32_t ph = (i / p.stages) & 1;
           mbar_wait(smem_u32(&s_empty[s]), ph ^ 1);
           const uint32_t full = smem_u32(&s_full[s]);
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
-          const int px = (kb_lo + i) * WG_PX;
+          const int px = (kb_lo + i) * p.px;
           mbar_expect_tx(full, (uint32_t)stage_bytes);            // TMA counts whole boxes (zero-filled parts included)
           tma_load_2d(sa, &mapA, full, r0, px);                    // out-of-range channels / pixels are zero-filled: they add 0
-          tma_load_2d(sa + WG_BOX_BYTES, &mapA, full, r0 + 64, px);
-          for (int j = 0; j < nbb; ++j) {
-            const int c = c0 + j * 64;
-            if (c < p.C1) tma_load_2d(sb + j * WG_BOX_BYTES, &mapB1, full, c, px);
-            else tma_load_2d(sb + j * WG_BOX_BYTES, &mapB2, full, c - p.C1, px);
+          tma_load_2d(sa + box_bytes, &mapA, full, r0 + 64, px);
+          if (p.stem_ho > 0) {
+            const int b = (kb_lo + i) / p.stem_ho, oh = (kb_lo + i) - b * p.stem_ho;
+            for (int j = 0; j < nbb; ++j)                          // tap a = c0 / 64 + j: the windows of s2d row oh - 2 + a
+              tma_load_4d(sb + j * box_bytes, &mapB1, full, 0, 0, oh - 2 + c0 / 64 + j, b);
+          } else {
+            for (int j = 0; j < nbb; ++j) {
+              const int c = c0 + j * 64;
+              if (c < p.C1) tma_load_2d(sb + j * box_bytes, &mapB1, full, c, px);
+              else tma_load_2d(sb + j * box_bytes, &mapB2, full, c - p.C1, px);
+            }
           }
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      {                                                          // whole warp, warp-uniform; one elected lane issues (tc_umma.cuh)
         const uint32_t idesc = umma_idesc_mn(WG_BR, p.bc);
         for (int i = 0; i < nkb; ++i) {
-          const int s = i % WG_STAGES;
-          const uint32_t ph = (i / WG_STAGES) & 1;
+          const int s = i % p.stages;
+          const uint32_t ph = (i / p.stages) & 1;
           mbar_wait(smem_u32(&s_full[s]), ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
           // MN blocks of 64 channels are WG_BOX_BYTES apart (LBO); 8-pixel K groups are 1024 B apart (SBO)
           const uint64_t da = umma_desc_mn_sw128(sa, p.lbo, p.sbo), db = umma_desc_mn_sw128(sb, p.lbo, p.sbo);
-#pragma unroll
-          for (int k = 0; k < WG_PX / 16; ++k)                     // 16 pixels = two 1024-byte atoms: start address += 2048 B
-            umma_f16(tmem_base, da + (uint64_t)(k * (2048 >> 4)), db + (uint64_t)(k * (2048 >> 4)), idesc, (i | k) != 0);
-          umma_commit(smem_u32(&s_empty[s]));
+          if (elect_one()) {
+            for (int k = 0; k < p.px / 16; ++k)                      // 16 pixels = two 1024-byte atoms: start address += 2048 B
+              umma_f16(tmem_base, da + (uint64_t)(k * (2048 >> 4)), db + (uint64_t)(k * (2048 >> 4)), idesc, (i | k) != 0);
+            umma_commit(smem_u32(&s_empty[s]));
+          }
+          __syncwarp();
         }
-        umma_commit(smem_u32(&s_tfull));
+        if (elect_one()) umma_commit(smem_u32(&s_tfull));
+        __syncwarp();
       }
     } else {
       // ===================== epilogue: TMEM -> registers -> global reductions =====================
@@ -205,6 +219,7 @@ extern "C" int cotb200_wgrad_bf16(int M, int R, const void* A, long long lda, in
   // MN blocks of 64 channels are one box (8 KB) apart = LBO; 8-pixel K groups are 1024 B apart = SBO (validated on the B200
   // against fp32 matmul; the swapped convention reads past the operand tiles).
   p.lbo = WG_BOX_BYTES; p.sbo = 1024;
+  p.px = WG_PX; p.stages = WG_STAGES; p.stem_ho = 0;
   CUtensorMap ma, mb1, mb2;
   int rc;
   if ((rc = wg_make_map(&ma, A, M, R, lda))) return rc;
@@ -220,4 +235,71 @@ extern "C" int cotb200_wgrad_bf16(int M, int R, const void* A, long long lda, in
   COTB200_PROF_B("tc_wgrad", 2.0 * (double)M * (R + Cc) + 4.0 * (double)R * Cc);
   tc_wgrad_kernel<<<tiles * splits, WG_THREADS, smem, st>>>(ma, mb1, mb2, p);
   return check_launch("tc_wgrad");
+}
+
+
+// Weight gradient of the stem convolution (cotb200_stem7x7s2_bf16), in the packed layout of its weight:
+//   dWm[n, a*64 + j] += sum over output pixels (b, oh, ow) of  dY[(b, oh, ow), n] * P-window[b, oh - 2 + a, ow][j]
+// P = the space-to-depth scratch image the forward call filled (B, H/2, W/2 + 4, 16).  One pipeline stage = one output row:
+// the dY rows of that output row as the A operand, the four tap windows (overlapping-window TMA map) as four B boxes.
+extern "C" int cotb200_stem7x7s2_wgrad_bf16(int B, int H, int W, const void* dY, long long ldy, int N, const void* scratch, float* dWm,
+                                            void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || N <= 0) { set_error("stem7x7s2_wgrad: bad dims"); return COTB200_EINVAL; }
+  if (!dY || !scratch || !dWm) { set_error("stem7x7s2_wgrad: NULL operand"); return COTB200_ENULL; }
+  const int Hh = H / 2, Wh = W / 2;
+  if ((H & 1) || (W & 1) || (Wh & 15) || Wh > 128 || (N & 7) || N > 128 || (reinterpret_cast<uintptr_t>(dWm) & 15)) {
+    set_error("stem7x7s2_wgrad: geometry not supported (W/2 = %d must be a multiple of 16, <= 128; N = %d <= 128)", Wh, N);
+    return COTB200_EUNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  WgParams p{};
+  p.M = B * Hh * Wh; p.R = N; p.Cc = 256; p.C1 = 256; p.transpose = 0; p.ldo = 256; p.out = dWm;
+  p.bc = 256; p.tiles_c = 1; p.tiles_r = 1;
+  p.px = Wh; p.stem_ho = Hh;
+  p.kb_total = B * Hh;
+  int splits = num_sms();
+  if (splits > p.kb_total) splits = p.kb_total;
+  const int per = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + per - 1) / per;
+  const int box_bytes = 128 * p.px;
+  p.lbo = box_bytes; p.sbo = 1024;
+  const int stage_bytes = 6 * box_bytes;
+  p.stages = (216 * 1024) / stage_bytes;
+  if (p.stages > WG_STAGES) p.stages = WG_STAGES;
+  if (p.stages < 2) { set_error("stem7x7s2_wgrad: row of %d pixels does not fit two pipeline stages", Wh); return COTB200_EUNSUPPORTED; }
+  CUtensorMap ma, mb;
+  TcEncodeTiledFn enc = tc_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return COTB200_EINVAL; }
+  {
+    if ((reinterpret_cast<uintptr_t>(dY) & 15) || ((ldy * 2) & 15)) { set_error("stem7x7s2_wgrad: dY not 16-byte aligned"); return COTB200_EALIGN; }
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)p.M};
+    cuuint64_t strides[1] = {(cuuint64_t)ldy * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)p.px};
+    cuuint32_t es[2] = {1, 1};
+    if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(dY), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(stem wgrad dY) failed"); return COTB200_EINVAL;
+    }
+  }
+  {
+    const long long Wp = Wh + 4;
+    cuuint64_t dims[4] = {64, (cuuint64_t)(Wh + 1), (cuuint64_t)Hh, (cuuint64_t)B};
+    cuuint64_t strides[3] = {32, (cuuint64_t)Wp * 32, (cuuint64_t)Wp * 32 * Hh};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.px, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(scratch), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(stem wgrad windows) failed"); return COTB200_EUNSUPPORTED;
+    }
+  }
+  const int smem = p.stages * stage_bytes + 1024;
+  static PerDevFlag configured_d;
+  if (bool& configured = configured_d.get(); !configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  COTB200_PROF_B("tc_stem_wgrad", 2.0 * (double)p.M * N + (double)B * Hh * (Wh + 4) * 32 + 4.0 * N * 256);
+  tc_wgrad_kernel<<<p.splits, WG_THREADS, smem, st>>>(ma, mb, mb, p);
+  return check_launch("tc_stem_wgrad");
 }

@@ -831,13 +831,15 @@ class StemConvBNFn(Function):
         xd = x.detach()
         wm = _tc.prepare_stem_weight(weight)
         out = torch.empty((B, N, H // 2, W // 2), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
-        pre = scale = mean = rstd = None
+        pre = scale = mean = rstd = scratch = None
         batch = bn.training or bn.running_mean is None
         if batch:
             sums = _zeros((2, N,), x.device)
             pre = torch.empty_like(out, memory_format=torch.channels_last)
-            if _tc.stem7x7s2_bf16(xd, wm, stats=(sums[0], sums[1]), out=pre) is None:
+            r = _tc.stem7x7s2_bf16(xd, wm, stats=(sums[0], sums[1]), out=pre, return_scratch=True)
+            if r is None:
                 raise RuntimeError("cotb200 stem7x7s2: geometry not supported")
+            scratch = r[1]
             ss = _bn_apply_batch(pre, None, sums, bn, bn_w, bn_b, relu, out, lib, st, dt)
             scale, shift, mean, rstd = ss[0], ss[1], ss[2], ss[3]
         else:
@@ -846,13 +848,13 @@ class StemConvBNFn(Function):
                 raise RuntimeError("cotb200 stem7x7s2: geometry not supported")
             if any(ctx.needs_input_grad):
                 pre = _tc.stem7x7s2_bf16(xd, wm)
-        ctx.save_for_backward(xd, weight.detach(), pre, out if relu else None, scale, mean, rstd)
+        ctx.save_for_backward(xd, weight.detach(), pre, out if relu else None, scale, mean, rstd, scratch)
         ctx.cfg = (relu, batch, bn_w.dtype)
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, pre, y, scale, mean, rstd = ctx.saved_tensors
+        x, weight, pre, y, scale, mean, rstd, scratch = ctx.saved_tensors
         relu, batch, bndt = ctx.cfg
         B, N, Ho, Wo = dy.shape
         M = B * Ho * Wo
@@ -872,12 +874,19 @@ class StemConvBNFn(Function):
         if ctx.needs_input_grad[0]:
             dx = torch.nn.grad.conv2d_input(x.shape, wq, dpre, stride=2, padding=3)
         if ctx.needs_input_grad[1]:
-            dw = torch.nn.grad.conv2d_weight(x, weight.shape, dpre, stride=2, padding=3).to(weight.dtype)
+            # weight gradient on the MN-major tcgen05 wgrad kernel over the space-to-depth image of the forward (one stage = one
+            # output row, the four row taps as four B boxes); geometries it does not take: cuDNN
+            if scratch is not None and stem_wgrad_tc:
+                dw = _tc.stem7x7s2_wgrad(dpre, scratch, x.shape, N)
+            if dw is None:
+                dw = torch.nn.grad.conv2d_weight(x, weight.shape, dpre, stride=2, padding=3)
+            dw = dw.to(weight.dtype)
         return dx, dw, sums[1].to(bndt), sums[0].to(bndt), None, None
 
 
 #: the trunk's 7x7 stem convolution on the tcgen05 implicit GEMM (0 = cuDNN, the round-1 path)
 stem_tc = _os.environ.get("COTB200_STEM_TC", "1") != "0"
+stem_wgrad_tc = _os.environ.get("COTB200_STEM_WGRAD_TC", "1") != "0"
 
 
 def stem_conv_bn(x, conv, bn, relu=True):

@@ -143,7 +143,7 @@ def prepare_stem_weight(weight):
     return wm.reshape(N, 256).to(torch.bfloat16).contiguous()
 
 
-def stem7x7s2_bf16(x, wm, scale=None, shift=None, relu=False, stats=None, out=None):
+def stem7x7s2_bf16(x, wm, scale=None, shift=None, relu=False, stats=None, out=None, return_scratch=False):
     """x: channels_last bf16 [B,3,H,W] -> channels_last bf16 [B,N,H/2,W/2] = conv 7x7 / stride 2 / pad 3 with the prepared weight
     wm (prepare_stem_weight).  Returns None when the library cannot take the geometry (COTB200_EUNSUPPORTED)."""
     assert x.dim() == 4 and x.shape[1] == 3 and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
@@ -159,4 +159,26 @@ def stem7x7s2_bf16(x, wm, scale=None, shift=None, relu=False, stats=None, out=No
     if rc == -7:
         return None
     _lib.check(rc, "stem7x7s2_bf16")
-    return out
+    return (out, scratch) if return_scratch else out
+
+
+def unpack_stem_weight_grad(dwm):
+    """[N, 256] gradient in the packed layout of prepare_stem_weight -> [N, 3, 7, 7] (the inverse gather: packed entries that stand for
+    kernel index -1 or for the pad channels have no counterpart and are dropped)."""
+    N = dwm.shape[0]
+    g = dwm.view(N, 4, 4, 16)[..., :12].reshape(N, 4, 4, 2, 2, 3)       # [n, a, a2, di, dj, c]
+    g = g.permute(0, 5, 1, 3, 2, 4).reshape(N, 3, 8, 8)                  # [n, c, 2a+di, 2a2+dj]
+    return g[:, :, 1:, 1:].contiguous()
+
+
+def stem7x7s2_wgrad(dy, scratch, x_shape, N):
+    """dW [N, 3, 7, 7] fp32 of the stem convolution from dy (channels_last bf16 [B, N, H/2, W/2]) and the space-to-depth scratch image
+    of the forward call; None when the library cannot take the geometry."""
+    B, _, H, W = x_shape
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous(memory_format=torch.channels_last)
+    dwm = torch.zeros(N, 256, dtype=torch.float32, device=dy.device)
+    rc = _lib.load().cotb200_stem7x7s2_wgrad_bf16(B, H, W, dy.data_ptr(), N, N, scratch.data_ptr(), dwm.data_ptr(), _lib.stream_ptr(dy))
+    if rc == -7:
+        return None
+    _lib.check(rc, "stem7x7s2_wgrad_bf16")
+    return unpack_stem_weight_grad(dwm)

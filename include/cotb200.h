@@ -299,6 +299,13 @@ int cotb200_stem7x7s2_bf16(int B, int H, int W, const void* X, const void* Wm, i
                            const float* scale, const float* shift, int relu, float* col_sum, float* col_sqsum,
                            void* scratch, void* stream);
 
+/* cotb200_stem7x7s2_wgrad_bf16: weight gradient of that convolution in the packed layout of Wm (cuDNN wgrad in the reference's
+ *   autograd graph):  dWm[n, a*64 + j] += sum_px dY[px, n] * window_a(px)[j], fp32 [N, 256], ZEROED by the caller.  dY [B*(H/2)*(W/2), N]
+ *   bf16 (row pitch ldy); scratch = the space-to-depth image cotb200_stem7x7s2_bf16 filled for the same X.  One pipeline stage of
+ *   the MN-major tcgen05 wgrad kernel = one output row (W/2 pixels, a multiple of 16, <= 128).  COTB200_EUNSUPPORTED otherwise. */
+int cotb200_stem7x7s2_wgrad_bf16(int B, int H, int W, const void* dY, long long ldy, int N, const void* scratch, float* dWm,
+                                 void* stream);
+
 /* cotb200_wgrad_bf16: weight gradient of a 1x1 convolution,  OUT += A[M,R]^T [B1[M,C1] | B2[M,C2]]  (contraction over the M
  *   pixels; A = dY, B = the convolution input(s); bf16 operands, fp32 accumulation in TMEM, fp32 OUT).  Replaces cuDNN's wgrad
  *   for embed.0 / embed.3 / conv1x1.0 (models/cotnet.py:52,55,60) and the bottleneck's 1x1 convolutions (:228-264).

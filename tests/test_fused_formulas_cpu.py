@@ -190,3 +190,10 @@ def test_stem_space_to_depth_weight_packing():
         out += win @ wm[:, a * 64:(a + 1) * 64].t()
     assert (out.permute(0, 3, 1, 2) - want_q).abs().max() < 1e-9
     assert (out.permute(0, 3, 1, 2) - want).abs().max() < 0.2
+
+
+def test_stem_weight_grad_unpack_is_inverse_of_packing():
+    from cotnet_b200 import tc
+    torch.manual_seed(4)
+    w = torch.randn(8, 3, 7, 7).bfloat16().float()
+    assert torch.equal(tc.unpack_stem_weight_grad(tc.prepare_stem_weight(w).float()), w)

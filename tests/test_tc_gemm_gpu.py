@@ -297,3 +297,20 @@ def test_stem_conv_bn_autograd_vs_cudnn_path():
     bn.eval(); bn2.eval()
     with torch.no_grad():
         _close(fused.stem_conv_bn(x, conv, bn, relu=True), fused.bn_act(conv2(x).contiguous(memory_format=torch.channels_last), bn2, relu=True), 2e-2)
+
+
+@pytest.mark.parametrize("B,H,W,N", [(2, 224, 224, 64), (3, 64, 96, 64), (5, 32, 160, 32)])
+def test_stem7x7s2_wgrad_vs_conv2d_weight(B, H, W, N):
+    """Weight gradient of the stem convolution on the MN-major tcgen05 kernel (one stage = one output row over the space-to-depth
+    image) against fp32 torch math on the same bf16 operands."""
+    g = torch.Generator(device="cuda").manual_seed(B + H)
+    x = torch.randn(B, 3, H, W, generator=g, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(N, 3, 7, 7, generator=g, device="cuda") / 12).bfloat16()
+    dy = torch.randn(B, N, H // 2, W // 2, generator=g, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    tc = _tc()
+    out, scratch = tc.stem7x7s2_bf16(x, tc.prepare_stem_weight(w), return_scratch=True)
+    got = tc.stem7x7s2_wgrad(dy, scratch, x.shape, N)
+    assert got is not None, "stem wgrad geometry refused"
+    want = torch.nn.grad.conv2d_weight(x.float(), w.shape, dy.float(), stride=2, padding=3)
+    rel = ((got - want).norm() / want.norm()).item()
+    assert got.shape == want.shape and rel <= 2e-3, rel
