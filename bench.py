@@ -255,6 +255,11 @@ def main_reference(a):
 
 
 # ----------------------------------------------------------------------------------------------- our arm
+def _train_backend():
+    from cotnet_b200.cot_layer import CotLayer
+    return CotLayer.train_conv_backend
+
+
 def build_model(name, **kw):
     from cotnet_b200 import backbone, backbone_hybrid
     ctor = backbone.MODELS.get(name) or backbone_hybrid.MODELS.get(name)
@@ -507,10 +512,14 @@ def main_ours(a):
                        "l2": "per-step working set (activations, several GB) >> 126 MB L2; no explicit flush needed",
                        "step": "cotnet_b200.trainer.TrainStep: weights %s, gradient bucket %s, %d comm chunk(s), overlap %s"
                                % (a.weights, str(ts.G_big.dtype), len(ts.plan["chunks"]), ts.overlap),
-                       "cot_path": "libcotb200: LocalConv fwd/dX/dW, GroupNorm(9 taps) fwd/bwd, bn+SiLU+pool+radix-2 "
-                                   "recombination fwd/bwd (also SplitAttnConv2d's tail), fused BatchNorm(+ReLU,+residual), NHWC "
-                                   "pooling, gradient fan-in, embed.0 = tcgen05 two-pair GEMM, gradient gather + SGD/EMA/bf16-copy "
-                                   "kernel, uint8->bf16 NHWC normalise; remaining convolutions cuDNN"},
+                       "cot_path": "libcotb200 (train_conv_backend=%s): LocalConv fwd/dX/dW, GroupNorm(9 taps) fwd/bwd, bn+SiLU+pool+"
+                                   "radix-2 recombination fwd/bwd (also SplitAttnConv2d's tail), fused BatchNorm(+ReLU,+residual), NHWC pooling, "
+                                   "gradient fan-in; tcgen05: the block's 1x1 convolutions (embed.0 concat-free two-pair GEMM, embed.3, conv1x1) "
+                                   "fwd + dgrad + wgrad with BatchNorm statistics in the epilogue, key_embed 3x3 grouped conv on the haloed-tile "
+                                   "kernel (dim <= 128), the bottleneck's 1x1 convolutions of stages 1-2, the 7x7 stem as a 4-tap implicit GEMM "
+                                   "(+ its weight gradient); gradient gather + SGD/EMA/bf16-copy kernel, uint8->bf16 NHWC normalise; cuDNN: "
+                                   "grouped 3x3 at 14x14 / 7x7 and its weight gradients, bottleneck 1x1 convolutions of stages 3-4, fc"
+                                   % _train_backend()},
             "e2e": e2e, "gpu_launches": int(launches), "launch_mode": graph_info, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
         line.update(extra)

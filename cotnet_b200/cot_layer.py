@@ -244,14 +244,20 @@ class CotLayer(nn.Module):
         u = fused.AggTapFn.apply(v, w, 1, gc)
         return fused.cot_tail(u, k, self.bn, self.se)
 
-    #: "tc" = tcgen05 kernels for the block's convolutions also when autograd is on; "cudnn" = cuDNN convolutions +
-    #: fused normalisation kernels.  Inference (no_grad, eval) always takes the tcgen05 path when the shape allows.
-    #: "tc_e0" / "tc_1x1": hybrids of the fused path -- only embed.0 (concat-free two-pair GEMM) / embed.0 and conv1x1 on
-    #: the tcgen05 kernels, the 3x3 key convolution and embed.3 stay on cuDNN.
-    #: Measured inside the whole CoTNet-50 bs256 training step (CUDA graph, profiles/r01_bench_conv_backends_run18.json):
-    #: cudnn 42.80 ms, tc_e0 41.29 ms, tc_1x1 42.37 ms, tc 46.38 ms  ->  tc_e0 is the default (bf16 channels_last, dim % 64 == 0;
-    #: anything else silently uses cuDNN for embed.0 as well).
-    train_conv_backend = os.environ.get("COTB200_TRAIN_CONV", "tc_e0")
+    #: Training-mode convolution backend of the block (COTB200_TRAIN_CONV):
+    #:   "cudnn"      cuDNN convolutions + the fused normalisation kernels
+    #:   "tc_e0"      embed.0 (the 2C -> C/2 conv on [x ; k]) as ONE concat-free two-operand-pair tcgen05 GEMM: forward with the
+    #:                BatchNorm statistics in the epilogue, data and weight gradients on the tcgen05 kernels
+    #:   "tc_1x1" / "tc_e0e3" / "tc_all1x1"   + conv1x1 / + embed.3 / + both (all three 1x1 convolutions of the block; with
+    #:                "tc_all1x1" the enclosing bottleneck's conv1 / conv3 / downsample of stages 1-2 as well, fused.conv1x1_bn)
+    #:   "...+k"      key_embed (grouped 3x3) on the haloed-tile tcgen05 convolution for dim <= tc_key_max_dim
+    #:   "tc"         the older all-tcgen05 autograd path (TcConv3x3Fn + TcConv1x1Fn for everything, per-tap conv at 7x7)
+    #: Inference (no_grad, eval) always takes the tcgen05 path when the shape allows.
+    #: Measured inside the whole CoTNet-50 bs256 training step (one CUDA graph, same box, profiles/r02_bench_cotnet50_callK_*.json):
+    #: tc_e0 39.23 ms, tc_e0+k 38.89, tc_all1x1 38.62, tc_all1x1+k 38.35  ->  "tc_all1x1+k" is the default (bf16 channels_last,
+    #: dim % 64 == 0; anything else uses cuDNN for that convolution).  Round 1 (before the warp-uniform MMA issue and the haloed
+    #: convolution): cudnn 42.80, tc_e0 41.29, tc 46.38 (profiles/r01_bench_conv_backends_run18.json).
+    train_conv_backend = os.environ.get("COTB200_TRAIN_CONV", "tc_all1x1+k")
     #: "+k" suffix of the backend: key_embed on the haloed-tile tcgen05 convolution for dim <= this (stages 1-2: there it beats
     #: cuDNN's grouped kernels 94 vs 159 us and 57 vs 74-82 us per call, profiles/r02_bench_halo_callJ.json; at 14x14 / 7x7 cuDNN wins)
     tc_key_max_dim = int(os.environ.get("COTB200_TC_KEY_MAX_DIM", "128"))
@@ -329,7 +335,7 @@ class CoXtLayer(nn.Module):
         kc, kt = fused.fan_out(k, 2)
         wx, wk = _coxt_embed0_dense(self.embed[0].weight, G)
         w0 = torch.cat([wx, wk], 1).reshape(C // 2, 2 * C, 1, 1)
-        be = self.train_conv_backend
+        be = self.train_conv_backend.replace("+k", "")      # the grouped key conv of CoXt (groups 8, dense block-diagonal) stays on cuDNN
         use_tc = be != "cudnn" and x.dtype == torch.bfloat16 and C % 16 == 0 and k.dtype == x.dtype and w0.dtype == x.dtype
         em, cv = self.embed, self.conv1x1
         if use_tc:
@@ -353,7 +359,7 @@ class CoXtLayer(nn.Module):
         u = fused.AggTapFn.apply(v.contiguous(memory_format=torch.channels_last), w, self.dw_group, gc)
         return fused.cot_tail(u, kt.contiguous(memory_format=torch.channels_last), self.bn, self.se)
 
-    train_conv_backend = os.environ.get("COTB200_TRAIN_CONV", "tc_e0")
+    train_conv_backend = os.environ.get("COTB200_TRAIN_CONV", "tc_all1x1+k")
 
     def forward(self, x):
         B, C, H, W = x.shape

@@ -904,7 +904,7 @@ def stem_conv_bn(x, conv, bn, relu=True):
 #: which 1x1 convolutions of the ENCLOSING bottleneck (conv1 / conv3 / stride-1 downsample) run on the tcgen05 kernels in
 #: training: "tc_all1x1" = all of them (forward with the BatchNorm statistics in the epilogue, data and weight gradients),
 #: anything else = cuDNN + the fused BatchNorm kernels.  Same environment variable as CotLayer.train_conv_backend.
-trunk_conv_backend = _os.environ.get("COTB200_TRAIN_CONV", "tc_e0").replace("+k", "")
+trunk_conv_backend = _os.environ.get("COTB200_TRAIN_CONV", "tc_all1x1+k").replace("+k", "")
 
 
 #: the bottleneck convolutions of stages 3-4 (weights of 256K .. 1M elements, 12.5K-50K pixels) are compute-shaped; measured per
