@@ -110,6 +110,8 @@ class CotLayer(nn.Module):
         # one kernel each (fused.fan_out) instead of autograd's pairwise strided adds
         xk, xc, xv = fused.fan_out(x, 3)
         be = self.train_conv_backend
+        if B * H * W < self.tc_min_pixels and be not in ("cudnn", "tc_e0"):
+            be = "tc_e0"           # small problems: only the concat-free embed.0 GEMM stays on tcgen05 (fixed per-launch costs dominate)
         if (be.endswith("+k") and self.dim <= self.tc_key_max_dim and fused.tc_supported(x, self.dim)
                 and self.key_embed[0].weight.dtype == x.dtype):
             # key_embed on the haloed-tile tcgen05 convolution: forward with the BatchNorm statistics in the epilogue, data gradient by
@@ -261,6 +263,8 @@ class CotLayer(nn.Module):
     #: "+k" suffix of the backend: key_embed on the haloed-tile tcgen05 convolution for dim <= this (stages 1-2: there it beats
     #: cuDNN's grouped kernels 94 vs 159 us and 57 vs 74-82 us per call, profiles/r02_bench_halo_callJ.json; at 14x14 / 7x7 cuDNN wins)
     tc_key_max_dim = int(os.environ.get("COTB200_TC_KEY_MAX_DIM", "128"))
+    #: pixels (B*H*W) below which the backend degrades to "tc_e0"
+    tc_min_pixels = int(os.environ.get("COTB200_TC_MIN_PIXELS", "0"))
     #: inference: GroupNorm-apply, LocalConv, bn + SiLU and the pooling in ONE kernel (cotb200_cot_agg_eval); default 0 = separate
     #: kernels, which measure faster (11.65 -> 9.70 ms CoTNet-50 bs256 eval forward, profiles/r02_prof_cotnet50_eval_callI*.md)
     eval_fused_agg = os.environ.get("COTB200_EVAL_FUSED_AGG", "0") != "0"
@@ -359,7 +363,9 @@ class CoXtLayer(nn.Module):
         u = fused.AggTapFn.apply(v.contiguous(memory_format=torch.channels_last), w, self.dw_group, gc)
         return fused.cot_tail(u, kt.contiguous(memory_format=torch.channels_last), self.bn, self.se)
 
-    train_conv_backend = os.environ.get("COTB200_TRAIN_CONV", "tc_all1x1+k")
+    #: CoXt: the dense block-diagonal form of its grouped 1x1 convolutions doubles their FLOPs; measured in the CoTNeXt-50 step
+    #: (profiles/r02_bench_cotnext50_callL*.json): tc_e0 61.20 ms, tc_all1x1 61.84 ms -> only embed.0 on the two-pair GEMM
+    train_conv_backend = os.environ.get("COTB200_TRAIN_CONV_COXT", "tc_e0")
 
     def forward(self, x):
         B, C, H, W = x.shape

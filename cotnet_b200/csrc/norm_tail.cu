@@ -60,6 +60,17 @@ __device__ __forceinline__ void cta_col_reduce(float (&acc)[NS][VEC], float* sm,
   __syncthreads();
 }
 
+// dst[c] += src[c] for c < C: the CTA's column totals leave as 16-byte vector reductions (red.global.add.v4.f32: one L2 atomic
+// transaction per four columns) where the destination allows, scalar atomics otherwise.
+__device__ __forceinline__ void red_add_cols(float* __restrict__ dst, const float* __restrict__ src, int C) {
+  if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    for (int c = threadIdx.x * 4; c < C; c += NT_THREADS * 4)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(src[c]), "f"(src[c + 1]), "f"(src[c + 2]), "f"(src[c + 3]) : "memory");
+  } else {
+    for (int c = threadIdx.x; c < C; c += NT_THREADS) atomicAdd(dst + c, src[c]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ column statistics
 // sum[c] += sum_rows x, sq[c] += sum_rows x^2       (BatchNorm batch statistics of u, models/cotnet.py:89)
 template <typename T, int VEC>
@@ -82,10 +93,8 @@ col_stats_kernel(const T* __restrict__ x, float* __restrict__ sum, float* __rest
     }
   }
   cta_col_reduce<2, VEC>(acc, sm, g, tx, ty, active);
-  for (int c = threadIdx.x; c < g.C; c += NT_THREADS) {
-    atomicAdd(sum + c, sm[c]);
-    atomicAdd(sq + c, sm[g.ry * g.C + c]);
-  }
+  red_add_cols(sum, sm, g.C);
+  red_add_cols(sq, sm + g.ry * g.C, g.C);
 }
 
 // ------------------------------------------------------------------------------------------------ tail forward
@@ -116,7 +125,7 @@ tail_pool_kernel(const T* __restrict__ u, const T* __restrict__ k, const float* 
     }
   }
   cta_col_reduce<1, VEC>(acc, sm, g, tx, ty, active);
-  for (int c = threadIdx.x; c < g.C; c += NT_THREADS) atomicAdd(psum + (long long)b * g.C + c, sm[c]);
+  red_add_cols(psum + (long long)b * g.C, sm, g.C);
 }
 
 // out = a0 * silu(u*scale+shift) + a1 * k        a: [B, C, 2] fp32          (models/cotnet.py:101-104)
@@ -225,10 +234,8 @@ tail_bwd_dz_sums_kernel(const T* __restrict__ dout, const T* __restrict__ u, con
     }
   }
   cta_col_reduce<2, VEC>(acc, sm, g, tx, ty, active);
-  for (int c = threadIdx.x; c < g.C; c += NT_THREADS) {
-    atomicAdd(sum_dz + c, sm[c]);
-    atomicAdd(sum_dzx + c, sm[g.ry * g.C + c]);
-  }
+  red_add_cols(sum_dz, sm, g.C);
+  red_add_cols(sum_dzx, sm + g.ry * g.C, g.C);
 }
 
 // du = scale * (dz - c1 - xhat*c2)   [c1 = sum_dz/n, c2 = sum_dzx/n in training; 0 in eval]
@@ -365,10 +372,8 @@ bn_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* _
     }
   }
   cta_col_reduce<2, VEC>(acc, sm, g, tx, ty, active);
-  for (int c = threadIdx.x; c < g.C; c += NT_THREADS) {
-    atomicAdd(sum_dz + c, sm[c]);
-    atomicAdd(sum_dzx + c, sm[g.ry * g.C + c]);
-  }
+  red_add_cols(sum_dz, sm, g.C);
+  red_add_cols(sum_dzx, sm + g.ry * g.C, g.C);
 }
 
 // dx = scale * (dz - c1 - xhat*c2)   (c1 = c2 = 0 in eval mode);   dres = dz when RES
@@ -623,15 +628,21 @@ static int make_geo(RowsGeo& g, int B, int HW, int C, int vec, int nsums, size_t
   while (g.cq_pad < g.cq) g.cq_pad <<= 1;
   if (g.cq_pad > NT_THREADS) { set_error("norm/tail kernel: %d channels exceed the %d-packet row limit", C, NT_THREADS); return COTB200_EINVAL; }
   g.ry = NT_THREADS / g.cq_pad;
-  // rows per CTA: enough CTAs to fill the machine (>= ~6 waves of 148), at least 2 rows per lane when possible
-  long long want = (long long)num_sms() * 6;
-  int chunks = (int)((want + B - 1) / B);
-  if (chunks < 1) chunks = 1;
-  int rows = (HW + chunks - 1) / chunks;
-  // every CTA ends with one atomic per column: give it enough rows to amortise them (wide, short tensors otherwise
-  // spend their time in atomics: 2048 channels x 49 rows)
-  int min_rows = g.ry * 4;
-  if (min_rows < 64) min_rows = 64;
+  // rows per CTA: the CTA count along the rows is a whole multiple k of the SM count (k = 6 .. 1: no partial last wave) with at
+  // least `min_rows` rows each, so that the closing column reductions (vector reds, one per four columns per CTA) stay amortised.
+  // Short, wide tensors (the 7x7 stage: 12 544 rows x 512..2048 channels) used to get 196 CTAs of 64 rows -- 1.3 waves of ONE
+  // 256-thread CTA per SM, latency-bound at ~0.25 of the roof; they now get 3-4 CTAs per SM.
+  int min_rows = g.ry * 2;
+  if (min_rows < 24) min_rows = 24;
+  const int sms = num_sms();
+  int rows = HW;
+  for (int k = 6; k >= 1; --k) {
+    const long long ctas = (long long)sms * k;
+    const int per_b = (int)((ctas + B - 1) / B);           // row chunks per sample
+    const int r = (HW + per_b - 1) / per_b;
+    rows = r;
+    if (r >= min_rows) break;
+  }
   if (rows < min_rows) rows = min_rows;
   if (rows > HW) rows = HW;
   g.rows_per_cta = rows;

@@ -912,6 +912,9 @@ trunk_conv_backend = _os.environ.get("COTB200_TRAIN_CONV", "tc_all1x1+k").replac
 TC_TRUNK_MAX_WEIGHT = int(_os.environ.get("COTB200_TC_TRUNK_MAX_WEIGHT", str(128 * 1024)))
 
 
+TC_MIN_PIXELS = int(_os.environ.get("COTB200_TC_MIN_PIXELS", "0"))
+
+
 def conv1x1_bn(x, conv, bn, relu, res=None):
     """act(BN(conv1x1(x)) (+ res)) for the bottleneck's 1x1 convolutions (models/cotnet.py:229-235,249-262): on the tcgen05
     GEMMs when the backend says so and the geometry allows (bf16 channels_last, stride 1, dense, no bias), else cuDNN + the
@@ -919,7 +922,8 @@ def conv1x1_bn(x, conv, bn, relu, res=None):
     w = conv.weight
     if (trunk_conv_backend == "tc_all1x1" and x.dtype == torch.bfloat16 and supported(x) and conv.kernel_size == (1, 1)
             and conv.stride == (1, 1) and conv.groups == 1 and conv.bias is None and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0
-            and w.shape[0] * w.shape[1] <= TC_TRUNK_MAX_WEIGHT and (torch.is_grad_enabled() or not bn.training)):
+            and w.shape[0] * w.shape[1] <= TC_TRUNK_MAX_WEIGHT and x.shape[0] * x.shape[2] * x.shape[3] >= TC_MIN_PIXELS
+            and (torch.is_grad_enabled() or not bn.training)):
         return TcConv1x1Fn.apply(x, None, w, None, bn.weight, bn.bias, bn, relu, res)
     return bn_act(conv(x).contiguous(memory_format=torch.channels_last), bn, relu=relu, res=res)
 
