@@ -263,8 +263,10 @@ class CotLayer(nn.Module):
     #: "+k" suffix of the backend: key_embed on the haloed-tile tcgen05 convolution for dim <= this (stages 1-2: there it beats
     #: cuDNN's grouped kernels 94 vs 159 us and 57 vs 74-82 us per call, profiles/r02_bench_halo_callJ.json; at 14x14 / 7x7 cuDNN wins)
     tc_key_max_dim = int(os.environ.get("COTB200_TC_KEY_MAX_DIM", "128"))
-    #: pixels (B*H*W) below which the backend degrades to "tc_e0"
-    tc_min_pixels = int(os.environ.get("COTB200_TC_MIN_PIXELS", "0"))
+    #: pixels (B*H*W) below which the backend degrades to "tc_e0": on the 14x14 / 7x7 stages the fixed per-launch costs of the
+    #: all-tcgen05 path outweigh its byte savings (one box, profiles/r02_bench_callM_*.json: CoTNet-50 bs256 38.99 -> 38.90 ms,
+    #: SE-CoTNetD-101 bs128 43.58 -> 43.23, SE-CoTNetD-152 320^2 bs64 67.77 -> 67.48 with the threshold at 100 000)
+    tc_min_pixels = int(os.environ.get("COTB200_TC_MIN_PIXELS", "100000"))
     #: inference: GroupNorm-apply, LocalConv, bn + SiLU and the pooling in ONE kernel (cotb200_cot_agg_eval); default 0 = separate
     #: kernels, which measure faster (11.65 -> 9.70 ms CoTNet-50 bs256 eval forward, profiles/r02_prof_cotnet50_eval_callI*.md)
     eval_fused_agg = os.environ.get("COTB200_EVAL_FUSED_AGG", "0") != "0"

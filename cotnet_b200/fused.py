@@ -912,7 +912,7 @@ trunk_conv_backend = _os.environ.get("COTB200_TRAIN_CONV", "tc_all1x1+k").replac
 TC_TRUNK_MAX_WEIGHT = int(_os.environ.get("COTB200_TC_TRUNK_MAX_WEIGHT", str(128 * 1024)))
 
 
-TC_MIN_PIXELS = int(_os.environ.get("COTB200_TC_MIN_PIXELS", "0"))
+TC_MIN_PIXELS = int(_os.environ.get("COTB200_TC_MIN_PIXELS", "100000"))
 
 
 def conv1x1_bn(x, conv, bn, relu, res=None):

@@ -249,7 +249,7 @@ def _grad_errors(grads, g):
 
 
 @pytest.mark.parametrize("model_name,fixture", [("cotnet50", "cotnet50_train_bf16w.npz"), ("cotnext50_2x48d", "cotnext50_train_bf16w.npz")])
-def test_bench_path_matches_reference_golden(model_name, fixture):
+def test_bench_path_matches_reference_golden(model_name, fixture, monkeypatch):
     """EXACTLY what bench.py times -- TrainStep with bf16 weight copies, bf16 autocast, channels_last, the whole step
     replayed from a CUDA graph, gradients read from the flat bucket -- at 224x224, bs16, against loss and per-parameter
     gradients of the reference's own model code (fp64) on the same bf16-representable weights and batch (lr = 0 keeps the
@@ -280,7 +280,11 @@ def test_bench_path_matches_reference_golden(model_name, fixture):
     loss_plain.backward()
     errs_plain = _grad_errors({n: p.grad for n, p in mp_.named_parameters()}, g)
     del mp_
-    # (b) the bench path
+    # (b) the bench path.  The batch here is 16, not 256: lift the pixel threshold so that every layer takes the backend the bs256 bench
+    # takes (all-tcgen05 1x1 convolutions + haloed key conv), i.e. the code under test is the code that is timed
+    from cotnet_b200 import cot_layer as _cl, fused as _fu
+    monkeypatch.setattr(_cl.CotLayer, "tc_min_pixels", 0)
+    monkeypatch.setattr(_fu, "TC_MIN_PIXELS", 0)
     m = m.cuda().to(memory_format=torch.channels_last)
     xc = x.contiguous(memory_format=torch.channels_last)
     m.eval()
