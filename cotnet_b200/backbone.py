@@ -42,9 +42,15 @@ class Bottleneck(nn.Module):
     def zero_init_last_bn(self):
         nn.init.zeros_(self.bn3.weight)
 
+    #: training: hand the block output to the next block as TWO aliases (conv1 reads one, the shortcut the other) so that their
+    #: gradients are summed inside bn3's backward kernels instead of by an autograd add (fused._two_grads); False on the last block
+    fork_output = os.environ.get("COTB200_FORK", "1") != "0"
+
     def forward(self, x):
-        if fused.supported(x):
-            return self._forward_fused(x)
+        xs = x if isinstance(x, tuple) else (x, x)
+        if fused.supported(xs[0]):
+            return self._forward_fused(xs)
+        x = xs[0]
         residual = x
         x = self.act1(self.bn1(self.conv1(x)))
         if self.avd is not None:
@@ -56,19 +62,20 @@ class Bottleneck(nn.Module):
         x += residual
         return self.act3(x)
 
-    def _forward_fused(self, x):
+    def _forward_fused(self, xs):
         """channels_last path: bn1+ReLU and bn3+residual+ReLU run on the fused BatchNorm
         kernels (2 passes each way) instead of ATen's channels_last batch-norm kernels."""
         cl = torch.channels_last
-        residual = x
+        x, residual = xs                           # two aliases of the previous block's output (or the same tensor twice)
         y = fused.conv1x1_bn(x, self.conv1, self.bn1, relu=True)
         if self.avd is not None:
             y = fused.avg_pool3x3s2(y)              # nn.AvgPool2d(3, 2, padding=1) on the fused NHWC kernel
         y = self.conv2(y.contiguous(memory_format=cl))
         if self.downsample is not None:
-            residual = fused.conv1x1_bn(x, self.downsample[0], self.downsample[1], relu=False)
+            residual = fused.conv1x1_bn(residual, self.downsample[0], self.downsample[1], relu=False)
+        fork = self.fork_output and torch.is_grad_enabled() and self.training
         return fused.conv1x1_bn(y.contiguous(memory_format=cl), self.conv3, self.bn3, relu=True,
-                                res=residual.contiguous(memory_format=cl))
+                                res=residual.contiguous(memory_format=cl), fork=fork)
 
 
 class CoTResNet(nn.Module):
@@ -93,6 +100,7 @@ class CoTResNet(nn.Module):
                 blocks.append(Bottleneck(inplanes, planes, s, down, cardinality, base_width))
                 inplanes = planes * Bottleneck.expansion
             self.add_module("layer%d" % (i + 1), nn.Sequential(*blocks))
+        self.layer4[-1].fork_output = False          # the network's last block feeds the global pool only
         self.num_features = inplanes
         self.global_pool = nn.AdaptiveAvgPool2d(1)
         self.fc = nn.Linear(self.num_features, num_classes)

@@ -340,7 +340,7 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float*
 // sum_dz[c] += dz ; sum_dzx[c] += dz * xhat
 template <typename T, int VEC, int ACT>
 __global__ void __launch_bounds__(NT_THREADS)
-bn_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ scale,
+bn_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ dy2, const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ scale,
                    const float* __restrict__ shift, const float* __restrict__ mu, const float* __restrict__ rstd,
                    float* __restrict__ sum_dz, float* __restrict__ sum_dzx, RowsGeo g) {
   extern __shared__ float sm[];
@@ -358,11 +358,13 @@ bn_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* _
     for (int r = r0 + ty; r < r1; r += g.ry) {
       const Pack<T, VEC> dv = ld_pack<T, VEC>(dy + base + (long long)r * g.ld);
       const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.ld);
-      Pack<T, VEC> yv;
+      Pack<T, VEC> yv, d2;
       if (ACT == 1) yv = ld_pack<T, VEC>(y + base + (long long)r * g.ld);
+      if (dy2) d2 = ld_pack<T, VEC>(dy2 + base + (long long)r * g.ld);    // two-consumer output: dy = dy + dy2, summed here in fp32
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         float dz = to_acc(dv.v[i]);
+        if (dy2) dz += to_acc(d2.v[i]);
         const float xf = to_acc(xv.v[i]);
         if (ACT == 1 && !(to_acc(yv.v[i]) > 0.f)) dz = 0.f;
         if (ACT == 2 && !(fmaf(xf, sc[i], sh[i]) > 0.f)) dz = 0.f;       // the forward's own fp32 z: identical mask, y not read
@@ -379,7 +381,7 @@ bn_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* _
 // dx = scale * (dz - c1 - xhat*c2)   (c1 = c2 = 0 in eval mode);   dres = dz when RES
 template <typename T, int VEC, int ACT, bool RES>
 __global__ void __launch_bounds__(NT_THREADS)
-bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ scale,
+bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ dy2, const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ mu, const float* __restrict__ rstd,
                     const float* __restrict__ c1, const float* __restrict__ c2, float inv_n, T* __restrict__ dx,
                     T* __restrict__ dres, RowsGeo g) {
@@ -397,12 +399,14 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
   for (int r = r0 + ty; r < r1; r += g.ry) {
     const Pack<T, VEC> dv = ld_pack<T, VEC>(dy + base + (long long)r * g.ld);
     const Pack<T, VEC> xv = ld_pack<T, VEC>(x + base + (long long)r * g.ld);
-    Pack<T, VEC> yv;
+    Pack<T, VEC> yv, d2;
     if (ACT == 1) yv = ld_pack<T, VEC>(y + base + (long long)r * g.ld);
+    if (dy2) d2 = ld_pack<T, VEC>(dy2 + base + (long long)r * g.ld);
     Pack<T, VEC> o, o2;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       float dz = to_acc(dv.v[i]);
+      if (dy2) dz += to_acc(d2.v[i]);
       const float xf = to_acc(xv.v[i]);
       if (ACT == 1 && !(to_acc(yv.v[i]) > 0.f)) dz = 0.f;
       if (ACT == 2 && !(fmaf(xf, sc[i], sh[i]) > 0.f)) dz = 0.f;
@@ -986,9 +990,9 @@ extern "C" int cotb200_bn_apply_batch(int dtype, int B, int HW, int C, const voi
   return bn_apply_impl("bn_apply_batch", dtype, B, HW, C, x, res, nullptr, nullptr, relu, y, &f, stream);
 }
 
-extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y,
-                                   const float* scale, const float* shift, const float* mu, const float* rstd, int relu,
-                                   float* sum_dz, float* sum_dzx, void* stream) {
+static int bn_bwd_sums_impl(int dtype, int B, int HW, int C, const void* dy, const void* dy2, const void* x, const void* y,
+                            const float* scale, const float* shift, const float* mu, const float* rstd, int relu,
+                            float* sum_dz, float* sum_dzx, void* stream) {
   if (!dy || !x || !mu || !rstd || !sum_dz || !sum_dzx || (relu == 1 && !y) || (relu == 2 && (!scale || !shift))) {
     set_error("bn_bwd_sums: NULL pointer"); return COTB200_ENULL; }
   if (relu < 0 || relu > 2) { set_error("bn_bwd_sums: relu must be 0, 1 or 2"); return COTB200_EINVAL; }
@@ -998,7 +1002,7 @@ extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   COTB200_DISPATCH_DTYPE(dtype, {
     if constexpr (!std::is_same<T, double>::value) {
-      const int vec = pick_vec<T>(C, dy, x, relu == 1 ? y : nullptr);
+      const int vec = pick_vec<T>(C, dy, x, relu == 1 ? y : nullptr, dy2);
       const int cw = col_chunk(C, vec);
       if (!cw) { set_error("bn_bwd_sums: cannot tile %d channels", C); return COTB200_EINVAL; }
       for (int c0 = 0; c0 < C; c0 += cw) {
@@ -1007,15 +1011,16 @@ extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* 
         if (rc) return rc;
         g.ld = C;
         const T* dp = (const T*)dy + c0; const T* xp = (const T*)x + c0; const T* yp = y ? (const T*)y + c0 : nullptr;
-        COTB200_PROF_B("bn_bwd_sums", (double)B * HW * cw * (2 + (relu == 1 ? 1 : 0)) * sizeof(T));
+        const T* d2p = dy2 ? (const T*)dy2 + c0 : nullptr;
+        COTB200_PROF_B("bn_bwd_sums", (double)B * HW * cw * (2 + (relu == 1 ? 1 : 0) + (dy2 ? 1 : 0)) * sizeof(T));
         const float* scp = scale ? scale + c0 : nullptr; const float* shp = shift ? shift + c0 : nullptr;
         NT_DISPATCH_VEC(vec, {
           if (relu == 1) { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 1>, smem))) return rc;
-                           bn_bwd_sums_kernel<T, V, 1><<<NT_GRID, NT_THREADS, smem, st>>>(dp, xp, yp, scp, shp, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
+                           bn_bwd_sums_kernel<T, V, 1><<<NT_GRID, NT_THREADS, smem, st>>>(dp, d2p, xp, yp, scp, shp, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
           else if (relu == 2) { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 2>, smem))) return rc;
-                                bn_bwd_sums_kernel<T, V, 2><<<NT_GRID, NT_THREADS, smem, st>>>(dp, xp, nullptr, scp, shp, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
+                                bn_bwd_sums_kernel<T, V, 2><<<NT_GRID, NT_THREADS, smem, st>>>(dp, d2p, xp, nullptr, scp, shp, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
           else { if ((rc = ensure_smem(bn_bwd_sums_kernel<T, V, 0>, smem))) return rc;
-                 bn_bwd_sums_kernel<T, V, 0><<<NT_GRID, NT_THREADS, smem, st>>>(dp, xp, nullptr, scp, shp, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
+                 bn_bwd_sums_kernel<T, V, 0><<<NT_GRID, NT_THREADS, smem, st>>>(dp, d2p, xp, nullptr, scp, shp, mu + c0, rstd + c0, sum_dz + c0, sum_dzx + c0, g); }
         });
         if ((rc = check_launch("bn_bwd_sums"))) return rc;
       }
@@ -1025,10 +1030,10 @@ extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* 
   return 0;
 }
 
-#define BN_BWD_APPLY_LAUNCH(ACT, RES, YP, DRP) bn_bwd_apply_kernel<T, V, ACT, RES><<<NT_GRID, NT_THREADS, 0, st>>>(dp, xp, YP, scale + c0, shp, mu + c0, rstd + c0, k1, k2, inv_n, dxp, DRP, g)
-extern "C" int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y,
-                                    const float* scale, const float* shift, const float* mu, const float* rstd,
-                                    const float* c1, const float* c2, float inv_n, int relu, void* dx, void* dres, void* stream) {
+#define BN_BWD_APPLY_LAUNCH(ACT, RES, YP, DRP) bn_bwd_apply_kernel<T, V, ACT, RES><<<NT_GRID, NT_THREADS, 0, st>>>(dp, d2p, xp, YP, scale + c0, shp, mu + c0, rstd + c0, k1, k2, inv_n, dxp, DRP, g)
+static int bn_bwd_apply_impl(int dtype, int B, int HW, int C, const void* dy, const void* dy2, const void* x, const void* y,
+                             const float* scale, const float* shift, const float* mu, const float* rstd,
+                             const float* c1, const float* c2, float inv_n, int relu, void* dx, void* dres, void* stream) {
   if (!dy || !x || !scale || !mu || !rstd || !dx || (relu == 1 && !y) || (relu == 2 && !shift)) {
     set_error("bn_bwd_apply: NULL pointer"); return COTB200_ENULL; }
   if (relu < 0 || relu > 2) { set_error("bn_bwd_apply: relu must be 0, 1 or 2"); return COTB200_EINVAL; }
@@ -1040,6 +1045,7 @@ extern "C" int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void*
     if constexpr (!std::is_same<T, double>::value) {
       int vec = pick_vec<T>(C, dy, x, relu == 1 ? y : nullptr, dx);
       if (dres && ((uintptr_t)dres & (vec * sizeof(T) - 1))) vec = 1;
+      if (dy2 && ((uintptr_t)dy2 & (vec * sizeof(T) - 1))) vec = 1;
       const int cw = col_chunk(C, vec);
       if (!cw) { set_error("bn_bwd_apply: cannot tile %d channels", C); return COTB200_EINVAL; }
       for (int c0 = 0; c0 < C; c0 += cw) {
@@ -1049,8 +1055,9 @@ extern "C" int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void*
         g.ld = C;
         const T* dp = (const T*)dy + c0; const T* xp = (const T*)x + c0; const T* yp = y ? (const T*)y + c0 : nullptr;
         T* dxp = (T*)dx + c0; T* drp = dres ? (T*)dres + c0 : nullptr;
+        const T* d2p = dy2 ? (const T*)dy2 + c0 : nullptr;
         const float* k1 = c1 ? c1 + c0 : nullptr; const float* k2 = c2 ? c2 + c0 : nullptr;
-        COTB200_PROF_B("bn_bwd_apply", (double)B * HW * cw * (3 + (relu == 1 ? 1 : 0) + (dres ? 1 : 0)) * sizeof(T));
+        COTB200_PROF_B("bn_bwd_apply", (double)B * HW * cw * (3 + (relu == 1 ? 1 : 0) + (dres ? 1 : 0) + (dy2 ? 1 : 0)) * sizeof(T));
         const float* shp = shift ? shift + c0 : nullptr;
         NT_DISPATCH_VEC(vec, {
           if (relu == 1) { if (dres) BN_BWD_APPLY_LAUNCH(1, true, yp, drp); else BN_BWD_APPLY_LAUNCH(1, false, yp, nullptr); }
@@ -1077,4 +1084,27 @@ extern "C" int cotb200_bn_finalize(int C, const float* sum, const float* sq, con
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sum, sq, weight, bias, running_mean, running_var, n, eps, momentum, use_batch,
                                                      update_running, scale, shift, mean, rstd, C);
   return check_launch("bn_finalize");
+}
+
+
+// ---- public entry points of the BatchNorm backward: one incoming gradient, or two that are summed on the fly (fp32)
+extern "C" int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y,
+                                   const float* scale, const float* shift, const float* mu, const float* rstd, int relu,
+                                   float* sum_dz, float* sum_dzx, void* stream) {
+  return bn_bwd_sums_impl(dtype, B, HW, C, dy, nullptr, x, y, scale, shift, mu, rstd, relu, sum_dz, sum_dzx, stream);
+}
+extern "C" int cotb200_bn_bwd_sums2(int dtype, int B, int HW, int C, const void* dy, const void* dy2, const void* x, const void* y,
+                                    const float* scale, const float* shift, const float* mu, const float* rstd, int relu,
+                                    float* sum_dz, float* sum_dzx, void* stream) {
+  return bn_bwd_sums_impl(dtype, B, HW, C, dy, dy2, x, y, scale, shift, mu, rstd, relu, sum_dz, sum_dzx, stream);
+}
+extern "C" int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y,
+                                    const float* scale, const float* shift, const float* mu, const float* rstd,
+                                    const float* c1, const float* c2, float inv_n, int relu, void* dx, void* dres, void* stream) {
+  return bn_bwd_apply_impl(dtype, B, HW, C, dy, nullptr, x, y, scale, shift, mu, rstd, c1, c2, inv_n, relu, dx, dres, stream);
+}
+extern "C" int cotb200_bn_bwd_apply2(int dtype, int B, int HW, int C, const void* dy, const void* dy2, const void* x, const void* y,
+                                     const float* scale, const float* shift, const float* mu, const float* rstd,
+                                     const float* c1, const float* c2, float inv_n, int relu, void* dx, void* dres, void* stream) {
+  return bn_bwd_apply_impl(dtype, B, HW, C, dy, dy2, x, y, scale, shift, mu, rstd, c1, c2, inv_n, relu, dx, dres, stream);
 }

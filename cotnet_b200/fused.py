@@ -161,8 +161,9 @@ class BNActFn(Function):
     single cost of the eager step."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, res, bn, relu):
+    def forward(ctx, x, weight, bias, res, bn, relu, fork=False):
         assert _is_cl(x) and (res is None or (_is_cl(res) and res.dtype == x.dtype and res.shape == x.shape))
+        ctx.set_materialize_grads(False)
         B, C, H, W = x.shape
         lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.dtype_code(x)
         x = x.detach()
@@ -180,36 +181,54 @@ class BNActFn(Function):
         # forward's own scale/shift (relu code 2) and y is neither saved nor read
         ctx.save_for_backward(x, y if (relu and res is not None) else None, ss)
         ctx.cfg = (relu, batch, res is not None, weight.dtype, bias.dtype)
+        if fork:            # two aliases of ONE tensor: each consumer's gradient reaches backward() separately (see _two_grads)
+            return y, y.detach()
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, *grads):
         x, y, ss = ctx.saved_tensors
         relu, batch, has_res, wdt, bdt = ctx.cfg
         B, C, H, W = x.shape
         lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.dtype_code(x)
-        dy = dy.contiguous(memory_format=torch.channels_last)
+        dy, dy2 = _two_grads(grads)
+        if dy is None:
+            return (None,) * 7
         rcode = 0 if not relu else (1 if y is not None else 2)
         sums = None
         if batch or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)       # escapes as dgamma/dbeta: not from the arena
-            _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), x.data_ptr(), _lib.ptr(y), ss[0].data_ptr(),
-                                               ss[1].data_ptr(), ss[2].data_ptr(), ss[3].data_ptr(), rcode,
-                                               sums[0].data_ptr(), sums[1].data_ptr(), st), "bn_bwd_sums")
+            _lib.check(lib.cotb200_bn_bwd_sums2(dt, B, H * W, C, dy.data_ptr(), _lib.ptr(dy2), x.data_ptr(), _lib.ptr(y), ss[0].data_ptr(),
+                                                ss[1].data_ptr(), ss[2].data_ptr(), ss[3].data_ptr(), rcode,
+                                                sums[0].data_ptr(), sums[1].data_ptr(), st), "bn_bwd_sums")
         dx = torch.empty_like(x, memory_format=torch.channels_last)
         dres = torch.empty_like(x, memory_format=torch.channels_last) if (has_res and ctx.needs_input_grad[3]) else None
-        _lib.check(lib.cotb200_bn_bwd_apply(dt, B, H * W, C, dy.data_ptr(), x.data_ptr(), _lib.ptr(y), ss[0].data_ptr(),
-                                            ss[1].data_ptr(), ss[2].data_ptr(), ss[3].data_ptr(),
-                                            _lib.ptr(sums[0]) if batch else None, _lib.ptr(sums[1]) if batch else None,
-                                            1.0 / float(B * H * W), rcode, dx.data_ptr(), _lib.ptr(dres), st), "bn_bwd_apply")
+        _lib.check(lib.cotb200_bn_bwd_apply2(dt, B, H * W, C, dy.data_ptr(), _lib.ptr(dy2), x.data_ptr(), _lib.ptr(y), ss[0].data_ptr(),
+                                             ss[1].data_ptr(), ss[2].data_ptr(), ss[3].data_ptr(),
+                                             _lib.ptr(sums[0]) if batch else None, _lib.ptr(sums[1]) if batch else None,
+                                             1.0 / float(B * H * W), rcode, dx.data_ptr(), _lib.ptr(dres), st), "bn_bwd_apply")
         dgamma = sums[1].to(wdt) if ctx.needs_input_grad[1] else None
         dbeta = sums[0].to(bdt) if ctx.needs_input_grad[2] else None
-        return dx, dgamma, dbeta, dres, None, None
+        return dx, dgamma, dbeta, dres, None, None, None
 
 
-def bn_act(x, bn: torch.nn.BatchNorm2d, relu=False, res=None):
-    """Fused BatchNorm2d (+ residual add) (+ ReLU) with the module's parameters / buffers / train-eval semantics."""
-    return BNActFn.apply(x, bn.weight, bn.bias, res, bn, relu)
+def _two_grads(grads):
+    """Incoming gradients of a (possibly forked) output: (dy, dy2) as channels_last tensors, dy2 None when there is one gradient.
+    A forked BatchNorm output feeds two consumers -- the next bottleneck's conv1 and its shortcut (models/cotnet.py:228-262) -- and
+    autograd would add their gradients with a separate kernel (read 2 + write 1 of the block-sized tensor, 1.2 ms per CoTNet-50 step);
+    handing both to the BatchNorm backward kernels, which sum them in fp32 while they stream dy anyway, costs one extra read each."""
+    g = [t.contiguous(memory_format=torch.channels_last) for t in grads if t is not None]
+    if not g:
+        return None, None
+    if len(g) == 1:
+        return g[0], None
+    return g[0], g[1]
+
+
+def bn_act(x, bn: torch.nn.BatchNorm2d, relu=False, res=None, fork=False):
+    """Fused BatchNorm2d (+ residual add) (+ ReLU) with the module's parameters / buffers / train-eval semantics.
+    fork=True returns two aliases of the output (see _two_grads)."""
+    return BNActFn.apply(x, bn.weight, bn.bias, res, bn, relu, fork)
 
 
 class GroupNorm9Fn(Function):
@@ -665,7 +684,17 @@ class TcConv1x1Fn(Function):
 
     @staticmethod
     def forward(ctx, a1, a2, weight, cbias, bn_w, bn_b, bn, relu, res=None):
+        return TcConv1x1Fn._fwd(ctx, False, a1, a2, weight, cbias, bn_w, bn_b, bn, relu, res)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return TcConv1x1Fn._bwd(ctx, grads)
+
+    @staticmethod
+    def _fwd(ctx, fork, a1, a2, weight, cbias, bn_w, bn_b, bn, relu, res):
         assert _is_cl(a1) and a1.dtype == torch.bfloat16 and (a2 is None or (_is_cl(a2) and a2.dtype == a1.dtype))
+        if fork:
+            ctx.set_materialize_grads(False)
         assert res is None or (bn is not None and _is_cl(res) and res.dtype == a1.dtype)
         B, K1, H, W = a1.shape
         K2 = 0 if a2 is None else a2.shape[1]
@@ -704,30 +733,35 @@ class TcConv1x1Fn(Function):
         ctx.save_for_backward(a1, a2, wb, pre, out if relu else None, scale, mean, rstd)
         ctx.cfg = (relu, batch, bn is not None, cbias is not None, weight.dtype, weight.shape,
                    None if bn_w is None else bn_w.dtype, None if cbias is None else cbias.dtype, K1, K2, res is not None)
+        if fork:
+            assert bn is not None, "fork needs the BatchNorm form (the sum of the two gradients happens in its backward kernels)"
+            return out, out.detach()
         return out
 
     @staticmethod
-    def backward(ctx, dy):
+    def _bwd(ctx, grads):
         a1, a2, wb, pre, y, scale, mean, rstd = ctx.saved_tensors
         relu, batch, has_bn, has_bias, wdt, wshape, bndt, cbdt, K1, K2, has_res = ctx.cfg
+        dy, dy2 = _two_grads(grads)
+        if dy is None:
+            return (None,) * 9
         B, N, H, W = dy.shape
         M = B * H * W
         lib, st, dt = _lib.load(), _lib.stream_ptr(dy), _lib.BF16
-        dy = dy.contiguous(memory_format=torch.channels_last)
         dgamma = dbeta = dcb = dres = None
         if has_bn:
             sums = torch.zeros(2, N, dtype=torch.float32, device=dy.device)      # escapes as dgamma/dbeta
             if has_res and ctx.needs_input_grad[8]:
                 dres = torch.empty_like(dy, memory_format=torch.channels_last)
-            _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
-                                               None, mean.data_ptr(), rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(),
-                                               sums[1].data_ptr(), st),
+            _lib.check(lib.cotb200_bn_bwd_sums2(dt, B, H * W, N, dy.data_ptr(), _lib.ptr(dy2), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
+                                                None, mean.data_ptr(), rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(),
+                                                sums[1].data_ptr(), st),
                        "bn_bwd_sums")
             dpre = torch.empty_like(dy, memory_format=torch.channels_last)
-            _lib.check(lib.cotb200_bn_bwd_apply(dt, B, H * W, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
-                                                None, mean.data_ptr(), rstd.data_ptr(), _lib.ptr(sums[0]) if batch else None,
-                                                _lib.ptr(sums[1]) if batch else None, 1.0 / M, 1 if relu else 0,
-                                                dpre.data_ptr(), _lib.ptr(dres), st), "bn_bwd_apply")
+            _lib.check(lib.cotb200_bn_bwd_apply2(dt, B, H * W, N, dy.data_ptr(), _lib.ptr(dy2), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
+                                                 None, mean.data_ptr(), rstd.data_ptr(), _lib.ptr(sums[0]) if batch else None,
+                                                 _lib.ptr(sums[1]) if batch else None, 1.0 / M, 1 if relu else 0,
+                                                 dpre.data_ptr(), _lib.ptr(dres), st), "bn_bwd_apply")
             dgamma, dbeta = sums[1].to(bndt), sums[0].to(bndt)
         else:
             dpre = dy if not relu else dy * (y > 0)
@@ -758,6 +792,19 @@ class TcConv1x1Fn(Function):
                 _tc.wgrad_bf16(dpre, a1, a2, out=acc)
                 dw = acc.reshape(wshape).to(wdt)
         return da1, da2, dw, dcb, dgamma, dbeta, None, None, dres
+
+
+class TcConv1x1ForkFn(Function):
+    """TcConv1x1Fn whose output comes as TWO aliases (one per consumer); their gradients are summed inside the BatchNorm backward
+    kernels (_two_grads) instead of by an autograd add kernel."""
+
+    @staticmethod
+    def forward(ctx, a1, a2, weight, cbias, bn_w, bn_b, bn, relu, res=None):
+        return TcConv1x1Fn._fwd(ctx, True, a1, a2, weight, cbias, bn_w, bn_b, bn, relu, res)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return TcConv1x1Fn._bwd(ctx, grads)
 
 
 class TcConv3x3Fn(Function):
@@ -915,7 +962,7 @@ TC_TRUNK_MAX_WEIGHT = int(_os.environ.get("COTB200_TC_TRUNK_MAX_WEIGHT", str(128
 TC_MIN_PIXELS = int(_os.environ.get("COTB200_TC_MIN_PIXELS", "100000"))
 
 
-def conv1x1_bn(x, conv, bn, relu, res=None):
+def conv1x1_bn(x, conv, bn, relu, res=None, fork=False):
     """act(BN(conv1x1(x)) (+ res)) for the bottleneck's 1x1 convolutions (models/cotnet.py:229-235,249-262): on the tcgen05
     GEMMs when the backend says so and the geometry allows (bf16 channels_last, stride 1, dense, no bias), else cuDNN + the
     fused BatchNorm kernels."""
@@ -924,8 +971,8 @@ def conv1x1_bn(x, conv, bn, relu, res=None):
             and conv.stride == (1, 1) and conv.groups == 1 and conv.bias is None and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0
             and w.shape[0] * w.shape[1] <= TC_TRUNK_MAX_WEIGHT and x.shape[0] * x.shape[2] * x.shape[3] >= TC_MIN_PIXELS
             and (torch.is_grad_enabled() or not bn.training)):
-        return TcConv1x1Fn.apply(x, None, w, None, bn.weight, bn.bias, bn, relu, res)
-    return bn_act(conv(x).contiguous(memory_format=torch.channels_last), bn, relu=relu, res=res)
+        return (TcConv1x1ForkFn if fork else TcConv1x1Fn).apply(x, None, w, None, bn.weight, bn.bias, bn, relu, res)
+    return bn_act(conv(x).contiguous(memory_format=torch.channels_last), bn, relu=relu, res=res, fork=fork)
 
 
 def tc_supported(x, dim):

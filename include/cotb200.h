@@ -192,6 +192,15 @@ int cotb200_bn_apply_batch(int dtype, int B, int HW, int C, const void* x, const
 int cotb200_bn_bwd_sums(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y, const float* scale,
                         const float* shift, const float* mu, const float* rstd, int relu, float* sum_dz, float* sum_dzx,
                         void* stream);
+/* Two-consumer form: the BatchNorm output fed TWO consumers (the next block's conv1 and its shortcut, models/cotnet.py:228-262) and
+ * autograd would first add their gradients (one more kernel, three HBM passes); here dy := dy + dy2 is formed in fp32 inside the
+ * backward kernels (dy2 may be NULL = the one-gradient form). */
+int cotb200_bn_bwd_sums2(int dtype, int B, int HW, int C, const void* dy, const void* dy2, const void* x, const void* y,
+                         const float* scale, const float* shift, const float* mu, const float* rstd, int relu, float* sum_dz,
+                         float* sum_dzx, void* stream);
+int cotb200_bn_bwd_apply2(int dtype, int B, int HW, int C, const void* dy, const void* dy2, const void* x, const void* y,
+                          const float* scale, const float* shift, const float* mu, const float* rstd, const float* c1,
+                          const float* c2, float inv_n, int relu, void* dx, void* dres, void* stream);
 /* dx = scale*(dz - c1*inv_n - xhat*c2*inv_n) (c1,c2 = the raw sums of cotb200_bn_bwd_sums, NULL in eval mode) ;
  * dres = dz when dres != NULL (gradient of the residual) */
 int cotb200_bn_bwd_apply(int dtype, int B, int HW, int C, const void* dy, const void* x, const void* y, const float* scale,
