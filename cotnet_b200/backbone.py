@@ -42,9 +42,12 @@ class Bottleneck(nn.Module):
     def zero_init_last_bn(self):
         nn.init.zeros_(self.bn3.weight)
 
-    #: training: hand the block output to the next block as TWO aliases (conv1 reads one, the shortcut the other) so that their
-    #: gradients are summed inside bn3's backward kernels instead of by an autograd add (fused._two_grads); False on the last block
-    fork_output = os.environ.get("COTB200_FORK", "1") != "0"
+    #: (opt-in, COTB200_FORK=1) training: hand the block output to the next block as TWO aliases (conv1 reads one, the shortcut the
+    #: other) so that their gradients are summed inside bn3's backward kernels instead of by an autograd add (fused._two_grads).
+    #: MEASURED AND REJECTED as a default (one box, profiles/r02_bench_callO_*.json): CoTNet-50 38.59 ms with it, 37.97 without --
+    #: ATen's add runs at the HBM roof, while the extra read costs the BatchNorm backward kernels (0.6-0.75 of the roof) more than
+    #: the add saves (bn_bwd_sums 4.62 -> 5.18 ms, bn_bwd_apply 5.35 -> 6.14 ms).  Always False on the network's last block.
+    fork_output = os.environ.get("COTB200_FORK", "0") != "0"
 
     def forward(self, x):
         xs = x if isinstance(x, tuple) else (x, x)

@@ -123,7 +123,7 @@ class CoTBottleneck(nn.Module):
             return fused.avg_pool3x3s2(y)
         return self.avd(y)
 
-    fork_output = os.environ.get("COTB200_FORK", "1") != "0"             # see backbone.Bottleneck.fork_output
+    fork_output = os.environ.get("COTB200_FORK", "0") != "0"             # see backbone.Bottleneck.fork_output
 
     def forward(self, x):
         cl = torch.channels_last

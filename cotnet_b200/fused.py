@@ -26,6 +26,7 @@ class _ZeroArena:
     def __init__(self):
         self.buf = {}                  # device -> [buffer, used]
         self.active = False
+        self.escape_ok = False         # a trainer that consumes every gradient before the next step_begin() may set this (see _zeros_esc)
 
     def begin(self, device):
         ent = self.buf.get(device)
@@ -73,6 +74,45 @@ def _zeros(shape, device):
     return t.view(*shape)
 
 
+def _zeros_esc(shape, device):
+    """Zeros that ESCAPE the autograd function as gradients (BatchNorm d-gamma / d-beta sums).  Plain torch.zeros in general -- a
+    gradient must survive until its owner reads it -- but a trainer that gathers every gradient inside the step (TrainStep: one gather
+    launch into the flat bucket before the next step_begin()) may take them from the pre-zeroed arena too: ~140 fill launches per
+    CoTNet-50 step less (profiles/r02_launches_cotnet50_callN.md)."""
+    return _zeros(shape, device) if _ARENA.escape_ok else torch.zeros(*shape, dtype=torch.float32, device=device)
+
+
+def arena_escape_ok(on=True):
+    _ARENA.escape_ok = bool(on)
+
+
+#: BatchNorm `num_batches_tracked += 1` bookkeeping: one tiny kernel per BatchNorm per step (~106 in CoTNet-50).  A trainer may defer
+#: them (defer_bn_counters) and bump all counters with ONE multi-tensor add per step (flush_bn_counters).
+_DEFERRED_COUNTERS = None
+
+
+def defer_bn_counters(on=True):
+    global _DEFERRED_COUNTERS
+    _DEFERRED_COUNTERS = [] if on else None
+
+
+def flush_bn_counters():
+    if _DEFERRED_COUNTERS:
+        with torch.no_grad():
+            torch._foreach_add_(_DEFERRED_COUNTERS, 1)
+        _DEFERRED_COUNTERS.clear()
+
+
+def _bump_counter(bn):
+    """num_batches_tracked += 1 now, or on the trainer's flush; returns True when the caller may rely on the NEW value immediately."""
+    if _DEFERRED_COUNTERS is not None and bn.momentum is not None:
+        _DEFERRED_COUNTERS.append(bn.num_batches_tracked)
+        return False
+    with torch.no_grad():
+        bn.num_batches_tracked += 1
+    return True
+
+
 def _is_cl(t):
     return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
 
@@ -91,8 +131,7 @@ def _bn_running(bn, use_batch):
     mom = 0.0
     rm = rv = None
     if update:
-        with torch.no_grad():
-            bn.num_batches_tracked += 1
+        _bump_counter(bn)
         mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
     if update or not use_batch:
         rm, rv = bn.running_mean, bn.running_var
@@ -197,7 +236,7 @@ class BNActFn(Function):
         rcode = 0 if not relu else (1 if y is not None else 2)
         sums = None
         if batch or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)       # escapes as dgamma/dbeta: not from the arena
+            sums = _zeros_esc((2, C,), x.device)       # escapes as dgamma/dbeta
             _lib.check(lib.cotb200_bn_bwd_sums2(dt, B, H * W, C, dy.data_ptr(), _lib.ptr(dy2), x.data_ptr(), _lib.ptr(y), ss[0].data_ptr(),
                                                 ss[1].data_ptr(), ss[2].data_ptr(), ss[3].data_ptr(), rcode,
                                                 sums[0].data_ptr(), sums[1].data_ptr(), st), "bn_bwd_sums")
@@ -269,7 +308,7 @@ class GroupNorm9Fn(Function):
         dg = dg.contiguous(memory_format=torch.channels_last)
         lib, st, dt = _lib.load(), _lib.stream_ptr(l), _lib.dtype_code(l)
         sums = torch.empty(2, B, wc, dtype=torch.float32, device=l.device)      # s1, s2 (written)
-        dgb = torch.zeros(3, J, dtype=torch.float32, device=l.device)            # dgamma, dbeta, dlbias (escape)
+        dgb = _zeros_esc((3, J,), l.device)            # dgamma, dbeta, dlbias (escape)
         work = _zeros((3 * B * J,), l.device)                                     # per-sample column partials
         want_db = lb32 is not None and ctx.needs_input_grad[5]
         _lib.check(lib.cotb200_gn9_bwd_sums(dt, B, HW, wc, ctx.gc, dg.data_ptr(), l.data_ptr(), _lib.ptr(lb32), mean.data_ptr(),
@@ -393,7 +432,7 @@ class CotTailFn(Function):
         grads = torch.autograd.grad(a, [p_leaf] + mlp_params, grad_outputs=S, allow_unused=True)
         dpn = grads[0].contiguous()                      # d/d(pooled mean); the kernels apply the 1/HW (pscale)
         mlp_grads = [None if g is None else g for g in grads[1:]]
-        sums = torch.zeros(2, C, dtype=torch.float32, device=u.device)          # escapes as dgamma/dbeta
+        sums = _zeros_esc((2, C,), u.device)          # escapes as dgamma/dbeta
         need_param = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         if ctx.training or need_param:
             _lib.check(lib.cotb200_tail_bwd_dz_sums(dt, B, HW, C, dout.data_ptr(), u.data_ptr(), scale.data_ptr(), shift.data_ptr(),
@@ -512,8 +551,8 @@ def _mlp_fp32(c0, b1, c3, p, act):
         rm = rv = None
         mom = 0.0
         if track:
+            _bump_counter(b1)
             with torch.no_grad():
-                b1.num_batches_tracked += 1
                 mom = b1.momentum if b1.momentum is not None else 1.0 / float(b1.num_batches_tracked)
                 rm, rv = b1.running_mean.float().clone(), b1.running_var.float().clone()
         z = F.batch_norm(z, rm, rv, w1, bb1, True, mom, b1.eps)
@@ -750,7 +789,7 @@ class TcConv1x1Fn(Function):
         lib, st, dt = _lib.load(), _lib.stream_ptr(dy), _lib.BF16
         dgamma = dbeta = dcb = dres = None
         if has_bn:
-            sums = torch.zeros(2, N, dtype=torch.float32, device=dy.device)      # escapes as dgamma/dbeta
+            sums = _zeros_esc((2, N,), dy.device)      # escapes as dgamma/dbeta
             if has_res and ctx.needs_input_grad[8]:
                 dres = torch.empty_like(dy, memory_format=torch.channels_last)
             _lib.check(lib.cotb200_bn_bwd_sums2(dt, B, H * W, N, dy.data_ptr(), _lib.ptr(dy2), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
@@ -844,7 +883,7 @@ class TcConv3x3Fn(Function):
         M = B * H * W
         lib, st, dt = _lib.load(), _lib.stream_ptr(x), _lib.BF16
         dy = dy.contiguous(memory_format=torch.channels_last)
-        sums = torch.zeros(2, C, dtype=torch.float32, device=x.device)          # escapes as dgamma/dbeta
+        sums = _zeros_esc((2, C,), x.device)          # escapes as dgamma/dbeta
         _lib.check(lib.cotb200_bn_bwd_sums(dt, B, H * W, C, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
                                            None, mean.data_ptr(), rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(),
                                            sums[1].data_ptr(), st),
@@ -907,7 +946,7 @@ class StemConvBNFn(Function):
         M = B * Ho * Wo
         lib, st, dt = _lib.load(), _lib.stream_ptr(dy), _lib.BF16
         dy = dy.contiguous(memory_format=torch.channels_last)
-        sums = torch.zeros(2, N, dtype=torch.float32, device=dy.device)          # escapes as dgamma/dbeta
+        sums = _zeros_esc((2, N,), dy.device)          # escapes as dgamma/dbeta
         _lib.check(lib.cotb200_bn_bwd_sums(dt, B, Ho * Wo, N, dy.data_ptr(), pre.data_ptr(), _lib.ptr(y), scale.data_ptr(),
                                            None, mean.data_ptr(), rstd.data_ptr(), 1 if relu else 0, sums[0].data_ptr(),
                                            sums[1].data_ptr(), st), "bn_bwd_sums")

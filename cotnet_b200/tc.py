@@ -90,6 +90,9 @@ def wgrad_bf16(dy, a1, a2=None, out=None):
     return out
 
 
+_CONV_IDX = {}
+
+
 def conv_tile(C, groups):
     """N tile (output channels per CTA) used by conv3x3_bf16 for a grouped conv, or None if unsupported."""
     cg = C // groups
@@ -110,10 +113,15 @@ def prepare_conv3x3_weight(weight, groups, transpose_for_dgrad=False):
         w = w.permute(0, 2, 1, 3, 4).flip(3, 4)                       # dX = conv(dY, W^T flipped)
     w = w.reshape(C, cg, 9)
     Wp = torch.zeros(C, 9, bn, dtype=torch.float32, device=weight.device)
-    n = torch.arange(C, device=weight.device)
-    off = (n // cg) * cg - (n // bn) * bn                              # first input channel of n's group inside the tile
-    idx = off[:, None] + torch.arange(cg, device=weight.device)[None, :]          # [C, cg]
-    Wp.scatter_(2, idx[:, None, :].expand(C, 9, cg), w.permute(0, 2, 1))
+    key = (C, cg, bn, str(weight.device))
+    idx3 = _CONV_IDX.get(key)
+    if idx3 is None:                                                   # shape-only index tensor: built once (5 tiny launches per call otherwise)
+        n = torch.arange(C, device=weight.device)
+        off = (n // cg) * cg - (n // bn) * bn                          # first input channel of n's group inside the tile
+        idx = off[:, None] + torch.arange(cg, device=weight.device)[None, :]      # [C, cg]
+        idx3 = idx[:, None, :].expand(C, 9, cg).contiguous()
+        _CONV_IDX[key] = idx3
+    Wp.scatter_(2, idx3, w.permute(0, 2, 1))
     return Wp.reshape(C, 9 * bn).to(torch.bfloat16).contiguous(), bn
 
 

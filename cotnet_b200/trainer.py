@@ -29,6 +29,10 @@ import torch.nn.functional as F
 
 from . import _lib, fused
 
+#: COTB200_BOOKKEEPING=0: BatchNorm gradient sums from torch.zeros and one counter kernel per BatchNorm (the pre-call-Q behaviour)
+import os as _os
+_BOOKKEEPING = _os.environ.get("COTB200_BOOKKEEPING", "1") != "0"
+
 ALIGN = 8          # elements: every parameter slot starts 16-byte aligned in the bf16 bucket (32 B in fp32)
 
 
@@ -296,6 +300,11 @@ class TrainStep:
     def forward_backward(self, x, lab):
         if self._cuda:
             fused.step_begin(self.dev)
+            # every gradient of this step is gathered into the flat bucket before the next step_begin(): the BatchNorm gradient sums
+            # may live in the step arena, and the ~100 `num_batches_tracked += 1` kernels become one multi-tensor add after the forward
+            if _BOOKKEEPING:
+                fused.arena_escape_ok(True)
+                fused.defer_bn_counters(True)
         for _, p, _ in self.plan["big"]:
             p.grad = None
         for _, p, _ in self.plan["small"]:
@@ -306,8 +315,13 @@ class TrainStep:
         with torch.autocast(self.dev.type, dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             out = self.model(x)
             loss = self.loss_fn(out, lab)
+        if self._cuda:
+            fused.flush_bn_counters()
+            fused.defer_bn_counters(False)
         loss.backward()
         self._finish_grads()
+        if self._cuda:
+            fused.arena_escape_ok(False)
         return loss
 
     def optimizer_step(self):
