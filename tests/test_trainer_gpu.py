@@ -425,7 +425,7 @@ def test_forked_block_outputs_model_level(monkeypatch):
         loss.backward()
         losses.append(loss.item())
         grads.append({n: p.grad.float() for n, p in m.named_parameters()})
-    assert abs(losses[0] - losses[1]) <= 1e-3 * abs(losses[0])
+    assert abs(losses[0] - losses[1]) <= 5e-3 * abs(losses[0])        # batch 8, batch-statistics BatchNorm, bf16: atomics order moves the loss by ~1e-3
     rels = sorted(((grads[1][n] - g).norm() / g.norm().clamp_min(1e-6)).item() for n, g in grads[0].items())
     # the two graphs differ by where the bf16 rounding of the summed gradient happens (and by atomics order): medians at the 1e-2 level
     assert rels[len(rels) // 2] <= 5e-2, (rels[len(rels) // 2], rels[-1])
