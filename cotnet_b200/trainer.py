@@ -29,9 +29,13 @@ import torch.nn.functional as F
 
 from . import _lib, fused
 
-#: COTB200_BOOKKEEPING=0: BatchNorm gradient sums from torch.zeros and one counter kernel per BatchNorm (the pre-call-Q behaviour)
+#: COTB200_BOOKKEEPING=0: one `num_batches_tracked += 1` kernel per BatchNorm instead of one multi-tensor add per step.
+#: COTB200_ARENA_ESCAPE=1 (opt-in): BatchNorm / GroupNorm gradient sums from the pre-zeroed step arena instead of torch.zeros (~140 fill
+#: launches per step less; 37.89 vs 37.98 ms on one box, profiles/r02_bench_callQ_*.json).  Off by default: it is worth < 0.1 ms and the
+#: gradients of 1-D parameters would then alias memory that the next step_begin() recycles.
 import os as _os
 _BOOKKEEPING = _os.environ.get("COTB200_BOOKKEEPING", "1") != "0"
+_ARENA_ESCAPE = _os.environ.get("COTB200_ARENA_ESCAPE", "0") != "0"
 
 ALIGN = 8          # elements: every parameter slot starts 16-byte aligned in the bf16 bucket (32 B in fp32)
 
@@ -302,8 +306,9 @@ class TrainStep:
             fused.step_begin(self.dev)
             # every gradient of this step is gathered into the flat bucket before the next step_begin(): the BatchNorm gradient sums
             # may live in the step arena, and the ~100 `num_batches_tracked += 1` kernels become one multi-tensor add after the forward
-            if _BOOKKEEPING:
+            if _ARENA_ESCAPE:
                 fused.arena_escape_ok(True)
+            if _BOOKKEEPING:
                 fused.defer_bn_counters(True)
         for _, p, _ in self.plan["big"]:
             p.grad = None
