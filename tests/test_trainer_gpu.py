@@ -405,28 +405,34 @@ def test_split_attn_fused_vs_plain(dtype, tol, training):
         assert torch.allclose(mb.bn1.running_var.float(), m2.bn1.running_var, atol=5 * tol, rtol=5 * tol)
 
 
-def test_forked_block_outputs_model_level(monkeypatch):
+def test_forked_block_outputs_model_level():
     """COTB200_FORK=1 (opt-in): every bottleneck hands its output to the next one as two aliases and bn3's backward kernels sum the two
-    incoming gradients (cotb200_bn_bwd_{sums,apply}2).  Same loss and gradients as the default graph (autograd add), bf16 autocast,
-    training-mode BatchNorm."""
+    incoming gradients (cotb200_bn_bwd_{sums,apply}2).  Same loss and gradients as the default graph (autograd add).  Training-mode
+    gradients of these nets are ill-conditioned (batch-statistics BatchNorms, atomics-ordered sums: two runs of the SAME graph differ at
+    the percent level), so the gate is relative: forked vs default must be as close as default vs default."""
     from cotnet_b200 import backbone
     torch.manual_seed(3)
-    m1 = backbone.CoTResNet([2, 1, 1, 1], num_classes=16, zero_init_last_bn=False).cuda().to(memory_format=torch.channels_last).train()
-    m2 = copy.deepcopy(m1)
-    for blk in m2.modules():
-        if isinstance(blk, backbone.Bottleneck):
-            blk.fork_output = True
-    m2.layer4[-1].fork_output = False
-    x = torch.randn(8, 3, 64, 64, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
-    y = torch.randint(0, 16, (8,), device="cuda")
-    losses, grads = [], []
-    for m in (m1, m2):
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            loss = torch.nn.functional.cross_entropy(m(x).float(), y)
+    m0 = backbone.CoTResNet([2, 1, 1, 1], num_classes=16, zero_init_last_bn=False).cuda().to(memory_format=torch.channels_last).train()
+    x = torch.randn(16, 3, 96, 96, device="cuda").contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 16, (16,), device="cuda")
+
+    def run(fork):
+        m = copy.deepcopy(m0)
+        for blk in m.modules():
+            if isinstance(blk, backbone.Bottleneck):
+                blk.fork_output = fork
+        m.layer4[-1].fork_output = False
+        loss = torch.nn.functional.cross_entropy(m(x), y)          # fp32, no autocast: the plumbing is what is under test
         loss.backward()
-        losses.append(loss.item())
-        grads.append({n: p.grad.float() for n, p in m.named_parameters()})
-    assert abs(losses[0] - losses[1]) <= 5e-3 * abs(losses[0])        # batch 8, batch-statistics BatchNorm, bf16: atomics order moves the loss by ~1e-3
-    rels = sorted(((grads[1][n] - g).norm() / g.norm().clamp_min(1e-6)).item() for n, g in grads[0].items())
-    # the two graphs differ by where the bf16 rounding of the summed gradient happens (and by atomics order): medians at the 1e-2 level
-    assert rels[len(rels) // 2] <= 5e-2, (rels[len(rels) // 2], rels[-1])
+        return loss.item(), {n: p.grad.float() for n, p in m.named_parameters()}
+
+    def med(ga, gb):
+        rels = sorted(((ga[n] - g).norm() / g.norm().clamp_min(1e-6)).item() for n, g in gb.items())
+        return rels[len(rels) // 2]
+
+    la, ga = run(False)
+    lb, gb = run(False)
+    lc, gc = run(True)
+    assert abs(lc - la) <= 1e-4 * abs(la) + 2 * abs(lb - la), (la, lb, lc)
+    noise, diff = med(gb, ga), med(gc, ga)
+    assert diff <= 3 * noise + 1e-3, (diff, noise)
