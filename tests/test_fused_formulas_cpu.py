@@ -197,3 +197,24 @@ def test_stem_weight_grad_unpack_is_inverse_of_packing():
     torch.manual_seed(4)
     w = torch.randn(8, 3, 7, 7).bfloat16().float()
     assert torch.equal(tc.unpack_stem_weight_grad(tc.prepare_stem_weight(w).float()), w)
+
+
+def test_deferred_batchnorm_counters_bump_once_per_step():
+    """TrainStep bookkeeping (cotnet_b200/fused.py): with defer_bn_counters() the `num_batches_tracked += 1` of every BatchNorm is
+    recorded and applied by ONE multi-tensor add in flush_bn_counters(); without it (or for momentum=None modules, whose momentum
+    depends on the counter) the counter moves immediately -- nn.BatchNorm2d semantics either way."""
+    from cotnet_b200 import fused
+    bns = [torch.nn.BatchNorm2d(4) for _ in range(3)] + [torch.nn.BatchNorm2d(4, momentum=None)]
+    fused.defer_bn_counters(True)
+    try:
+        for bn in bns:
+            fused._bump_counter(bn)
+        assert [int(b.num_batches_tracked) for b in bns] == [0, 0, 0, 1]        # momentum=None is never deferred
+        fused.flush_bn_counters()
+        assert [int(b.num_batches_tracked) for b in bns] == [1, 1, 1, 1]
+        fused.flush_bn_counters()                                                # idempotent: the list was cleared
+        assert [int(b.num_batches_tracked) for b in bns] == [1, 1, 1, 1]
+    finally:
+        fused.defer_bn_counters(False)
+    fused._bump_counter(bns[0])
+    assert int(bns[0].num_batches_tracked) == 2

@@ -43,7 +43,7 @@ def main():
                 continue
         keep.append((src, short.replace("(int)", "").replace("(bool)", ""), regs, spill, smem))
     with open(out, "w") as f:
-        f.write("# r01 — static resources of the libcotb200 kernels (`ptxas -v`, sm_100a; bf16 / fp32 instantiations)\n\n")
+        f.write("# static resources of the libcotb200 kernels (`ptxas -v`, sm_100a; bf16 / fp32 instantiations)\n\n")
         f.write("65 536 registers and 227 KB of shared memory per SM: `regs x threads` bounds the resident CTAs of the register-heavy\n"
                 "kernels (LocalConv gen 2, fused NCHW backward), dynamic shared memory those of the TMA / bulk-copy pipelines.\n\n")
         f.write("| source | kernel | registers | spill bytes | static smem |\n|---|---|---|---|---|\n")
