@@ -218,3 +218,34 @@ def test_deferred_batchnorm_counters_bump_once_per_step():
         fused.defer_bn_counters(False)
     fused._bump_counter(bns[0])
     assert int(bns[0].num_batches_tracked) == 2
+
+
+def test_coxt_grouped_convs_as_dense_block_diagonal():
+    """CoXtLayer's fast path runs its grouped convolutions as dense convolutions with block-diagonal weights built from the grouped
+    parameters (cot_layer._dense_from_grouped) and embed.0 -- which consumes the channel-INTERLEAVED qk = [x0,k0,x1,k1,...]
+    (models/cotnet.py:153-154) with groups=2 -- as  x @ Wx^T + k @ Wk^T  (cot_layer._coxt_embed0_dense).  Same arithmetic, and the
+    gradient of the grouped parameter is the blocks of the dense weight gradient: checked against F.conv2d(groups=...) in fp64."""
+    from cotnet_b200.cot_layer import _coxt_embed0_dense, _dense_from_grouped
+    torch.manual_seed(5)
+    F = torch.nn.functional
+    B, C, H = 2, 48, 5
+    x = torch.randn(B, C, H, H, dtype=torch.float64)
+    k = torch.randn(B, C, H, H, dtype=torch.float64)
+    # 3x3, groups 8 (key_embed) and 1x1, groups 2 (embed.3 / conv1x1)
+    for groups, ks, cout in ((8, 3, C), (2, 1, 54), (2, 1, C)):
+        w = torch.randn(cout, C // groups, ks, ks, dtype=torch.float64, requires_grad=True)
+        want = F.conv2d(x, w, None, 1, ks // 2, 1, groups)
+        got = F.conv2d(x, _dense_from_grouped(w, groups), None, 1, ks // 2)
+        assert (got - want).abs().max() < 1e-10
+        g = torch.randn_like(want)
+        gw_want, = torch.autograd.grad(want, w, g, retain_graph=True)
+        gw_got, = torch.autograd.grad(got, w, g)
+        assert (gw_got - gw_want).abs().max() < 1e-9
+    # embed.0 on the interleaved concat
+    G = 2
+    w0 = torch.randn(C // 2, 2 * C // G, 1, 1, dtype=torch.float64)
+    qk = torch.stack([x, k], dim=2).reshape(B, 2 * C, H, H)
+    want = F.conv2d(qk, w0, None, 1, 0, 1, G)
+    wx, wk = _coxt_embed0_dense(w0, G)
+    got = torch.einsum("bchw,nc->bnhw", x, wx) + torch.einsum("bchw,nc->bnhw", k, wk)
+    assert (got - want).abs().max() < 1e-10
