@@ -249,3 +249,29 @@ def test_coxt_grouped_convs_as_dense_block_diagonal():
     wx, wk = _coxt_embed0_dense(w0, G)
     got = torch.einsum("bchw,nc->bnhw", x, wx) + torch.einsum("bchw,nc->bnhw", k, wk)
     assert (got - want).abs().max() < 1e-10
+
+
+def test_haloed_tile_conv_index_math():
+    """Index math of tc_conv3x3_halo_kernel (csrc/tc_gemm.cu), restated with torch: ONE haloed tile {W+2, R+2} per work item, output
+    pixels enumerated in PADDED coordinates q = r*(W+2) + c, tap (dh, dw) reads tile row q + (dh+1)*(W+2) + (dw+1); outputs with
+    c >= W are garbage columns that are dropped, and rows past the loaded box (NaN here, stale shared memory on the GPU) never reach a
+    valid output.  == conv2d(3x3, pad 1)."""
+    torch.manual_seed(0)
+    F = torch.nn.functional
+    B, C, H, W, R = 2, 4, 6, 5, 3
+    x = torch.randn(B, C, H, W, dtype=torch.float64)
+    w = torch.randn(C, C, 3, 3, dtype=torch.float64)
+    want = F.conv2d(x, w, None, 1, 1)
+    Wp = W + 2
+    xp = F.pad(x, (1, 1, 1, 1))                                   # the TMA out-of-bounds fill
+    out = torch.full_like(want, float("nan"))
+    for b in range(B):
+        for h0 in range(0, H, R):
+            tile = xp[b, :, h0:h0 + R + 2, :].permute(1, 2, 0).reshape((R + 2) * Wp, C)
+            tile = torch.cat([tile, torch.full((2 * Wp + 4, C), float("nan"), dtype=torch.float64)])
+            for q in range(R * Wp):
+                ro, co = divmod(q, Wp)
+                acc = sum(w[:, :, t // 3, t % 3] @ tile[q + (t // 3) * Wp + (t % 3)] for t in range(9))
+                if co < W:                                         # the epilogue compacts the garbage columns away
+                    out[b, :, h0 + ro, co] = acc
+    assert (out - want).abs().max() < 1e-12
