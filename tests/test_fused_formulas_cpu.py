@@ -275,3 +275,27 @@ def test_haloed_tile_conv_index_math():
                 if co < W:                                         # the epilogue compacts the garbage columns away
                     out[b, :, h0 + ro, co] = acc
     assert (out - want).abs().max() < 1e-12
+
+
+def test_stem_weight_gradient_in_packed_layout():
+    """cotb200_stem7x7s2_wgrad_bf16 accumulates  dWm[n, a*64 + j] = sum_px dY[px, n] * window_a(px)[j]  over the space-to-depth image;
+    cotnet_b200.tc.unpack_stem_weight_grad maps it back to [N, 3, 7, 7].  Restated in torch fp64 == conv2d weight gradient."""
+    from cotnet_b200 import tc
+    torch.manual_seed(6)
+    F = torch.nn.functional
+    B, H, W, N = 2, 8, 12, 8
+    x = torch.randn(B, 3, H, W, dtype=torch.float64)
+    dy = torch.randn(B, N, H // 2, W // 2, dtype=torch.float64)
+    want = torch.nn.grad.conv2d_weight(x, (N, 3, 7, 7), dy, stride=2, padding=3)
+    Hh, Wh = H // 2, W // 2
+    P = torch.zeros(B, Hh, Wh + 4, 16, dtype=torch.float64)
+    P[:, :, 2:Wh + 2, :12] = x.view(B, 3, Hh, 2, Wh, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, Hh, Wh, 12)
+    Pp = F.pad(P, (0, 0, 0, 0, 2, 2))                              # s2d rows -2, -1, Hh, Hh+1 are zero (TMA out-of-bounds fill)
+    dwm = torch.zeros(N, 256, dtype=torch.float64)
+    dyr = dy.permute(0, 2, 3, 1).reshape(-1, N)                    # [px, N]
+    for a in range(4):
+        rows = Pp[:, a:a + Hh]
+        win = torch.stack([rows[:, :, k:k + Wh] for k in range(4)], dim=3).reshape(-1, 64)      # [px, 64]
+        dwm[:, a * 64:(a + 1) * 64] = dyr.t() @ win
+    got = tc.unpack_stem_weight_grad(dwm)
+    assert got.shape == want.shape and (got - want).abs().max() < 1e-10
